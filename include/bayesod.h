@@ -1,0 +1,211 @@
+/*
+ * bayesod.h — C ABI of the B200-native BayesOD post-head path.
+ *
+ * The reference (asharakeh/bayes-od-rc) has no FFI of its own: the boundary it
+ * offers is the Python pair
+ *     inference_utils.bayes_od_inference   (src/retina_net/experiments/inference_utils.py:13-217)
+ *     inference_utils.bayes_od_clustering  (src/retina_net/experiments/inference_utils.py:285-364)
+ * piped into each other by run_inference.py:137-149.  This header declares the
+ * entry points a ctypes binding for that pair needs; every
+ * function notes which reference lines it stands in for.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; device pointers are CUDA global-memory
+ *     addresses (fp32, row-major, contiguous), owned by the caller, read-only.
+ *   - every function returns 0 (BOD_OK) or a negative bod_status; the message of
+ *     the last failure on a context is available through bod_last_error().
+ *   - a bod_ctx is bound to one device and owns its workspace; contexts are
+ *     independent (one per GPU / per pipeline slot), a single context is not
+ *     thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device bod_create fails.
+ */
+#ifndef BAYESOD_H
+#define BAYESOD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOD_ABI_VERSION 3
+
+typedef enum bod_status {
+    BOD_OK            = 0,
+    BOD_ERR_INVALID   = -1, /* bad argument / unsupported configuration          */
+    BOD_ERR_CUDA      = -2, /* a CUDA runtime call failed (see bod_last_error)   */
+    BOD_ERR_NOMEM     = -3, /* workspace allocation failed                       */
+    BOD_ERR_STATE     = -4, /* call order violated (fetch before run, ...)       */
+    BOD_ERR_OVERFLOW  = -5  /* an image produced more survivors than max_survivors */
+} bod_status;
+
+/* cov_layout — how `anchors_box_covar_predictions` is handed over
+ * (retinanet_model.py:103-112) */
+#define BOD_COV_NONE    0 /* key absent: aleatoric term = 0 (inference_utils.py:83-84) */
+#define BOD_COV_FULL16  1 /* [B,N,A,4,4] after tfp.math.fill_triangular              */
+#define BOD_COV_PACKED10 2 /* [B,N,A,10] raw head output, fill_triangular order      */
+
+#define BOD_PRIOR_NONE 0
+#define BOD_DIRICHLET_NON_INFORMATIVE 1 /* retinanet_bdd.yaml:135 */
+#define BOD_GAUSSIAN_ISOTROPIC 1        /* retinanet_bdd.yaml:138 */
+
+#define BOD_RANK_SCORE 0          /* inference_utils.py:202 */
+#define BOD_RANK_JOINT_ENTROPY 1  /* inference_utils.py:169-200 */
+
+#define BOD_ANCHORS_TENSOR 0     /* anchors passed as [A,4] (v,u,h,w) */
+#define BOD_ANCHORS_GENERATE 1   /* FPN anchors regenerated in-kernel from (im_h, im_w) */
+
+/* Everything run_inference.py:25-29 reads from testing_config, as a plain
+ * struct, plus the shapes and the extension knobs of SURVEY.md §8(d). */
+typedef struct bod_config {
+    int32_t  B;                  /* images per call (the reference is B=1: run_inference.py:68) */
+    int32_t  N;                  /* mc_dropout_samples (retinanet_bdd.yaml:68)            */
+    int32_t  A;                  /* anchors per image                                      */
+    int32_t  K;                  /* logits per anchor = classes + background (last)        */
+    int32_t  cov_layout;         /* BOD_COV_*                                              */
+    int32_t  use_full_covar;     /* testing_config.use_full_covar                          */
+    int32_t  dirichlet_prior;    /* bayes_od_config.dirichlet_prior.type                   */
+    int32_t  gaussian_prior;     /* bayes_od_config.gaussian_prior.type                    */
+    float    isotropic_variance; /* bayes_od_config.gaussian_prior.isotropic_variance      */
+    int32_t  ranking_method;     /* bayes_od_config.ranking_method                         */
+    int32_t  max_output_size;    /* nms_config.max_output_size (<= 256)                    */
+    float    iou_threshold;      /* nms_config.iou_threshold; also the affinity threshold
+                                    of bayes_od_clustering (run_inference.py:149)          */
+    float    soft_nms_sigma;     /* nms_config.soft_nms_sigma                              */
+    float    scale_v, scale_u;   /* KITTI rescale orig/resized (inference_utils.py:147-167);
+                                    1,1 elsewhere                                          */
+    float    cov_calibration;    /* the literal 70 of inference_utils.py:361               */
+    int32_t  num_draws;          /* the literal 30 of inference_utils.py:42                */
+    uint64_t seed;               /* Philox key; used only when counts == NULL              */
+    uint32_t image_id_base;      /* global id of image 0 of this context's shard: RNG
+                                    counters are keyed by global image id, so results do
+                                    not depend on how a batch is sharded over GPUs        */
+    float    score_threshold;    /* EXTENSION (default -INFINITY = off)                    */
+    int32_t  pre_nms_top_k;      /* EXTENSION (default 0 = off)                            */
+    int32_t  anchor_mode;        /* BOD_ANCHORS_*                                          */
+    int32_t  im_h, im_w;         /* image shape for BOD_ANCHORS_GENERATE                   */
+    int32_t  max_survivors;      /* per-image survivor capacity; 0 => A                    */
+    int32_t  emit_probs;         /* keep the [B,A,K] mean class probabilities (parity)     */
+} bod_config;
+
+typedef struct bod_ctx bod_ctx;
+
+/* Results of bayes_od_clustering for the whole batch, padded to
+ * Dmax = max_output_size rows per image (rows >= num_dets[b] are zero).
+ * Row d of image b corresponds to nms_indices[b][d] (inference_utils.py:312).
+ * Host pointers, caller-allocated (pinned memory makes the copies async);
+ * NULL members are skipped. */
+typedef struct bod_host_results {
+    int32_t* num_dets;          /* [B]          D                                         */
+    int32_t* num_survivors;     /* [B]          S                                         */
+    float*   means;             /* [B,Dmax,4]   final_box_means (v,u,h,w)                 */
+    float*   covs;              /* [B,Dmax,16]  final_box_covs, already x cov_calibration */
+    float*   cat_param;         /* [B,Dmax,K]   final_box_class_scores                    */
+    float*   cat_count;         /* [B,Dmax,K]   final_box_class_counts                    */
+    int32_t* nms_indices;       /* [B,Dmax]     survivor rank of each centre              */
+    int32_t* centre_anchor_idx; /* [B,Dmax]     original anchor index of each centre      */
+    float*   centre_scores;     /* [B,Dmax]     soft-NMS score at selection time          */
+} bod_host_results;
+
+/* The same blocks as device pointers (valid until the next bod_run on ctx),
+ * for consumers that stay on the GPU (e.g. an NCCL all-gather of detections). */
+typedef struct bod_device_results {
+    const int32_t* num_dets;
+    const int32_t* num_survivors;
+    const float*   means;
+    const float*   covs;
+    const float*   cat_param;
+    const float*   cat_count;
+    const int32_t* nms_indices;
+    const int32_t* centre_anchor_idx;
+    const float*   centre_scores;
+} bod_device_results;
+
+/* Per-image intermediates of bayes_od_inference, exposed for parity tests and
+ * for the drop-in's five return values (inference_utils.py:217).  Host
+ * pointers, each sized for `capacity` survivors; NULL members are skipped. */
+typedef struct bod_host_survivors {
+    int32_t  capacity;       /* in:  rows available in the arrays below                  */
+    int32_t  count;          /* out: S                                                   */
+    int32_t* anchor_idx;     /* [S]     kept anchor indices, ascending (boolean_mask)    */
+    float*   counts;         /* [S,K]   dirichlit_posterior_count  (:89-94)              */
+    float*   means;          /* [S,4]   gaussian_posterior_means   (:141-145,160)        */
+    float*   covs;           /* [S,16]  gaussian_posterior_covs    (:129,162)            */
+    float*   scores;         /* [S]     ranking_scores             (:169-202)            */
+    float*   corners;        /* [S,4]   predicted_boxes_corners    (:204)                */
+} bod_host_survivors;
+
+int         bod_abi_version(void);
+const char* bod_status_string(int status);
+
+/* Allocate a context + workspace on `device` for the given shapes/config. */
+int  bod_create(bod_ctx** out, int device, const bod_config* cfg);
+void bod_destroy(bod_ctx* ctx);
+const char* bod_last_error(const bod_ctx* ctx);
+/* Bytes of device workspace owned by the context. */
+int64_t bod_workspace_bytes(const bod_ctx* ctx);
+
+/*
+ * The hot path: inference_utils.py:25-217 (minus the model call) followed by
+ * bayes_od_clustering (:285-364) for B images, entirely on the GPU,
+ * asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).
+ *   cls     [B,N,A,K]            anchors_class_predictions (logits)
+ *   box     [B,N,A,4]            anchors_box_predictions (deltas)
+ *   cov     [B,N,A,16|10] / NULL anchors_box_covar_predictions (see cov_layout)
+ *   anchors [A,4] (v,u,h,w), shared by the batch / NULL when anchor_mode=GENERATE
+ *   counts  [B,A,K] categorical sample counts to inject (parity mode: replaces the
+ *           unseeded tfp Categorical.sample(30) of :37-46) / NULL = in-kernel
+ *           Philox4x32-10 sampler keyed by (seed, global image id, anchor)
+ */
+int bod_run(bod_ctx* ctx, const float* cls, const float* box, const float* cov,
+            const float* anchors, const float* counts, void* cuda_stream);
+
+/* Same call with HOST buffers (what a caller holding numpy arrays makes):
+ * stages the inputs host->device in image chunks overlapped with compute,
+ * runs the path and copies the padded results back into `out`.  Synchronous. */
+int bod_run_host(bod_ctx* ctx, const float* cls, const float* box, const float* cov,
+                 const float* anchors, const float* counts, bod_host_results* out);
+
+/* Second half of the drop-in on its own: bayes_od_clustering(...) for ONE image
+ * from host arrays (inference_utils.py:285-364).  `affinity` is the [S,S]
+ * matrix of the reference signature (only the D centre columns are read, :316). */
+int bod_cluster_host(bod_ctx* ctx, int32_t S, const float* counts /*[S,K]*/,
+                     const float* means /*[S,4]*/, const float* covs /*[S,16]*/,
+                     int32_t D, const int32_t* centres /*[D]*/,
+                     const float* affinity /*[S,S]*/, float affinity_threshold,
+                     bod_host_results* out /* B=1 blocks */);
+
+/* Wait for the last bod_run and copy the padded result blocks to the host. */
+int bod_fetch(bod_ctx* ctx, bod_host_results* out);
+/* Device pointers of the padded result blocks (no sync, no copy). */
+int bod_device_results_of(bod_ctx* ctx, bod_device_results* out);
+
+/* Parity / drop-in intermediates of image `b` of the last run (sync + D2H). */
+int bod_fetch_survivors(bod_ctx* ctx, int32_t b, bod_host_survivors* out);
+/* Cluster membership bitmask of image b: row d (centre d in NMS order) holds
+ * ceil(S/32) words, bit s set <=> bbox_iou_vuvu(survivor s, centre d) > thr
+ * (inference_utils.py:316).  `words_per_row` is the row pitch of `mask`. */
+int bod_fetch_members(bod_ctx* ctx, int32_t b, uint32_t* mask, int32_t words_per_row);
+/* [A,K] mean class probabilities of image b (needs cfg.emit_probs). */
+int bod_fetch_probs(bod_ctx* ctx, int32_t b, float* probs);
+/* [A,K] sampled categorical counts of image b as the Philox sampler drew them
+ * (needs cfg.emit_probs and counts == NULL in the last run). */
+int bod_fetch_sampled_counts(bod_ctx* ctx, int32_t b, float* counts);
+
+/* Device-time of the last run per stage in milliseconds (events recorded on the
+ * run's stream): [0]=moments/filter, [1]=scan, [2]=posterior, [3]=soft-NMS,
+ * [4]=fusion, [5]=total.  Syncs on the run. */
+int bod_last_stage_ms(bod_ctx* ctx, float ms[6]);
+/* Number of kernels the last bod_run launched. */
+int bod_last_launch_count(const bod_ctx* ctx);
+
+/* FPN anchors exactly as fpn_anchor_generator.py:21-59 produces them for levels
+ * 3..7, 3 aspect ratios x 3 scales, concatenated P3->P7
+ * (bdd_dataset_handler.py:161-186).  Writes [A,4] to device memory `anchors`
+ * and returns A (or a negative status).  Pass anchors=NULL to query A. */
+int bod_generate_anchors(int32_t im_h, int32_t im_w, float* anchors_dev, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYESOD_H */

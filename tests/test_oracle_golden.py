@@ -1,0 +1,103 @@
+"""CPU: pin the C oracle against the golden fixtures, i.e. against the
+reference's own source files executed over the numpy TF shim
+(tests/golden/make_golden.py).  Index outputs must be bit-exact; floating
+outputs within rtol 1e-4 / atol 1e-5 (north_star), with binary64 adjudication
+for ill-conditioned elements."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import (adjudicated_close, check_categorical_merge, golden_cases, load_golden, oracle_config_of,
+                     within_tol)
+
+CASES = golden_cases()
+
+
+def test_fixtures_present():
+    assert len(CASES) >= 10
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_anchors_bit_exact(name):
+    g = load_golden(name)
+    h, w = g["meta"]["image_shape"]
+    mine = oracle.generate_anchors(h, w)
+    assert mine.shape == g["anchors"].shape
+    assert np.array_equal(mine.view(np.uint32), g["anchors"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_inference_half(name):
+    """bayes_od_inference outputs (inference_utils.py:217)."""
+    g = load_golden(name)
+    cfg = oracle_config_of(g["meta"])
+    r = oracle.run_image(cfg, g["cls"], g["box"], g["cov"] if g["meta"]["has_cov"] else None, g["anchors"], g["counts"])
+    S = len(g["cnt_post"])
+    assert len(r.keep) == S
+    if S == 0:
+        assert len(r.nms_indices) == 0
+        return
+    # counts: small integers + 1/K -> exact
+    assert np.array_equal(r.cnt_post, g["cnt_post"])
+    mu_ref = g["mu_post"][:, :, 0]
+    assert within_tol(r.mu_post, mu_ref).all(), np.abs(r.mu_post - mu_ref).max()
+    r64 = oracle.run_image(cfg, g["cls"], g["box"], g["cov"] if g["meta"]["has_cov"] else None, g["anchors"], g["counts"],
+                           real="f64", force=dict(nms_indices=r.nms_indices, mask=r.mask))
+    ok, frac = adjudicated_close(r.sig_post, g["sig_post"], r64.sig_post)
+    assert ok.all(), (frac, np.abs(r.sig_post - g["sig_post"]).max())
+    assert frac > 0.99
+    # centre selection: bit-exact, in order
+    assert np.array_equal(r.nms_indices, g["nms_indices"]), (r.nms_indices[:20], g["nms_indices"][:20])
+    # membership of every cluster: bit-exact
+    mem = oracle.mask_to_bool(r.mask, S)                     # [D,S]
+    ref_mem = (g["iou_cols"] > cfg.iou_threshold).T            # iou[:, centre] > thr (:316)
+    assert np.array_equal(mem, ref_mem)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_clustering_half(name):
+    """bayes_od_clustering outputs (inference_utils.py:364)."""
+    g = load_golden(name)
+    if "final_means" not in g:
+        pytest.skip("no survivors in this fixture")
+    cfg = oracle_config_of(g["meta"])
+    cov = g["cov"] if g["meta"]["has_cov"] else None
+    r = oracle.run_image(cfg, g["cls"], g["box"], cov, g["anchors"], g["counts"])
+    r64 = oracle.run_image(cfg, g["cls"], g["box"], cov, g["anchors"], g["counts"], real="f64",
+                           force=dict(nms_indices=r.nms_indices, mask=r.mask))
+    assert r.empty_clusters == 0
+    assert within_tol(r.final_means, g["final_means"][:, :, 0]).all()
+    ok, frac = adjudicated_close(r.final_covs, g["final_covs"], r64.final_covs)
+    assert ok.all() and frac > 0.99, frac
+    mem = oracle.mask_to_bool(r.mask, len(r.keep))
+    n_plain, n_tied = check_categorical_merge(g, r.nms_indices, mem, r.extra["chosen"], r.final_scores, r.final_counts)
+    assert n_plain > 0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_stage_isolated_nms_and_clustering(name):
+    """Feed the GOLDEN posterior (means, covs, counts) to the oracle's NMS +
+    clustering: removes upstream float noise, so everything index-like is exact."""
+    g = load_golden(name)
+    S = len(g["cnt_post"])
+    if S == 0:
+        pytest.skip("no survivors")
+    cfg = oracle_config_of(g["meta"])
+    mu = g["mu_post"][:, :, 0]
+    corners = np.stack([mu[:, 0] - mu[:, 2] / np.float32(2), mu[:, 1] - mu[:, 3] / np.float32(2),
+                        mu[:, 0] + mu[:, 2] / np.float32(2), mu[:, 1] + mu[:, 3] / np.float32(2)], 1).astype(np.float32)
+    if cfg.ranking_method == "score":
+        p = g["cnt_post"] / g["cnt_post"].sum(1, keepdims=True)
+        score = p.max(1).astype(np.float32)
+        sel, _ = oracle.nms_v5(corners, score, cfg.max_output_size, cfg.iou_threshold, -np.inf, cfg.soft_nms_sigma)
+        assert np.array_equal(sel, g["nms_indices"])
+    sel = g["nms_indices"]
+    mask = oracle.membership(corners, sel, cfg.iou_threshold)
+    assert np.array_equal(oracle.mask_to_bool(mask, S), (g["iou_cols"] > cfg.iou_threshold).T)
+    fs, fm, fc, fn, mem, empty = oracle.clustering(g["cnt_post"], mu, g["sig_post"], sel, mask, 70.0)
+    assert empty == 0
+    assert within_tol(fm, g["final_means"][:, :, 0]).all()
+    check_categorical_merge(g, sel, oracle.mask_to_bool(mask, S), oracle.clustering.last_chosen, fs, fn)
+    fs64, fm64, fc64, *_ = oracle.clustering(g["cnt_post"], mu, g["sig_post"], sel, mask, 70.0, real="f64")
+    ok, frac = adjudicated_close(fc, g["final_covs"], fc64)
+    assert ok.all() and frac > 0.99
