@@ -1,0 +1,562 @@
+// bod_api.cu — the C ABI of include/bayesod.h: context, workspace, launch
+// sequence of the stage kernels, result transfer.  No CPU fallback anywhere:
+// without a CUDA device bod_create fails with BOD_ERR_CUDA.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/bayesod.h"
+#include "bod_common.cuh"
+#include "bod_kernels.h"
+
+using namespace bod;
+
+struct bod_ctx {
+    bod_config cfg;
+    int device = 0;
+    int tiles = 0, capacity = 0, words = 0, Dmax = 0;
+    char err[512] = {0};
+    // one slab of device memory, carved up below
+    unsigned char* slab = nullptr;
+    size_t slab_bytes = 0;
+    // K1 outputs
+    int32_t* slot_anchor = nullptr; float* slot_counts = nullptr; int32_t* tile_count = nullptr;
+    int32_t* tile_off = nullptr; int32_t* num_survivors = nullptr; int32_t* status = nullptr;
+    float* probs = nullptr; float* sampled = nullptr;
+    // K2 outputs
+    int32_t* surv_anchor = nullptr; float* cnt_post = nullptr; float* mu_post = nullptr; float* sig_post = nullptr;
+    float* score = nullptr; float4* corners = nullptr; float* info = nullptr;
+    // K3 scratch + outputs
+    float* stale = nullptr; float* cur = nullptr; int32_t* begin = nullptr; uint32_t* pend = nullptr;
+    int32_t* nms_idx = nullptr; float* nms_score = nullptr; int32_t* centre_anchor = nullptr; int32_t* num_dets = nullptr;
+    uint32_t* member = nullptr;
+    // K4 outputs
+    float* out_means = nullptr; float* out_covs = nullptr; float* out_param = nullptr; float* out_count = nullptr;
+    // device staging of host inputs (bod_run_host), allocated on first use
+    float* in_cls = nullptr; float* in_box = nullptr; float* in_cov = nullptr; float* in_anchors = nullptr; float* in_counts = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t last_stream = nullptr;
+    // stage-timing events: a ring of the last kEvRing runs, 6 events each
+    static constexpr int kEvRing = 128;
+    cudaEvent_t evring[kEvRing][6] = {{nullptr}};
+    cudaEvent_t* ev = nullptr;            // event set of the run being issued
+    long long runs_recorded = 0, runs_reported = 0;
+    cudaEvent_t ev_copy[4] = {nullptr};
+    bool ran = false, used_sampler = false, timing = true, last_timed = false;
+    int launches = 0;
+};
+
+static int fail(bod_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(c->err, sizeof c->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CU(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, BOD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" int bod_abi_version(void) { return BOD_ABI_VERSION; }
+
+extern "C" const char* bod_status_string(int s) {
+    switch (s) {
+        case BOD_OK: return "ok";
+        case BOD_ERR_INVALID: return "invalid argument or unsupported configuration";
+        case BOD_ERR_CUDA: return "CUDA error";
+        case BOD_ERR_NOMEM: return "out of device memory";
+        case BOD_ERR_STATE: return "call order violated";
+        case BOD_ERR_OVERFLOW: return "more survivors than max_survivors";
+        default: return "unknown status";
+    }
+}
+
+// message of the last failed bod_create on this thread (there is no context to ask)
+static thread_local char create_err[512] = {0};
+extern "C" const char* bod_last_error(const bod_ctx* ctx) { return ctx ? ctx->err : create_err; }
+extern "C" int64_t bod_workspace_bytes(const bod_ctx* ctx) { return ctx ? (int64_t)ctx->slab_bytes : 0; }
+extern "C" int bod_last_launch_count(const bod_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static int cov_width(int layout) { return layout == BOD_COV_FULL16 ? 16 : (layout == BOD_COV_PACKED10 ? 10 : 0); }
+
+extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
+    if (!out || !cfg) return BOD_ERR_INVALID;
+    *out = nullptr;
+    bod_ctx* c = new (std::nothrow) bod_ctx();
+    if (!c) return BOD_ERR_NOMEM;
+    c->cfg = *cfg;
+    c->device = device;
+    auto bad = [&](const char* msg) { snprintf(create_err, sizeof create_err, "%s", msg); delete c; return BOD_ERR_INVALID; };
+    if (cfg->B < 1 || cfg->B > 128) return bad("B must be in [1,128]");
+    if (cfg->N < 2) return bad("N (mc_dropout_samples) must be >= 2: the sample covariance divides by N-1");
+    if (cfg->A < 1) return bad("A must be positive");
+    if (!k1_supports(cfg->K)) return bad("unsupported K (classes + background)");
+    if (cfg->max_output_size < 1 || cfg->max_output_size > kMaxOut) return bad("max_output_size must be in [1,256]");
+    if (cfg->cov_layout < 0 || cfg->cov_layout > 2) return bad("bad cov_layout");
+    if (!(cfg->iou_threshold >= 0.0f)) return bad("iou_threshold must be >= 0");
+    if (!(cfg->soft_nms_sigma >= 0.0f)) return bad("soft_nms_sigma must be >= 0");
+    if (cfg->num_draws < 1 || cfg->num_draws > 4096) return bad("num_draws must be in [1,4096]");
+    if (cfg->pre_nms_top_k != 0 || cfg->score_threshold > -INFINITY) return bad("score_threshold / pre_nms_top_k extensions are not built yet");
+    if (cfg->anchor_mode == BOD_ANCHORS_GENERATE && count_anchors(cfg->im_h, cfg->im_w) != cfg->A)
+        return bad("anchor_mode=GENERATE: A does not match the FPN anchor count of (im_h, im_w)");
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { snprintf(create_err, sizeof create_err, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); delete c; return BOD_ERR_CUDA; }
+
+    const int B = cfg->B, A = cfg->A, K = cfg->K;
+    c->tiles = (A + kTileAnchors - 1) / kTileAnchors;
+    c->capacity = (cfg->max_survivors > 0 && cfg->max_survivors < A) ? cfg->max_survivors : A;
+    c->capacity = (c->capacity + 31) & ~31;
+    c->words = c->capacity / 32;
+    c->Dmax = cfg->max_output_size;
+    const size_t cap = (size_t)c->capacity, D = (size_t)c->Dmax;
+
+    // carve the slab
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    struct Piece { void** p; size_t o; };
+    std::vector<Piece> pieces;
+#define TAKE(ptr, bytes) pieces.push_back(Piece{reinterpret_cast<void**>(&c->ptr), take(bytes)})
+    TAKE(slot_anchor, (size_t)B * A * 4);
+    TAKE(slot_counts, (size_t)B * A * K * 4);
+    TAKE(tile_count, (size_t)B * c->tiles * 4);
+    TAKE(tile_off, (size_t)B * (c->tiles + 1) * 4);
+    TAKE(num_survivors, (size_t)B * 4);
+    TAKE(status, 256);
+    if (cfg->emit_probs) { TAKE(probs, (size_t)B * A * K * 4); TAKE(sampled, (size_t)B * A * K * 4); }
+    TAKE(surv_anchor, B * cap * 4);
+    TAKE(cnt_post, B * cap * K * 4);
+    TAKE(mu_post, B * cap * 16);
+    TAKE(sig_post, B * cap * 64);
+    TAKE(score, B * cap * 4);
+    TAKE(corners, B * cap * 16);
+    TAKE(info, B * cap * 8);
+    TAKE(stale, B * cap * 4);
+    TAKE(cur, B * cap * 4);
+    TAKE(begin, B * cap * 4);
+    TAKE(pend, B * cap * kMaskWords * 4);
+    TAKE(nms_idx, B * D * 4);
+    TAKE(nms_score, B * D * 4);
+    TAKE(centre_anchor, B * D * 4);
+    TAKE(num_dets, (size_t)B * 4);
+    TAKE(member, B * D * c->words * 4);
+    TAKE(out_means, B * D * 16);
+    TAKE(out_covs, B * D * 64);
+    TAKE(out_param, B * D * K * 4);
+    TAKE(out_count, B * D * K * 4);
+#undef TAKE
+    c->slab_bytes = off;
+    e = cudaMalloc(&c->slab, off);
+    if (e != cudaSuccess) {
+        snprintf(create_err, sizeof create_err, "cudaMalloc(%zu): %s", off, cudaGetErrorString(e));
+        cudaGetLastError(); delete c; return BOD_ERR_NOMEM;
+    }
+    for (auto& p : pieces) *p.p = c->slab + p.o;
+    cudaMemset(c->slab, 0, off);
+    cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (auto& set : c->evring) for (auto& ev : set) cudaEventCreate(&ev);
+    for (auto& ev : c->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { snprintf(create_err, sizeof create_err, "init: %s", cudaGetErrorString(e)); bod_destroy(c); return BOD_ERR_CUDA; }
+    *out = c;
+    return BOD_OK;
+}
+
+extern "C" void bod_destroy(bod_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->slab) cudaFree(c->slab);
+    for (float* p : {c->in_cls, c->in_box, c->in_cov, c->in_anchors, c->in_counts}) if (p) cudaFree(p);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto& set : c->evring) for (auto& ev : set) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
+    delete c;
+}
+
+// Launch the stage kernels for images [b0, b0+nb) of the context's batch.
+static int run_range(bod_ctx* c, int b0, int nb, const float* cls, const float* box, const float* cov,
+                     const float* anchors, const float* counts, cudaStream_t st, bool record) {
+    const bod_config& g = c->cfg;
+    const size_t A = g.A, K = g.K, N = g.N, cap = c->capacity, D = c->Dmax;
+    const int cw = cov_width(g.cov_layout);
+
+    if (record) CU(c, cudaEventRecord(c->ev[0], st));
+    K1Args k1{};
+    k1.cls = cls; k1.counts_in = counts;
+    k1.probs_out = c->probs ? c->probs + b0 * A * K : nullptr;
+    k1.sampled_out = (c->sampled && !counts) ? c->sampled + b0 * A * K : nullptr;
+    k1.slot_anchor = c->slot_anchor + b0 * A; k1.slot_counts = c->slot_counts + b0 * A * K;
+    k1.tile_count = c->tile_count + (size_t)b0 * c->tiles;
+    k1.B = nb; k1.N = g.N; k1.A = g.A; k1.K = g.K; k1.tiles = c->tiles;
+    k1.num_draws = g.num_draws; k1.seed = g.seed; k1.image_id_base = g.image_id_base + (uint32_t)b0;
+    CU(c, launch_k1(k1, st));
+    if (record) CU(c, cudaEventRecord(c->ev[1], st));
+
+    ScanArgs sc{};
+    sc.tile_count = k1.tile_count; sc.tile_off = c->tile_off + (size_t)b0 * (c->tiles + 1);
+    sc.num_survivors = c->num_survivors + b0; sc.status = c->status;
+    sc.B = nb; sc.tiles = c->tiles; sc.capacity = c->capacity;
+    CU(c, launch_scan(sc, st));
+    if (record) CU(c, cudaEventRecord(c->ev[2], st));
+
+    K2Args k2{};
+    k2.box = box; k2.cov = cw ? cov : nullptr; k2.anchors = anchors;
+    k2.slot_anchor = k1.slot_anchor; k2.slot_counts = k1.slot_counts; k2.tile_off = sc.tile_off;
+    k2.num_survivors = sc.num_survivors;
+    k2.surv_anchor = c->surv_anchor + b0 * cap; k2.cnt_post = c->cnt_post + b0 * cap * K;
+    k2.mu_post = c->mu_post + b0 * cap * 4; k2.sig_post = c->sig_post + b0 * cap * 16;
+    k2.score = c->score + b0 * cap; k2.corners = c->corners + b0 * cap; k2.info = c->info + b0 * cap * 2;
+    k2.B = nb; k2.N = g.N; k2.A = g.A; k2.K = g.K; k2.tiles = c->tiles; k2.capacity = c->capacity;
+    k2.cov_layout = g.cov_layout; k2.use_full_covar = g.use_full_covar;
+    k2.dirichlet_prior = g.dirichlet_prior; k2.gaussian_prior = g.gaussian_prior;
+    // joint_entropy needs both priors (inference_utils.py:169-170), else falls back to 'score'
+    k2.ranking_method = (g.ranking_method == BOD_RANK_JOINT_ENTROPY && g.gaussian_prior != BOD_PRIOR_NONE &&
+                         g.dirichlet_prior != BOD_PRIOR_NONE) ? 1 : 0;
+    k2.isotropic_variance = g.isotropic_variance; k2.scale_v = g.scale_v; k2.scale_u = g.scale_u;
+    k2.anchor_mode = g.anchor_mode; k2.im_h = g.im_h; k2.im_w = g.im_w;
+    CU(c, launch_k2(k2, st));
+    int launches = 3;
+    if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, st)); ++launches; }
+    if (record) CU(c, cudaEventRecord(c->ev[3], st));
+
+    K3Args k3{};
+    k3.corners = k2.corners; k3.score = k2.score; k3.num_survivors = sc.num_survivors; k3.surv_anchor = k2.surv_anchor;
+    k3.stale = c->stale + b0 * cap; k3.cur = c->cur + b0 * cap; k3.begin = c->begin + b0 * cap;
+    k3.pend = c->pend + b0 * cap * kMaskWords;
+    k3.nms_idx = c->nms_idx + b0 * D; k3.nms_score = c->nms_score + b0 * D; k3.centre_anchor = c->centre_anchor + b0 * D;
+    k3.num_dets = c->num_dets + b0; k3.member = c->member + b0 * D * c->words;
+    k3.B = nb; k3.capacity = c->capacity; k3.Dmax = c->Dmax; k3.words = c->words;
+    k3.iou_threshold = g.iou_threshold; k3.soft_nms_sigma = g.soft_nms_sigma;
+    CU(c, launch_k3(k3, st));
+    if (record) CU(c, cudaEventRecord(c->ev[4], st));
+
+    K4Args k4{};
+    k4.cnt_post = k2.cnt_post; k4.mu_post = k2.mu_post; k4.sig_post = k2.sig_post; k4.num_survivors = sc.num_survivors;
+    k4.nms_idx = k3.nms_idx; k4.num_dets = k3.num_dets; k4.member = k3.member;
+    k4.out_means = c->out_means + b0 * D * 4; k4.out_covs = c->out_covs + b0 * D * 16;
+    k4.out_param = c->out_param + b0 * D * K; k4.out_count = c->out_count + b0 * D * K;
+    k4.B = nb; k4.K = g.K; k4.capacity = c->capacity; k4.Dmax = c->Dmax; k4.words = c->words;
+    k4.calibration = g.cov_calibration;
+    CU(c, launch_k4(k4, st));
+    if (record) CU(c, cudaEventRecord(c->ev[5], st));
+    c->launches += launches + 2;
+    return BOD_OK;
+}
+
+// padded output rows beyond num_dets must read as zero / -1
+static int clear_outputs(bod_ctx* c, cudaStream_t st) {
+    const size_t B = c->cfg.B, D = c->Dmax, K = c->cfg.K;
+    CU(c, cudaMemsetAsync(c->out_means, 0, B * D * 16, st));
+    CU(c, cudaMemsetAsync(c->out_covs, 0, B * D * 64, st));
+    CU(c, cudaMemsetAsync(c->out_param, 0, B * D * K * 4, st));
+    CU(c, cudaMemsetAsync(c->out_count, 0, B * D * K * 4, st));
+    CU(c, cudaMemsetAsync(c->nms_idx, 0xFF, B * D * 4, st));
+    CU(c, cudaMemsetAsync(c->centre_anchor, 0xFF, B * D * 4, st));
+    CU(c, cudaMemsetAsync(c->nms_score, 0, B * D * 4, st));
+    CU(c, cudaMemsetAsync(c->status, 0, 4, st));
+    return BOD_OK;
+}
+
+static int check_inputs(bod_ctx* c, const float* cls, const float* box, const float* cov, const float* anchors) {
+    if (!c) return BOD_ERR_INVALID;
+    if (!cls || !box) return fail(c, BOD_ERR_INVALID, "cls and box must not be NULL");
+    if (c->cfg.cov_layout != BOD_COV_NONE && !cov) return fail(c, BOD_ERR_INVALID, "cov is NULL but cov_layout != NONE");
+    if (c->cfg.anchor_mode == BOD_ANCHORS_TENSOR && !anchors) return fail(c, BOD_ERR_INVALID, "anchors is NULL but anchor_mode = TENSOR");
+    return BOD_OK;
+}
+
+extern "C" int bod_run(bod_ctx* c, const float* cls, const float* box, const float* cov, const float* anchors,
+                       const float* counts, void* cuda_stream) {
+    int rc = check_inputs(c, cls, box, cov, anchors);
+    if (rc) return rc;
+    if ((reinterpret_cast<uintptr_t>(box) & 15u) || (cov && (reinterpret_cast<uintptr_t>(cov) & 15u)) ||
+        (anchors && (reinterpret_cast<uintptr_t>(anchors) & 15u)))
+        return fail(c, BOD_ERR_INVALID, "box / cov / anchors must be 16-byte aligned");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    c->launches = 0;
+    rc = clear_outputs(c, st);
+    if (rc) return rc;
+    c->ev = c->evring[c->runs_recorded % bod_ctx::kEvRing];
+    rc = run_range(c, 0, c->cfg.B, cls, box, cov, anchors, counts, st, c->timing);
+    if (rc) return rc;
+    if (c->timing) ++c->runs_recorded;
+    c->last_timed = c->timing;
+    c->last_stream = st; c->ran = true; c->used_sampler = (counts == nullptr);
+    return BOD_OK;
+}
+
+static int sync_and_status(bod_ctx* c) {
+    if (!c->ran) return fail(c, BOD_ERR_STATE, "no bod_run has been issued on this context");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->last_stream));
+    int32_t status = 0;
+    CU(c, cudaMemcpy(&status, c->status, 4, cudaMemcpyDeviceToHost));
+    if (status & 1) return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
+    return BOD_OK;
+}
+
+static int copy_results(bod_ctx* c, bod_host_results* out, cudaStream_t st) {
+    const size_t B = c->cfg.B, D = c->Dmax, K = c->cfg.K;
+#define D2H(dst, src, bytes) if (out->dst) CU(c, cudaMemcpyAsync(out->dst, c->src, (bytes), cudaMemcpyDeviceToHost, st))
+    D2H(num_dets, num_dets, B * 4);
+    D2H(num_survivors, num_survivors, B * 4);
+    D2H(means, out_means, B * D * 16);
+    D2H(covs, out_covs, B * D * 64);
+    D2H(cat_param, out_param, B * D * K * 4);
+    D2H(cat_count, out_count, B * D * K * 4);
+    D2H(nms_indices, nms_idx, B * D * 4);
+    D2H(centre_anchor_idx, centre_anchor, B * D * 4);
+    D2H(centre_scores, nms_score, B * D * 4);
+#undef D2H
+    return BOD_OK;
+}
+
+extern "C" int bod_fetch(bod_ctx* c, bod_host_results* out) {
+    if (!c || !out) return BOD_ERR_INVALID;
+    int rc = sync_and_status(c);
+    if (rc) return rc;
+    rc = copy_results(c, out, c->last_stream);
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->last_stream));
+    return BOD_OK;
+}
+
+extern "C" int bod_device_results_of(bod_ctx* c, bod_device_results* out) {
+    if (!c || !out) return BOD_ERR_INVALID;
+    out->num_dets = c->num_dets; out->num_survivors = c->num_survivors;
+    out->means = c->out_means; out->covs = c->out_covs; out->cat_param = c->out_param; out->cat_count = c->out_count;
+    out->nms_indices = c->nms_idx; out->centre_anchor_idx = c->centre_anchor; out->centre_scores = c->nms_score;
+    return BOD_OK;
+}
+
+extern "C" int bod_fetch_survivors(bod_ctx* c, int32_t b, bod_host_survivors* out) {
+    if (!c || !out || b < 0 || b >= c->cfg.B) return BOD_ERR_INVALID;
+    int rc = sync_and_status(c);
+    if (rc) return rc;
+    int32_t S = 0;
+    CU(c, cudaMemcpy(&S, c->num_survivors + b, 4, cudaMemcpyDeviceToHost));
+    out->count = S;
+    if (S > out->capacity) return fail(c, BOD_ERR_INVALID, "bod_fetch_survivors: capacity %d < S %d", out->capacity, S);
+    const size_t cap = c->capacity, K = c->cfg.K, s = (size_t)S;
+    if (S == 0) return BOD_OK;
+#define D2H(dst, src, off, bytes) if (out->dst) CU(c, cudaMemcpy(out->dst, c->src + (off), (bytes), cudaMemcpyDeviceToHost))
+    D2H(anchor_idx, surv_anchor, b * cap, s * 4);
+    D2H(counts, cnt_post, b * cap * K, s * K * 4);
+    D2H(means, mu_post, b * cap * 4, s * 16);
+    D2H(covs, sig_post, b * cap * 16, s * 64);
+    D2H(scores, score, b * cap, s * 4);
+    D2H(corners, corners, b * cap, s * 16);
+#undef D2H
+    return BOD_OK;
+}
+
+extern "C" int bod_fetch_members(bod_ctx* c, int32_t b, uint32_t* mask, int32_t words_per_row) {
+    if (!c || !mask || b < 0 || b >= c->cfg.B) return BOD_ERR_INVALID;
+    int rc = sync_and_status(c);
+    if (rc) return rc;
+    int32_t S = 0, D = 0;
+    CU(c, cudaMemcpy(&S, c->num_survivors + b, 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&D, c->num_dets + b, 4, cudaMemcpyDeviceToHost));
+    const int nw = (S + 31) / 32;
+    if (words_per_row < nw) return fail(c, BOD_ERR_INVALID, "bod_fetch_members: words_per_row %d < %d", words_per_row, nw);
+    if (D == 0 || nw == 0) return BOD_OK;
+    CU(c, cudaMemcpy2D(mask, (size_t)words_per_row * 4, c->member + (size_t)b * c->Dmax * c->words, (size_t)c->words * 4,
+                       (size_t)nw * 4, D, cudaMemcpyDeviceToHost));
+    return BOD_OK;
+}
+
+extern "C" int bod_fetch_probs(bod_ctx* c, int32_t b, float* probs) {
+    if (!c || !probs || b < 0 || b >= c->cfg.B) return BOD_ERR_INVALID;
+    if (!c->probs) return fail(c, BOD_ERR_STATE, "context was created without emit_probs");
+    int rc = sync_and_status(c);
+    if (rc) return rc;
+    const size_t n = (size_t)c->cfg.A * c->cfg.K;
+    CU(c, cudaMemcpy(probs, c->probs + b * n, n * 4, cudaMemcpyDeviceToHost));
+    return BOD_OK;
+}
+
+extern "C" int bod_fetch_sampled_counts(bod_ctx* c, int32_t b, float* counts) {
+    if (!c || !counts || b < 0 || b >= c->cfg.B) return BOD_ERR_INVALID;
+    if (!c->sampled) return fail(c, BOD_ERR_STATE, "context was created without emit_probs");
+    if (!c->used_sampler) return fail(c, BOD_ERR_STATE, "last run injected counts; nothing was sampled");
+    int rc = sync_and_status(c);
+    if (rc) return rc;
+    const size_t n = (size_t)c->cfg.A * c->cfg.K;
+    CU(c, cudaMemcpy(counts, c->sampled + b * n, n * 4, cudaMemcpyDeviceToHost));
+    return BOD_OK;
+}
+
+extern "C" int bod_synchronize(bod_ctx* c) {
+    if (!c) return BOD_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    return BOD_OK;
+}
+
+extern "C" int bod_last_stage_ms(bod_ctx* c, float ms[6]) {
+    if (!c || !ms) return BOD_ERR_INVALID;
+    int rc = sync_and_status(c);
+    if (rc) return rc;
+    if (!c->last_timed || c->runs_recorded == 0) return fail(c, BOD_ERR_STATE, "the last run recorded no stage events");
+    cudaEvent_t* ev = c->evring[(c->runs_recorded - 1) % bod_ctx::kEvRing];
+    for (int i = 0; i < 5; ++i) CU(c, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    CU(c, cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
+    return BOD_OK;
+}
+
+extern "C" int bod_set_stage_timing(bod_ctx* c, int enabled) {
+    if (!c) return BOD_ERR_INVALID;
+    c->timing = enabled != 0;
+    return BOD_OK;
+}
+
+extern "C" int bod_stage_ms_accum(bod_ctx* c, float sum_ms[6], int32_t* runs) {
+    if (!c || !sum_ms || !runs) return BOD_ERR_INVALID;
+    for (int i = 0; i < 6; ++i) sum_ms[i] = 0.0f;
+    *runs = 0;
+    if (c->runs_recorded == c->runs_reported) return BOD_OK;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->last_stream));
+    long long first = c->runs_reported;
+    if (c->runs_recorded - first > bod_ctx::kEvRing) first = c->runs_recorded - bod_ctx::kEvRing;
+    for (long long r = first; r < c->runs_recorded; ++r) {
+        cudaEvent_t* ev = c->evring[r % bod_ctx::kEvRing];
+        float ms = 0.0f;
+        for (int i = 0; i < 5; ++i) { CU(c, cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); sum_ms[i] += ms; }
+        CU(c, cudaEventElapsedTime(&ms, ev[0], ev[5])); sum_ms[5] += ms;
+        ++*runs;
+    }
+    c->runs_reported = c->runs_recorded;
+    return BOD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer entry: H2D in image chunks on a copy stream, compute chunk i while
+// chunk i+1 is in flight, D2H of the padded result blocks.
+// ---------------------------------------------------------------------------
+extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, const float* cov, const float* anchors,
+                            const float* counts, bod_host_results* out) {
+    int rc = check_inputs(c, cls, box, cov, anchors);
+    if (rc) return rc;
+    if (!out) return fail(c, BOD_ERR_INVALID, "out is NULL");
+    CU(c, cudaSetDevice(c->device));
+    const bod_config& g = c->cfg;
+    const size_t B = g.B, N = g.N, A = g.A, K = g.K;
+    const size_t cw = cov_width(g.cov_layout);
+    if (!c->in_cls) {
+        CU(c, cudaMalloc(&c->in_cls, B * N * A * K * 4));
+        CU(c, cudaMalloc(&c->in_box, B * N * A * 16));
+        if (cw) CU(c, cudaMalloc(&c->in_cov, B * N * A * cw * 4));
+        CU(c, cudaMalloc(&c->in_anchors, A * 16));
+        CU(c, cudaMalloc(&c->in_counts, B * A * K * 4));
+    }
+    cudaStream_t cs = c->copy_stream, st = c->own_stream;
+    c->launches = 0;
+    rc = clear_outputs(c, st);
+    if (rc) return rc;
+    c->last_timed = false;
+    if (anchors) CU(c, cudaMemcpyAsync(c->in_anchors, anchors, A * 16, cudaMemcpyHostToDevice, cs));
+    // chunks of images: small enough to overlap, large enough to fill the GPU
+    const int chunk = (B >= 8) ? (int)((B + 3) / 4) : (int)B;
+    int nev = 0;
+    for (size_t b0 = 0; b0 < B; b0 += chunk) {
+        const size_t nb = (b0 + chunk <= B) ? chunk : B - b0;
+        CU(c, cudaMemcpyAsync(c->in_cls + b0 * N * A * K, cls + b0 * N * A * K, nb * N * A * K * 4, cudaMemcpyHostToDevice, cs));
+        if (counts) CU(c, cudaMemcpyAsync(c->in_counts + b0 * A * K, counts + b0 * A * K, nb * A * K * 4, cudaMemcpyHostToDevice, cs));
+        CU(c, cudaMemcpyAsync(c->in_box + b0 * N * A * 4, box + b0 * N * A * 4, nb * N * A * 16, cudaMemcpyHostToDevice, cs));
+        if (cw) CU(c, cudaMemcpyAsync(c->in_cov + b0 * N * A * cw, cov + b0 * N * A * cw, nb * N * A * cw * 4, cudaMemcpyHostToDevice, cs));
+        cudaEvent_t ev = c->ev_copy[nev++ & 3];
+        CU(c, cudaEventRecord(ev, cs));
+        CU(c, cudaStreamWaitEvent(st, ev, 0));
+        rc = run_range(c, (int)b0, (int)nb, c->in_cls + b0 * N * A * K, c->in_box + b0 * N * A * 4,
+                       cw ? c->in_cov + b0 * N * A * cw : nullptr, anchors ? c->in_anchors : nullptr,
+                       counts ? c->in_counts + b0 * A * K : nullptr, st, false);
+        if (rc) return rc;
+    }
+    c->last_stream = st; c->ran = true; c->used_sampler = (counts == nullptr);
+    rc = copy_results(c, out, st);
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(st));
+    int32_t status = 0;
+    CU(c, cudaMemcpy(&status, c->status, 4, cudaMemcpyDeviceToHost));
+    if (status & 1) return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
+    return BOD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// bayes_od_clustering on its own (inference_utils.py:285-364), one image
+// ---------------------------------------------------------------------------
+extern "C" int bod_cluster_host(bod_ctx* c, int32_t S, const float* counts, const float* means, const float* covs,
+                                int32_t D, const int32_t* centres, const float* affinity, float affinity_threshold,
+                                bod_host_results* out) {
+    if (!c || !out) return BOD_ERR_INVALID;
+    if (S < 0 || D < 0 || (S > 0 && (!counts || !means || !covs)) || (D > 0 && (!centres || !affinity)))
+        return fail(c, BOD_ERR_INVALID, "bod_cluster_host: NULL input");
+    if (S > c->capacity) return fail(c, BOD_ERR_INVALID, "bod_cluster_host: S=%d exceeds the context capacity %d", S, c->capacity);
+    if (D > c->Dmax) return fail(c, BOD_ERR_INVALID, "bod_cluster_host: D=%d exceeds max_output_size %d", D, c->Dmax);
+    for (int d = 0; d < D; ++d)
+        if (centres[d] < 0 || centres[d] >= S) return fail(c, BOD_ERR_INVALID, "bod_cluster_host: centre index out of range");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->own_stream;
+    const size_t K = c->cfg.K, Dm = c->Dmax;
+    c->launches = 0;
+    int rc = clear_outputs(c, st);
+    if (rc) return rc;
+    // membership bits from the caller's affinity matrix: affinity[s, centre] > thr (:316)
+    std::vector<uint32_t> mask((size_t)(D > 0 ? D : 1) * c->words, 0u);
+    for (int d = 0; d < D; ++d)
+        for (int s = 0; s < S; ++s)
+            if (affinity[(size_t)s * S + centres[d]] > affinity_threshold) mask[(size_t)d * c->words + (s >> 5)] |= 1u << (s & 31);
+    if (S > 0) {
+        CU(c, cudaMemcpyAsync(c->cnt_post, counts, (size_t)S * K * 4, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemcpyAsync(c->mu_post, means, (size_t)S * 16, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemcpyAsync(c->sig_post, covs, (size_t)S * 64, cudaMemcpyHostToDevice, st));
+    }
+    if (D > 0) {
+        CU(c, cudaMemcpyAsync(c->nms_idx, centres, (size_t)D * 4, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemcpyAsync(c->member, mask.data(), (size_t)D * c->words * 4, cudaMemcpyHostToDevice, st));
+    }
+    CU(c, cudaMemcpyAsync(c->num_survivors, &S, 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(c->num_dets, &D, 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaStreamSynchronize(st));          // `mask`, S, D are stack/heap temporaries
+    K4Args k4{};
+    k4.cnt_post = c->cnt_post; k4.mu_post = c->mu_post; k4.sig_post = c->sig_post; k4.num_survivors = c->num_survivors;
+    k4.nms_idx = c->nms_idx; k4.num_dets = c->num_dets; k4.member = c->member;
+    k4.out_means = c->out_means; k4.out_covs = c->out_covs; k4.out_param = c->out_param; k4.out_count = c->out_count;
+    k4.B = 1; k4.K = (int)K; k4.capacity = c->capacity; k4.Dmax = (int)Dm; k4.words = c->words;
+    k4.calibration = c->cfg.cov_calibration;
+    CU(c, launch_k4(k4, st));
+    c->launches = 1;
+    c->last_stream = st; c->ran = true;
+    // B=1 blocks
+    bod_host_results o = *out;
+    const size_t keepB = c->cfg.B;
+    c->cfg.B = 1;
+    rc = copy_results(c, &o, st);
+    c->cfg.B = (int32_t)keepB;
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(st));
+    return BOD_OK;
+}
+
+extern "C" int bod_generate_anchors(int32_t im_h, int32_t im_w, float* anchors_dev, void* cuda_stream) {
+    if (im_h < 1 || im_w < 1) return BOD_ERR_INVALID;
+    const int A = count_anchors(im_h, im_w);
+    if (!anchors_dev) return A;
+    if (launch_generate_anchors(im_h, im_w, anchors_dev, reinterpret_cast<cudaStream_t>(cuda_stream)) != cudaSuccess)
+        return BOD_ERR_CUDA;
+    return A;
+}

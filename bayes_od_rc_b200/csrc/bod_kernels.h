@@ -1,0 +1,105 @@
+// bod_kernels.h — argument blocks and launchers of the stage kernels (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bod {
+
+// ---- K1: moments + counts + filter + per-tile compaction ------------------
+struct K1Args {
+    const float* cls;        // [B,N,A,K]
+    const float* counts_in;  // [B,A,K] or nullptr (Philox)
+    float* probs_out;        // [B,A,K] or nullptr
+    float* sampled_out;      // [B,A,K] or nullptr (Philox counts, parity)
+    int32_t* slot_anchor;    // [B,A]    survivors of tile t at [t*TILE, t*TILE+count)
+    float* slot_counts;      // [B,A,K]
+    int32_t* tile_count;     // [B,tiles]
+    int B, N, A, K, tiles;
+    int num_draws;
+    uint64_t seed;
+    uint32_t image_id_base;
+};
+cudaError_t launch_k1(const K1Args& a, cudaStream_t st);
+bool k1_supports(int K);
+
+// ---- K1b: per-image exclusive scan of tile counts (+ optional pre-NMS top-k) --
+struct ScanArgs {
+    const int32_t* tile_count;  // [B,tiles]
+    int32_t* tile_off;          // [B,tiles+1]
+    int32_t* num_survivors;     // [B]
+    int32_t* status;            // [1] sticky error flags
+    int B, tiles, capacity;
+};
+cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st);
+
+// ---- K2: per-survivor posterior -------------------------------------------
+struct K2Args {
+    const float* box;           // [B,N,A,4]
+    const float* cov;           // [B,N,A,16|10] or nullptr
+    const float* anchors;       // [A,4] or nullptr (generate)
+    const int32_t* slot_anchor; // [B,A]
+    const float* slot_counts;   // [B,A,K]
+    const int32_t* tile_off;    // [B,tiles+1]
+    const int32_t* num_survivors;  // [B]
+    // outputs, [B,cap,*]
+    int32_t* surv_anchor;
+    float* cnt_post;   // [B,cap,K]
+    float* mu_post;    // [B,cap,4]
+    float* sig_post;   // [B,cap,16]
+    float* score;      // [B,cap]
+    float4* corners;   // [B,cap]
+    float* info;       // [B,cap,2] (gaussian, categorical) information gains (joint_entropy ranking)
+    int B, N, A, K, tiles, capacity;
+    int cov_layout, use_full_covar, dirichlet_prior, gaussian_prior, ranking_method;
+    float isotropic_variance, scale_v, scale_u;
+    int anchor_mode, im_h, im_w;
+};
+cudaError_t launch_k2(const K2Args& a, cudaStream_t st);
+// joint_entropy ranking: normalise the information gains over each image's survivors
+cudaError_t launch_rank_normalise(const K2Args& a, cudaStream_t st);
+
+// ---- K3: soft-NMS centre selection + membership masks -----------------------
+struct K3Args {
+    const float4* corners;        // [B,cap]
+    const float* score;           // [B,cap]
+    const int32_t* num_survivors; // [B]
+    const int32_t* surv_anchor;   // [B,cap]
+    // scratch per candidate, [B,cap]
+    float* stale;     // score as of the candidate's last queue update
+    float* cur;       // up-to-date score
+    int32_t* begin;   // suppress_begin_index
+    uint32_t* pend;   // [B,cap,kMaskWords] selected boxes with a non-unit weight
+    // outputs
+    int32_t* nms_idx;           // [B,Dmax]
+    float* nms_score;           // [B,Dmax]
+    int32_t* centre_anchor;     // [B,Dmax]
+    int32_t* num_dets;          // [B]
+    uint32_t* member;           // [B,Dmax,words]
+    int B, capacity, Dmax, words;
+    float iou_threshold, soft_nms_sigma;
+};
+cudaError_t launch_k3(const K3Args& a, cudaStream_t st);
+
+// ---- K4: per-cluster Bayesian fusion ----------------------------------------
+struct K4Args {
+    const float* cnt_post;   // [B,cap,K]
+    const float* mu_post;    // [B,cap,4]
+    const float* sig_post;   // [B,cap,16]
+    const int32_t* num_survivors;
+    const int32_t* nms_idx;  // [B,Dmax]
+    const int32_t* num_dets; // [B]
+    const uint32_t* member;  // [B,Dmax,words]
+    float* out_means;        // [B,Dmax,4]
+    float* out_covs;         // [B,Dmax,16]
+    float* out_param;        // [B,Dmax,K]
+    float* out_count;        // [B,Dmax,K]
+    int B, K, capacity, Dmax, words;
+    float calibration;
+};
+cudaError_t launch_k4(const K4Args& a, cudaStream_t st);
+
+// ---- anchors ----------------------------------------------------------------
+cudaError_t launch_generate_anchors(int im_h, int im_w, float* anchors, cudaStream_t st);
+int count_anchors(int im_h, int im_w);
+
+}  // namespace bod

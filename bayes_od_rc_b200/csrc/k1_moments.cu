@@ -1,0 +1,278 @@
+// k1_moments.cu — stage K1: per-anchor class moments over the N MC-dropout
+// samples, categorical draw counts, non-background filter and stable per-tile
+// compaction.
+//
+// Reference lines replaced (src/retina_net/experiments/inference_utils.py):
+//   :31-32,38  softmax over K per sample, mean over N         -> mean probabilities
+//   :37-46     Categorical(probs).sample(30) -> one_hot -> sum -> counts [A,K]
+//              (injected tensor in parity mode, Philox4x32-10 otherwise)
+//   :48-54     argmax(counts) != K-1 (first maximum) + boolean_mask (stable)
+//
+// This is the only stage that must touch every anchor: it streams the whole
+// [B,N,A,K] logits tensor exactly once (4*N*A*K bytes per image), so it IS the
+// HBM roofline of the path.  Data movement: one CTA owns a tile of
+// kTileAnchors consecutive anchors of one image; for every MC sample the
+// tile's [tile,K] slab is a contiguous span of global memory that is bulk-copied
+// into shared memory by the TMA engine (cp.async.bulk + mbarrier, all N slabs in
+// flight at once), so no thread issues a load and rows of any K (8, 11, 4, ...)
+// are consumed conflict-free from shared memory.
+#include "bod_common.cuh"
+#include "bod_kernels.h"
+
+namespace bod {
+
+// ---------------------------------------------------------------------------
+// mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS.*, UBLKCP)
+// ---------------------------------------------------------------------------
+BOD_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+BOD_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+BOD_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+BOD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+BOD_DEVINL void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Multinomial(T, p) counts for one anchor with the documented Philox stream:
+// call j -> 128 bits -> five 23-bit fields; u = (field + 0.5) * 2^-23 scaled by
+// the total mass; class = first k with u*total < cdf[k], else K-1.
+// ---------------------------------------------------------------------------
+template <int K>
+BOD_DEVINL void philox_counts(const float (&p)[K], uint32_t anchor, uint32_t image, uint2 key, int T,
+                              float (&cnt)[K]) {
+    float cdf[K];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { s = __fadd_rn(s, p[k]); cdf[k] = s; cnt[k] = 0.0f; }
+    const float total = cdf[K - 1];
+    int t = 0;
+    for (uint32_t j = 0; t < T; ++j) {
+        const uint4 w = philox4x32_10(make_uint4(anchor, image, j, 0x0B0Du), key);
+        const uint32_t f[5] = {w.x & 0x7FFFFFu,
+                               ((w.x >> 23) | (w.y << 9)) & 0x7FFFFFu,
+                               ((w.y >> 14) | (w.z << 18)) & 0x7FFFFFu,
+                               ((w.z >> 5)) & 0x7FFFFFu,
+                               ((w.z >> 28) | (w.w << 4)) & 0x7FFFFFu};
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            if (t < T) {
+                const float u = __fmul_rn(__fadd_rn((float)f[q], 0.5f), 1.1920928955078125e-07f);
+                const float x = __fmul_rn(u, total);
+                int c = K - 1;
+#pragma unroll
+                for (int k = K - 2; k >= 0; --k) c = (x < cdf[k]) ? k : c;
+#pragma unroll
+                for (int k = 0; k < K; ++k) cnt[k] += (c == k) ? 1.0f : 0.0f;
+                ++t;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------
+// grid = (tiles, B), block = kTileAnchors threads.  The N samples of a tile are
+// consumed in chunks of NC samples through a two-stage shared-memory ring
+// (stage = NC slabs of [tile,K] floats, one mbarrier per stage), so any N fits
+// and two chunks are always in flight per CTA (x2 resident CTAs per SM).
+// USE_BULK: slabs arrive through cp.async.bulk (needs 16-byte aligned spans);
+// otherwise a cooperative coalesced copy fills the same shared layout.
+template <int K, bool USE_BULK>
+__global__ void __launch_bounds__(kTileAnchors, 2)
+k1_moments_kernel(K1Args a, int NC) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar[2];
+    __shared__ int warp_count[kTileAnchors / 32];
+
+    const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int a0 = tile * kTileAnchors;
+    const int rows = min(kTileAnchors, a.A - a0);            // anchors in this tile
+    const int N = a.N;
+    const int nchunks = (N + NC - 1) / NC;
+    constexpr size_t slab_stride = (size_t)kTileAnchors * K;  // floats per smem slab
+    const size_t stage_stride = slab_stride * NC;
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    const float* src0 = a.cls + ((size_t)b * N * a.A + a0) * K;   // sample 0 of this tile
+    const uint32_t slab_bytes = (uint32_t)rows * K * 4u;
+
+    auto issue = [&](int c) {   // one thread: bulk-copy chunk c into stage c&1
+        const int n0 = c * NC, n1 = min(N, n0 + NC);
+        uint64_t* br = &bar[c & 1];
+        mbar_expect_tx(br, slab_bytes * (uint32_t)(n1 - n0));
+        for (int n = n0; n < n1; ++n)
+            bulk_g2s(ring + (c & 1) * stage_stride + (size_t)(n - n0) * slab_stride, src0 + (size_t)n * a.A * K,
+                     slab_bytes, br);
+    };
+
+    if (USE_BULK) {
+        if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) { issue(0); if (nchunks > 1) issue(1); }
+    }
+
+    // counts to inject (parity mode) are fetched while the slabs are in flight
+    const int anchor = a0 + tid;
+    const bool valid = tid < rows;
+    float cnt[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) cnt[k] = 0.0f;
+    if (a.counts_in != nullptr && valid) {
+        const float* c = a.counts_in + ((size_t)b * a.A + anchor) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) cnt[k] = __ldg(c + k);
+    }
+
+    // H2: softmax per sample, mean over samples (fast-math allowed here)
+    float p[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = 0.0f;
+    for (int c = 0; c < nchunks; ++c) {
+        const int n0 = c * NC, n1 = min(N, n0 + NC);
+        const float* stage = ring + (USE_BULK ? (c & 1) : 0) * stage_stride;
+        if (USE_BULK) {
+            mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
+        } else {
+            __syncthreads();
+            const int nflt = rows * K;
+            for (int n = n0; n < n1; ++n) {
+                const float* src = src0 + (size_t)n * a.A * K;
+                float* dst = ring + (size_t)(n - n0) * slab_stride;
+                for (int e = tid; e < nflt; e += kTileAnchors) dst[e] = __ldg(src + e);
+            }
+            __syncthreads();
+        }
+        if (valid) {
+            for (int n = n0; n < n1; ++n) {
+                const float* row = stage + (size_t)(n - n0) * slab_stride + tid * K;
+                float x[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) x[k] = row[k];
+                float m = x[0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) m = fmaxf(m, x[k]);
+                float s = 0.0f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) { x[k] = __expf(x[k] - m); s += x[k]; }
+                const float inv = __frcp_rn(s);
+#pragma unroll
+                for (int k = 0; k < K; ++k) p[k] = __fmaf_rn(x[k], inv, p[k]);
+            }
+        }
+        if (USE_BULK && c + 2 < nchunks) {
+            __syncthreads();                       // every thread is done reading stage c&1
+            if (tid == 0) issue(c + 2);
+        }
+    }
+    if (valid) {
+        const float invN = 1.0f / (float)N;
+#pragma unroll
+        for (int k = 0; k < K; ++k) p[k] *= invN;
+        if (a.probs_out != nullptr) {
+            float* o = a.probs_out + ((size_t)b * a.A + anchor) * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) o[k] = p[k];
+        }
+    }
+
+    // H3: categorical draw counts
+    if (a.counts_in == nullptr && valid) {
+        philox_counts<K>(p, (uint32_t)anchor, a.image_id_base + (uint32_t)b,
+                         make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws, cnt);
+        if (a.sampled_out != nullptr) {
+            float* o = a.sampled_out + ((size_t)b * a.A + anchor) * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) o[k] = cnt[k];
+        }
+    }
+
+    // H4: first-maximum argmax != background, stable compaction inside the tile
+    bool keep = false;
+    if (valid) {
+        int am = 0;
+        float best = cnt[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) if (cnt[k] > best) { best = cnt[k]; am = k; }
+        keep = (am != K - 1);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) warp_count[warp] = __popc(ballot);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kTileAnchors / 32; ++w) {
+        const int c = warp_count[w];
+        base += (w < warp) ? c : 0;
+        total += c;
+    }
+    if (keep) {
+        const int slot = a0 + base + __popc(ballot & ((1u << lane) - 1u));   // per-tile slot region
+        a.slot_anchor[(size_t)b * a.A + slot] = anchor;
+        float* o = a.slot_counts + ((size_t)b * a.A + slot) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) o[k] = cnt[k];
+    }
+    if (tid == 0) a.tile_count[(size_t)b * a.tiles + tile] = total;
+}
+
+template <int K>
+static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
+    // samples per ring stage: two stages of <= ~50 KB keep two CTAs resident per SM
+    const size_t slab = (size_t)kTileAnchors * K * sizeof(float);
+    int NC = (int)((50u * 1024u) / slab);
+    if (NC < 1) NC = 1;
+    if (NC > a.N) NC = a.N;
+    const size_t smem = 2 * (size_t)NC * slab;
+    // bulk copies need 16-byte aligned sources and sizes for every (image, sample, tile)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a.cls) & 15u) == 0) && (((size_t)a.A * K) % 4 == 0) &&
+                         ((kTileAnchors * K) % 4 == 0);
+    dim3 grid(a.tiles, a.B), block(kTileAnchors);
+    cudaError_t e;
+    if (aligned) {
+        e = cudaFuncSetAttribute(k1_moments_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k1_moments_kernel<K, true><<<grid, block, smem, st>>>(a, NC);
+    } else {
+        e = cudaFuncSetAttribute(k1_moments_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k1_moments_kernel<K, false><<<grid, block, smem, st>>>(a, NC);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k1(const K1Args& a, cudaStream_t st) {
+    switch (a.K) {
+#define BOD_CASE(KK) case KK: return launch_k<KK>(a, st);
+        BOD_CASE(2) BOD_CASE(3) BOD_CASE(4) BOD_CASE(5) BOD_CASE(6) BOD_CASE(7) BOD_CASE(8) BOD_CASE(9)
+        BOD_CASE(10) BOD_CASE(11) BOD_CASE(12) BOD_CASE(13) BOD_CASE(16) BOD_CASE(21) BOD_CASE(32)
+#undef BOD_CASE
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+bool k1_supports(int K) {
+    switch (K) {
+        case 2: case 3: case 4: case 5: case 6: case 7: case 8: case 9: case 10: case 11: case 12: case 13:
+        case 16: case 21: case 32: return true;
+        default: return false;
+    }
+}
+
+}  // namespace bod

@@ -192,10 +192,22 @@ int bod_fetch_probs(bod_ctx* ctx, int32_t b, float* probs);
  * (needs cfg.emit_probs and counts == NULL in the last run). */
 int bod_fetch_sampled_counts(bod_ctx* ctx, int32_t b, float* counts);
 
+/* cudaDeviceSynchronize() on the context's device.  For producers that do not
+ * expose their stream (TensorFlow eager tensors exported through DLPack): call
+ * it between the producer and bod_run. */
+int bod_synchronize(bod_ctx* ctx);
+
 /* Device-time of the last run per stage in milliseconds (events recorded on the
  * run's stream): [0]=moments/filter, [1]=scan, [2]=posterior, [3]=soft-NMS,
  * [4]=fusion, [5]=total.  Syncs on the run. */
 int bod_last_stage_ms(bod_ctx* ctx, float ms[6]);
+/* Stage events are recorded by default (6 cudaEventRecord per run); switch them
+ * off for latency-critical callers. */
+int bod_set_stage_timing(bod_ctx* ctx, int enabled);
+/* Sum of the per-stage device times (same layout as bod_last_stage_ms) over the
+ * runs issued since the previous call (at most the last 128), and how many runs
+ * that was.  Syncs on the last run. */
+int bod_stage_ms_accum(bod_ctx* ctx, float sum_ms[6], int32_t* runs);
 /* Number of kernels the last bod_run launched. */
 int bod_last_launch_count(const bod_ctx* ctx);
 

@@ -1,0 +1,176 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the
+CPU oracle on the same inputs (bit-exact) and against the golden fixtures
+(reference sources over the TF shim; tolerance rtol 1e-4 / atol 1e-5)."""
+import numpy as np
+import pytest
+
+import oracle
+from bayes_od_rc_b200 import anchors as anchors_mod
+from bayes_od_rc_b200 import synthetic
+from gpu_common import assert_bit_equal, compare_image_with_oracle, run_gpu_batch
+from helpers import (adjudicated_close, check_categorical_merge, golden_cases, load_golden, oracle_config_of,
+                     within_tol)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_fixture(name):
+    g = load_golden(name)
+    oc = oracle_config_of(g["meta"])
+    cov = g["cov"] if g["meta"]["has_cov"] else None
+    eng, res = run_gpu_batch(oc, g["cls"][None], g["box"][None], None if cov is None else cov[None], g["anchors"],
+                             g["counts"][None])
+    r = oracle.run_image(oc, g["cls"], g["box"], cov, g["anchors"], g["counts"])
+    K = g["cls"].shape[-1]
+    compare_image_with_oracle(eng, res, 0, r, K)
+    # and against what the reference's own code produced
+    S, D = len(g["cnt_post"]), len(g["nms_indices"])
+    assert int(res.num_survivors[0]) == S and int(res.num_dets[0]) == D
+    if S == 0:
+        return
+    sv = eng.survivors(0)
+    assert np.array_equal(sv["counts"], g["cnt_post"])
+    assert within_tol(sv["means"], g["mu_post"][:, :, 0]).all()
+    assert np.array_equal(res.nms_indices[0, :D], g["nms_indices"])
+    mem = oracle.mask_to_bool(eng.members(0, S, D), S)
+    assert np.array_equal(mem, (g["iou_cols"] > oc.iou_threshold).T)
+    assert within_tol(res.means[0, :D], g["final_means"][:, :, 0]).all()
+    r64 = oracle.run_image(oc, g["cls"], g["box"], cov, g["anchors"], g["counts"], real="f64",
+                           force=dict(nms_indices=r.nms_indices, mask=r.mask))
+    ok, frac = adjudicated_close(res.covs[0, :D], g["final_covs"], r64.final_covs)
+    assert ok.all() and frac > 0.99
+    check_categorical_merge(g, g["nms_indices"], mem, r.extra["chosen"], res.cat_param[0, :D], res.cat_count[0, :D])
+
+
+CONFIGS = {
+    # name: (SceneSpec kwargs, OracleConfig kwargs, B)
+    "bdd_covar_k8": (dict(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=3), dict(), 3),
+    "bdd_kendall_k8": (dict(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=2),
+                       dict(use_full_covar=False), 2),
+    "bdd_covar_k11": (dict(im_h=192, im_w=320, N=10, K=11, g_min=6, g_max=10, box_hi=150., config_id=31), dict(), 2),
+    "kitti_k4_n20": (dict(im_h=128, im_w=424, N=20, K=4, g_min=5, g_max=9, box_hi=120., config_id=4),
+                     dict(scale_v=375 / 512, scale_u=1242 / 1696), 2),
+    "packed_cov": (dict(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=33, packed_cov=True),
+                   dict(cov_layout=2), 2),
+    "n40_k11": (dict(im_h=96, im_w=160, N=40, K=11, g_min=4, g_max=6, box_hi=90., config_id=5), dict(), 2),
+    "hard_nms": (dict(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=34),
+                 dict(soft_nms_sigma=0.0), 2),
+    "joint_entropy": (dict(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=35),
+                      dict(ranking_method="joint_entropy"), 2),
+    "no_gaussian_prior": (dict(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=36),
+                          dict(gaussian_prior="None"), 1),
+    "odd_A_k7": (dict(im_h=70, im_w=90, N=5, K=7, g_min=3, g_max=4, box_hi=60., config_id=37), dict(), 2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_synthetic_batch_bit_exact(name):
+    spec_kw, oc_kw, B = CONFIGS[name]
+    spec = synthetic.SceneSpec(**spec_kw)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, B))
+    oc = oracle.OracleConfig(**oc_kw)
+    eng, res = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"])
+    for b in range(B):
+        r = oracle.run_image(oc, batch["cls"][b], batch["box"][b], batch["cov"][b], batch["anchors"], batch["counts"][b])
+        assert len(r.keep) > 0
+        compare_image_with_oracle(eng, res, b, r, spec.K)
+
+
+def test_host_path_equals_device_path():
+    spec = synthetic.SceneSpec(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=3)
+    B = 9       # > 8 so that the host path splits the batch into chunks
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, B))
+    oc = oracle.OracleConfig()
+    _, res_d = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"], emit_probs=False)
+    _, res_h = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"],
+                             emit_probs=False, via_host=True)
+    for k in ("num_dets", "num_survivors", "means", "covs", "cat_param", "cat_count", "nms_indices", "centre_anchor_idx"):
+        assert_bit_equal(getattr(res_h, k), getattr(res_d, k), k)
+
+
+def test_batch_composition_independence():
+    """Image i's result does not depend on what else is in the batch."""
+    spec = synthetic.SceneSpec(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=41)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, 4))
+    oc = oracle.OracleConfig()
+    _, res4 = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"], emit_probs=False)
+    for b in (0, 3):
+        _, res1 = run_gpu_batch(oc, batch["cls"][b:b + 1], batch["box"][b:b + 1], batch["cov"][b:b + 1], batch["anchors"],
+                                batch["counts"][b:b + 1], emit_probs=False)
+        for k in ("num_dets", "means", "covs", "cat_param", "cat_count", "nms_indices"):
+            assert_bit_equal(getattr(res1, k)[0], getattr(res4, k)[b], k)
+
+
+def test_philox_sampler_matches_restatement():
+    """Sampler mode: the counts the kernel draws equal the oracle's Philox restatement
+    run on the kernel's own mean probabilities, bit for bit; every row sums to T."""
+    spec = synthetic.SceneSpec(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=42)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, 2, with_counts=False))
+    oc = oracle.OracleConfig(seed=99, image_id_base=7)
+    eng, res = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], None)
+    for b in range(2):
+        p = eng.probs(b)
+        c = eng.sampled_counts(b)
+        assert (c.sum(1) == 30).all()
+        ref = oracle.philox_counts(p, 30, 99, 7 + b)
+        assert_bit_equal(c, ref, "philox counts")
+        # and the rest of the path on those counts is bit-exact again
+        r = oracle.run_image(oc, batch["cls"][b], batch["box"][b], batch["cov"][b], batch["anchors"], c)
+        compare_image_with_oracle(eng, res, b, r, spec.K)
+
+
+def test_generated_anchors_bit_exact():
+    import torch
+    from bayes_od_rc_b200 import _cabi
+    lib = _cabi.load()
+    for (h, w) in [(720, 1280), (512, 1696), (375, 1242), (70, 90)]:
+        A = lib.bod_generate_anchors(h, w, None, None)
+        assert A == anchors_mod.num_anchors(h, w)
+        buf = torch.empty(A, 4, device="cuda")
+        assert lib.bod_generate_anchors(h, w, buf.data_ptr(), None) == A
+        torch.cuda.synchronize()
+        assert_bit_equal(buf.cpu().numpy(), oracle.generate_anchors(h, w), f"anchors {h}x{w}")
+
+
+def test_anchor_generate_mode_equals_tensor_mode():
+    from bayes_od_rc_b200 import _cabi
+    spec = synthetic.SceneSpec(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=43)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, 2))
+    oc = oracle.OracleConfig()
+    _, res_t = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"], emit_probs=False)
+    _, res_g = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], None, batch["counts"], emit_probs=False,
+                             anchor_mode=_cabi.ANCHORS_GENERATE, im_h=96, im_w=160)
+    for k in ("num_dets", "means", "covs", "cat_param", "cat_count", "nms_indices"):
+        assert_bit_equal(getattr(res_g, k), getattr(res_t, k), k)
+
+
+def test_cluster_host_standalone():
+    """bayes_od_clustering as its own entry point (bod_cluster_host) on a golden posterior."""
+    from bayes_od_rc_b200.engine import BayesODConfig, BayesODEngine
+    g = load_golden("bdd_covar_k8")
+    S, K = g["cnt_post"].shape
+    mu = g["mu_post"][:, :, 0]
+    corners = np.stack([mu[:, 0] - mu[:, 2] / 2, mu[:, 1] - mu[:, 3] / 2, mu[:, 0] + mu[:, 2] / 2, mu[:, 1] + mu[:, 3] / 2], 1)
+    iou = oracle.iou_matrix(corners.astype(np.float32))
+    eng = BayesODEngine(1, 10, max(S, 64), K, BayesODConfig(use_full_covar=True))
+    fs, fm, fc, fn = eng.cluster_host(g["cnt_post"], mu, g["sig_post"], g["nms_indices"], iou, 0.5)
+    mask = oracle.membership(corners.astype(np.float32), g["nms_indices"], 0.5)
+    os_, om, oc_, on, _, _ = oracle.clustering(g["cnt_post"], mu, g["sig_post"], g["nms_indices"], mask, 70.0)
+    assert fm.shape == (len(g["nms_indices"]), 4, 1) and fc.shape[1:] == (4, 4)
+    assert_bit_equal(fm[:, :, 0], om, "means"); assert_bit_equal(fc, oc_, "covs")
+    assert_bit_equal(fs, os_, "scores"); assert_bit_equal(fn, on, "counts")
+
+
+def test_full_size_bdd_image_bit_exact():
+    """One full BDD-shape image (A = 172 980, N = 10, K = 8) end to end."""
+    spec = synthetic.SceneSpec(config_id=3)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, 2))
+    assert batch["cls"].shape[2] == 172980
+    oc = oracle.OracleConfig()
+    eng, res = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"], emit_probs=False)
+    for b in range(2):
+        r = oracle.run_image(oc, batch["cls"][b], batch["box"][b], batch["cov"][b], batch["anchors"], batch["counts"][b],
+                             with_probs=False)
+        assert 1000 < len(r.keep) < 10000
+        compare_image_with_oracle(eng, res, b, r, 8, check_probs=False)
