@@ -251,21 +251,7 @@ static int run_range(bod_ctx* c, int b0, int nb, const float* cls, const float* 
     k4.calibration = g.cov_calibration;
     CU(c, launch_k4(k4, st));
     if (record) CU(c, cudaEventRecord(c->ev[5], st));
-    c->launches += launches + 2;
-    return BOD_OK;
-}
-
-// padded output rows beyond num_dets must read as zero / -1
-static int clear_outputs(bod_ctx* c, cudaStream_t st) {
-    const size_t B = c->cfg.B, D = c->Dmax, K = c->cfg.K;
-    CU(c, cudaMemsetAsync(c->out_means, 0, B * D * 16, st));
-    CU(c, cudaMemsetAsync(c->out_covs, 0, B * D * 64, st));
-    CU(c, cudaMemsetAsync(c->out_param, 0, B * D * K * 4, st));
-    CU(c, cudaMemsetAsync(c->out_count, 0, B * D * K * 4, st));
-    CU(c, cudaMemsetAsync(c->nms_idx, 0xFF, B * D * 4, st));
-    CU(c, cudaMemsetAsync(c->centre_anchor, 0xFF, B * D * 4, st));
-    CU(c, cudaMemsetAsync(c->nms_score, 0, B * D * 4, st));
-    CU(c, cudaMemsetAsync(c->status, 0, 4, st));
+    c->launches += launches + 2;   // + K3, K4
     return BOD_OK;
 }
 
@@ -287,8 +273,6 @@ extern "C" int bod_run(bod_ctx* c, const float* cls, const float* box, const flo
     CU(c, cudaSetDevice(c->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     c->launches = 0;
-    rc = clear_outputs(c, st);
-    if (rc) return rc;
     c->ev = c->evring[c->runs_recorded % bod_ctx::kEvRing];
     rc = run_range(c, 0, c->cfg.B, cls, box, cov, anchors, counts, st, c->timing);
     if (rc) return rc;
@@ -304,7 +288,10 @@ static int sync_and_status(bod_ctx* c) {
     CU(c, cudaStreamSynchronize(c->last_stream));
     int32_t status = 0;
     CU(c, cudaMemcpy(&status, c->status, 4, cudaMemcpyDeviceToHost));
-    if (status & 1) return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
+    if (status & 1) {
+        CU(c, cudaMemset(c->status, 0, 4));        // sticky until reported once
+        return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
+    }
     return BOD_OK;
 }
 
@@ -465,8 +452,6 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
     }
     cudaStream_t cs = c->copy_stream, st = c->own_stream;
     c->launches = 0;
-    rc = clear_outputs(c, st);
-    if (rc) return rc;
     c->last_timed = false;
     if (anchors) CU(c, cudaMemcpyAsync(c->in_anchors, anchors, A * 16, cudaMemcpyHostToDevice, cs));
     // chunks of images: small enough to overlap, large enough to fill the GPU
@@ -492,7 +477,10 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
     CU(c, cudaStreamSynchronize(st));
     int32_t status = 0;
     CU(c, cudaMemcpy(&status, c->status, 4, cudaMemcpyDeviceToHost));
-    if (status & 1) return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
+    if (status & 1) {
+        CU(c, cudaMemset(c->status, 0, 4));
+        return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
+    }
     return BOD_OK;
 }
 
@@ -513,8 +501,7 @@ extern "C" int bod_cluster_host(bod_ctx* c, int32_t S, const float* counts, cons
     cudaStream_t st = c->own_stream;
     const size_t K = c->cfg.K, Dm = c->Dmax;
     c->launches = 0;
-    int rc = clear_outputs(c, st);
-    if (rc) return rc;
+    int rc = BOD_OK;
     // membership bits from the caller's affinity matrix: affinity[s, centre] > thr (:316)
     std::vector<uint32_t> mask((size_t)(D > 0 ? D : 1) * c->words, 0u);
     for (int d = 0; d < D; ++d)

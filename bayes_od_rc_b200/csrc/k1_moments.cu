@@ -48,38 +48,89 @@ BOD_DEVINL void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, u
 }
 
 // ---------------------------------------------------------------------------
-// Multinomial(T, p) counts for one anchor with the documented Philox stream:
-// call j -> 128 bits -> five 23-bit fields; u = (field + 0.5) * 2^-23 scaled by
-// the total mass; class = first k with u*total < cdf[k], else K-1.
+// Multinomial(T, p) counts for one anchor (stands in for the unseeded
+// Categorical(probs).sample(30) -> one_hot -> reduce_sum, inference_utils.py:37-46).
+// Uniform i of anchor a in global image g = 23-bit field (i % 5) of Philox call
+// (i / 5) with counter (a, g, call, 0x0B0D): u = (field + 0.5) * 2^-23.
+// Dominant-class split: the number of draws that do NOT land on the most likely
+// class m is Binomial(T, 1 - p_m), drawn by inversion from 0 upward (a background
+// anchor needs ~2 steps and ONE Philox call instead of 30 draws / 6 calls); each
+// of those draws then picks a class != m by inverse cdf.  Flat distributions
+// (p_m^T < 1e-30) fall back to T plain inverse-cdf draws.  Every operation is an
+// explicitly rounded binary32 intrinsic so the CPU restatement is bit-identical.
 // ---------------------------------------------------------------------------
+struct PhiloxStream {
+    uint4 w;
+    uint32_t anchor, image;
+    uint2 key;
+    int g;
+    BOD_DEVINL float next() {
+        const int f = g % 5;
+        if (f == 0) w = philox4x32_10(make_uint4(anchor, image, (uint32_t)(g / 5), 0x0B0Du), key);
+        uint32_t field;
+        switch (f) {
+            case 0: field = w.x; break;
+            case 1: field = (w.x >> 23) | (w.y << 9); break;
+            case 2: field = (w.y >> 14) | (w.z << 18); break;
+            case 3: field = w.z >> 5; break;
+            default: field = (w.z >> 28) | (w.w << 4); break;
+        }
+        ++g;
+        return __fmul_rn(__fadd_rn((float)(field & 0x7FFFFFu), 0.5f), 1.1920928955078125e-07f);
+    }
+};
+
 template <int K>
 BOD_DEVINL void philox_counts(const float (&p)[K], uint32_t anchor, uint32_t image, uint2 key, int T,
                               float (&cnt)[K]) {
     float cdf[K];
-    float s = 0.0f;
+    float s = 0.0f, pm = p[0];
+    int m = 0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) { s = __fadd_rn(s, p[k]); cdf[k] = s; cnt[k] = 0.0f; }
+    for (int k = 0; k < K; ++k) {
+        s = __fadd_rn(s, p[k]); cdf[k] = s; cnt[k] = 0.0f;
+        if (k > 0 && p[k] > pm) { pm = p[k]; m = k; }
+    }
     const float total = cdf[K - 1];
-    int t = 0;
-    for (uint32_t j = 0; t < T; ++j) {
-        const uint4 w = philox4x32_10(make_uint4(anchor, image, j, 0x0B0Du), key);
-        const uint32_t f[5] = {w.x & 0x7FFFFFu,
-                               ((w.x >> 23) | (w.y << 9)) & 0x7FFFFFu,
-                               ((w.y >> 14) | (w.z << 18)) & 0x7FFFFFu,
-                               ((w.z >> 5)) & 0x7FFFFFu,
-                               ((w.z >> 28) | (w.w << 4)) & 0x7FFFFFu};
+    const float rest = __fsub_rn(total, pm);
+    const float aa = __fdiv_rn(pm, total), odds = __fdiv_rn(rest, pm);
+    float pw = 1.0f, base = aa;
+    for (int e = T; e; e >>= 1) { if (e & 1) pw = __fmul_rn(pw, base); base = __fmul_rn(base, base); }
+    PhiloxStream rng{make_uint4(0, 0, 0, 0), anchor, image, key, 0};
+    if (pw >= 1e-30f) {
+        const float u = rng.next();
+        int j = 0;
+        float cd = pw, f = pw;
+        while (u >= cd && j < T) {
+            f = __fmul_rn(__fmul_rn(f, __fdiv_rn((float)(T - j), (float)(j + 1))), odds);
+            ++j;
+            cd = __fadd_rn(cd, f);
+        }
+        // running sums of p over the classes != m (adding 0 for m is exact)
+        float acc[K];
+        float t = 0.0f;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            if (t < T) {
-                const float u = __fmul_rn(__fadd_rn((float)f[q], 0.5f), 1.1920928955078125e-07f);
-                const float x = __fmul_rn(u, total);
-                int c = K - 1;
+        for (int k = 0; k < K; ++k) { t = __fadd_rn(t, (k == m) ? 0.0f : p[k]); acc[k] = t; }
+        const int last = (m == K - 1) ? K - 2 : K - 1;
+        for (int i = 0; i < j; ++i) {
+            const float x = __fmul_rn(rng.next(), rest);
+            int c = last;
 #pragma unroll
-                for (int k = K - 2; k >= 0; --k) c = (x < cdf[k]) ? k : c;
+            for (int k = K - 1; k >= 0; --k) c = (k != m && x < acc[k]) ? k : c;
 #pragma unroll
-                for (int k = 0; k < K; ++k) cnt[k] += (c == k) ? 1.0f : 0.0f;
-                ++t;
-            }
+            for (int k = 0; k < K; ++k) cnt[k] = __fadd_rn(cnt[k], (c == k) ? 1.0f : 0.0f);
+        }
+        const float cm = (float)(T - j);
+#pragma unroll
+        for (int k = 0; k < K; ++k) cnt[k] = (k == m) ? cm : cnt[k];
+    } else {
+        for (int t = 0; t < T; ++t) {
+            const float x = __fmul_rn(rng.next(), total);
+            int c = K - 1;
+#pragma unroll
+            for (int k = K - 2; k >= 0; --k) c = (x < cdf[k]) ? k : c;
+#pragma unroll
+            for (int k = 0; k < K; ++k) cnt[k] = __fadd_rn(cnt[k], (c == k) ? 1.0f : 0.0f);
         }
     }
 }

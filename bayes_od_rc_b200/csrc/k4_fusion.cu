@@ -47,7 +47,14 @@ k4_fusion_kernel(K4Args a) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = blockIdx.x * kK4Warps + warp, b = blockIdx.y;
-    if (d >= a.num_dets[b]) return;               // warp-uniform
+    if (d >= a.Dmax) return;                      // warp-uniform
+    if (d >= a.num_dets[b]) {                     // padding rows of the result blocks read as zero
+        const size_t prow = (size_t)b * a.Dmax + d;
+        if (lane < 16) a.out_covs[prow * 16 + lane] = 0.0f;
+        if (lane < 4) a.out_means[prow * 4 + lane] = 0.0f;
+        for (int k = lane; k < K; k += 32) { a.out_param[prow * K + k] = 0.0f; a.out_count[prow * K + k] = 0.0f; }
+        return;
+    }
     const int S = a.num_survivors[b];
     const int nwords = (S + 31) >> 5;
     const uint32_t* row = a.member + ((size_t)b * a.Dmax + d) * a.words;

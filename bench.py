@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — BayesOD post-head throughput (head outputs -> fused detections).
+
+    python bench.py --gpus 1 --steps 50 --warmup 5                 # our CUDA path
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # the CPU implementation of the path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W     # N GPUs, one rank each
+
+A "step" is one pass of the hot path (inference_utils.py:25-217 + :285-364 of the
+reference, minus the model call) over one batch of B synthetic BDD-shape images
+per GPU: K1 moments/sampler/filter -> scan -> K2 posterior -> K3 soft-NMS ->
+K4 fusion.  Images are sharded over GPUs by batch (weak scaling: B per GPU), no
+collective on the hot path.  Rank 0 prints ONE JSON line.
+
+  value     images/s over all GPUs, inputs resident in HBM, in-kernel Philox sampler
+  e2e       images/s through the C-ABI host entry (bod_run_host): inputs in pinned
+            host memory, H2D + compute + D2H of the result blocks inside the timed region
+  roofline  K1 (the only kernel that touches every anchor): algorithmic bytes of one
+            launch / its mean CUDA-event duration over the timed region, vs the
+            measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port of the reference path on the host cores (N=1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (im_h, im_w, N, K, B per GPU, use_full_covar, config_id)
+    # BASELINE.json target: "batch of 32 BDD-shape images at N=10", "10 classes" -> K = 11, full covariance
+    "bdd_covar_b32_k11": dict(im_h=720, im_w=1280, N=10, K=11, B=32, use_full_covar=True, config_id=3),
+    "bdd_covar_b32_k8": dict(im_h=720, im_w=1280, N=10, K=8, B=32, use_full_covar=True, config_id=3),
+    "bdd_kendall_b8_k8": dict(im_h=720, im_w=1280, N=10, K=8, B=8, use_full_covar=False, config_id=2),
+    "kitti_covar_b64_n20_k4": dict(im_h=512, im_w=1696, N=20, K=4, B=64, use_full_covar=True, config_id=4,
+                                   scale_v=375 / 512, scale_u=1242 / 1696),
+    "tiny": dict(im_h=192, im_w=320, N=10, K=8, B=4, use_full_covar=True, config_id=9),
+}
+DEFAULT_WORKLOAD = "bdd_covar_b32_k11"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML while the bench runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples = []            # (t, sm_mhz, reasons_bitmask, power_w)
+        self.sm_max = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = float("nan")
+                self.samples.append((time.perf_counter(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self, t0, t1):
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting",
+                 0x10: "sync_boost"}
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "note": "no NVML samples"}
+        sel = [s for s in self.samples if t0 <= s[0] <= t1]
+        note = "sampled during the timed region"
+        if len(sel) < 3:
+            sel = self.samples
+            note = "timed region shorter than the sampling period: samples span warm-up + timed + e2e"
+        clocks = sorted(s[1] for s in sel)
+        bits = 0
+        for s in sel:
+            bits |= s[2]
+        reasons = [n for b, n in names.items() if bits & b]
+        return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "power_w_max": max(s[3] for s in sel), "samples": len(sel), "note": note}
+
+
+def bytes_min_per_image(N, A, K, S_mean, D_mean, cov_width, injected_counts=False, anchors_gathered=True):
+    """SURVEY.md §8(d) / BASELINE.md §3 contract figure."""
+    b = 4 * N * A * K + 4 * N * S_mean * (4 + cov_width) + (16 * S_mean if anchors_gathered else 0)
+    if injected_counts:
+        b += 4 * A * K
+    b += 4 * D_mean * (4 + 16 + 2 * K) + 4
+    return b
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and world != args.gpus:
+        raise SystemExit(f"WORLD_SIZE={world} but --gpus {args.gpus}")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+
+    if args.impl == "reference":
+        return reference_arm(args, rank)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bayes_od_rc_b200 import _cabi, synthetic
+    from bayes_od_rc_b200.engine import BayesODConfig, BayesODEngine
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = dict(WORKLOADS[args.workload])
+    B = args.batch or wl["B"]
+    N, K = wl["N"], wl["K"]
+    spec = synthetic.SceneSpec(im_h=wl["im_h"], im_w=wl["im_w"], N=N, K=K, config_id=wl["config_id"])
+    first_image = rank * B                      # global image ids: shard-invariant RNG + data
+
+    # ---- synthetic head outputs, generated on the device, then resident in HBM ----
+    t_gen = time.time()
+    batch = synthetic.make_batch(spec, B, device=dev, with_counts=False, first_image_id=first_image)
+    cls, box, cov, anchors = batch["cls"], batch["box"], batch["cov"], batch["anchors"]
+    A = anchors.shape[0]
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+
+    cfg = BayesODConfig(use_full_covar=wl["use_full_covar"], cov_layout=_cabi.COV_FULL16, seed=1234,
+                        image_id_base=first_image, scale_v=wl.get("scale_v", 1.0), scale_u=wl.get("scale_u", 1.0),
+                        max_survivors=min(A, 32768))
+    eng = BayesODEngine(B, N, A, K, cfg, device=local_rank)
+    stream = torch.cuda.Stream(device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        eng.run(cls, box, cov, anchors, None, stream=stream.cuda_stream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident throughput ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    eng.stage_ms_accum()                         # reset the stage accumulators
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    stage_sum, stage_runs = eng.stage_ms_accum()
+    res = eng.fetch()
+    S_mean = float(res.num_survivors.mean())
+    D_mean = float(res.num_dets.mean())
+    launches_per_step = eng.launch_count
+
+    # ---- end to end: pinned host inputs -> bod_run_host -> host results ----
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda t: t.cpu().pin_memory()     # noqa: E731
+        h_cls, h_box, h_cov, h_anc = pin(cls), pin(box), pin(cov), pin(anchors)
+        n_e2e = args.e2e_steps or max(2, min(args.steps, 5))
+        run_e2e = lambda: eng.run_host_ptrs(h_cls.data_ptr(), h_box.data_ptr(), h_cov.data_ptr(), h_anc.data_ptr(), None)   # noqa: E731
+        run_e2e()                                 # warm-up (allocates the device staging buffers)
+        barrier()
+        te0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = run_e2e()
+        torch.cuda.synchronize()
+        te = time.perf_counter() - te0
+        h2d = (cls.numel() + box.numel() + cov.numel() + anchors.numel()) * 4
+        d2h = sum(v.nbytes for v in out.values())
+        e2e = dict(seconds=te, steps=n_e2e, h2d=h2d, d2h=d2h)
+    sampler.stop()
+
+    # ---- max over ranks ----
+    if world > 1:
+        tt = torch.tensor([elapsed_ms, e2e["seconds"] if e2e else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt[0]); e2e_seconds = float(tt[1])
+        ss = torch.tensor([S_mean, D_mean], device=dev, dtype=torch.float64)
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+        S_mean, D_mean = float(ss[0]) / world, float(ss[1]) / world
+    elif e2e:
+        e2e_seconds = e2e["seconds"]
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        images = world * B * args.steps
+        value = images / (elapsed_ms * 1e-3)
+        k1_ms = stage_sum["moments_filter"] / max(stage_runs, 1)
+        k1_bytes = 4.0 * N * A * K * B            # algorithmic bytes of ONE K1 launch: the [B,N,A,K] logits, read once
+        achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+        cw = 16
+        bmin = bytes_min_per_image(N, A, K, S_mean, D_mean, cw)
+        path_frac = (bmin * B / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak
+        line = {
+            "metric": "BayesOD images/s (head out -> fused dets)", "value": round(value, 1), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['im_h']}x{wl['im_w']} A={A} N={N} K={K} B={B}/GPU "
+                                   f"use_full_covar={wl['use_full_covar']} cov=[N,A,4,4] philox-sampler seed=1234",
+                       "images_per_gpu": B, "global_batch": B * world, "parallelism": f"image-shard x{world}, no collective",
+                       "l2": "inputs (%.2f GB per step) larger than L2" % ((cls.numel() + box.numel() + cov.numel()) * 4 / 1e9),
+                       "mean_survivors": round(S_mean, 1), "mean_dets": round(D_mean, 1),
+                       "bytes_min_per_image": int(bmin), "path_roofline_frac": round(path_frac, 4)},
+            "gpu_launches": launches_per_step * args.steps,
+            "stage_ms": {k: round(v / max(stage_runs, 1), 4) for k, v in stage_sum.items()},
+            "roofline": {"bound": "hbm", "kernel": "k1_moments_kernel", "achieved": round(achieved, 1) if achieved else None,
+                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": round(k1_ms, 4)},
+            "clocks": sampler.summary(t0, t1),
+        }
+        if e2e:
+            e2e_value = world * B * e2e["steps"] / e2e_seconds
+            line["e2e"] = {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(e2e["h2d"]),
+                           "d2h_bytes_per_step": int(e2e["d2h"]), "steps": e2e["steps"],
+                           "api": "bod_run_host (pinned host buffers -> padded host result blocks)"}
+        # ---- CPU baseline: the oracle port on the host cores, bounded sample ----
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cls, box, cov, anchors, wl, args.cpu_sample, first_image)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _oracle_cfg(wl, image_id_base):
+    import oracle
+    return oracle.OracleConfig(use_full_covar=wl["use_full_covar"], cov_layout=1, seed=1234, image_id_base=image_id_base,
+                               scale_v=wl.get("scale_v", 1.0), scale_u=wl.get("scale_u", 1.0))
+
+
+def cpu_baseline(cls, box, cov, anchors, wl, sample, first_image):
+    """The oracle (CPU port of the reference path, Philox sampler included) on a
+    bounded sample of the same images, all host cores (one image per thread)."""
+    import oracle
+    cores = os.cpu_count() or 1
+    B = cls.shape[0]
+    n = sample or min(B, max(4, min(cores, 32)))
+    n = min(n, B)
+    threads = min(cores, n)
+    c = cls[:n].cpu().numpy(); b = box[:n].cpu().numpy(); v = cov[:n].cpu().numpy(); a = anchors.cpu().numpy()
+    oc = _oracle_cfg(wl, first_image)
+    oracle.run_batch(oc, c[:1], b[:1], v[:1], a, None, nthreads=1)     # warm-up (page in, build)
+    t0 = time.perf_counter()
+    oracle.run_batch(oc, c, b, v, a, None, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": round(n / dt, 3), "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"{n} images of the same workload in {dt:.2f} s, oracle/bayesod_oracle.c (C restatement of "
+                      f"inference_utils.py:25-217,285-364), {threads} host threads (host has {cores})"}
+
+
+def reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path.  The
+    reference is Python/TensorFlow and TensorFlow is not installable offline, so
+    this arm times the oracle port (oracle/bayesod_oracle.c) on the host cores."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    import oracle
+    from bayes_od_rc_b200 import synthetic
+    wl = dict(WORKLOADS[args.workload])
+    N, K = wl["N"], wl["K"]
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample or min(wl["B"], max(4, min(cores, 32)))
+    threads = min(cores, n)
+    spec = synthetic.SceneSpec(im_h=wl["im_h"], im_w=wl["im_w"], N=N, K=K, config_id=wl["config_id"])
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, n, device=dev, with_counts=False))
+    oc = _oracle_cfg(wl, 0)
+    A = batch["anchors"].shape[0]
+    run = lambda: oracle.run_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], None, nthreads=threads)   # noqa: E731
+    for _ in range(min(args.warmup, 1)):
+        run()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = time.perf_counter() - t0
+    value = n * steps / dt
+    line = {"impl": "reference", "metric": "BayesOD images/s (head out -> fused dets)", "value": round(value, 3),
+            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['im_h']}x{wl['im_w']} A={A} N={N} K={K} "
+                                   f"use_full_covar={wl['use_full_covar']} cov=[N,A,4,4] philox-sampler seed=1234",
+                       "images_per_step": n},
+            "cpu_baseline": {"value": round(value, 3), "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} images per step x {steps} steps; the reference path is Python/TF (not "
+                                       f"installable offline), timed: its C oracle port on {threads} host threads"},
+            "e2e": {"value": round(value, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -220,33 +220,74 @@ void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint3
 
 /* Multinomial(T, probs) counts per anchor, standing in for
  * Categorical(probs).sample(30) -> one_hot -> reduce_sum (inference_utils.py:37-46).
- * Spec: for anchor a of global image g, call j = 0,1,.. of Philox with
- * counter (a, g, j, 0x0B0D) and key (seed lo, seed hi) yields 128 bits = five
- * 23-bit fields (bits [0,23), [23,46), ... of the little-endian 128-bit word);
- * draw t = 5j+f uses u = (field + 0.5) * 2^-23, scaled by the total mass
- * cdf[K-1]; class = first k with u*total < cdf[k] (cdf sequential in binary32),
- * else K-1. */
+ * The reference's draws are unseeded, so only the DISTRIBUTION is specified by
+ * it; this restates the product's sampler so its draws can be checked bit for
+ * bit.  Spec (all binary32, sequential):
+ *   uniforms: for anchor a of global image g, call j = 0,1,.. of Philox4x32-10
+ *     with counter (a, g, j, 0x0B0D) and key (seed lo, seed hi) yields 128 bits =
+ *     five 23-bit fields (bits [0,23), [23,46), .. of the little-endian word);
+ *     the i-th uniform of the anchor is (field_i + 0.5) * 2^-23, i = 5j + f.
+ *   cdf[k] = p[0]+..+p[k], total = cdf[K-1]; m = first argmax of p.
+ *   dominant-class split: a = p[m]/total, pw = a^T by square-and-multiply.
+ *   if pw >= 1e-30:  the number of draws NOT landing on m is Binomial(T, 1-a),
+ *       sampled by inversion from 0 upward with the first uniform
+ *       (f_0 = pw, f_{j+1} = f_j * ((T-j)/(j+1)) * ((total-p[m])/p[m]));
+ *       each of those draws then picks a class k != m with the next uniform u:
+ *       first k != m with u*(total-p[m]) < running sum of p over k != m
+ *       (last class != m as the fallback); cnt[m] = T - others.
+ *   else (flat distribution, a^T underflows): T plain inverse-cdf draws,
+ *       class = first k with u*total < cdf[k], else K-1.
+ * Both branches draw exactly Multinomial(T, p/total). */
+static float philox_uniform(uint32_t anchor, uint32_t image, const uint32_t key[2], uint32_t* w, int* g) {
+    const int f = *g % 5;
+    if (f == 0) {
+        uint32_t ctr[4] = {anchor, image, (uint32_t)(*g / 5), 0x0B0Du};
+        orc_philox4x32_10(ctr, key, w);
+    }
+    const int bit = 23 * f, wi = bit >> 5, sh = bit & 31;
+    const uint64_t two = (uint64_t)w[wi] | ((wi + 1 < 4) ? ((uint64_t)w[wi + 1] << 32) : 0);
+    const uint32_t field = (uint32_t)(two >> sh) & 0x7FFFFFu;
+    ++*g;
+    return ((float)field + 0.5f) * 1.1920928955078125e-07f;   /* 2^-23 */
+}
+
 void orc_philox_counts(const float* probs, int A, int K, int T, uint64_t seed,
                        uint32_t image_id, float* counts) {
-    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     float* cdf = (float*)malloc(sizeof(float) * (size_t)K);
     for (int a = 0; a < A; ++a) {
         const float* p = probs + (size_t)a * K;
         float* c = counts + (size_t)a * K;
         float s = 0.0f;
-        for (int k = 0; k < K; ++k) { s = s + p[k]; cdf[k] = s; c[k] = 0.0f; }
-        float total = cdf[K - 1];
-        int t = 0;
-        for (uint32_t j = 0; t < T; ++j) {
-            uint32_t ctr[4] = {(uint32_t)a, image_id, j, 0x0B0Du}, w[4];
-            orc_philox4x32_10(ctr, key, w);
-            for (int f = 0; f < 5 && t < T; ++f, ++t) {
-                int bit = 23 * f;
-                int wi = bit >> 5, sh = bit & 31;
-                uint64_t two = (uint64_t)w[wi] | ((wi + 1 < 4) ? ((uint64_t)w[wi + 1] << 32) : 0);
-                uint32_t field = (uint32_t)(two >> sh) & 0x7FFFFFu;
-                float u = ((float)field + 0.5f) * 1.1920928955078125e-07f; /* 2^-23 */
-                float x = u * total;
+        int m = 0;
+        for (int k = 0; k < K; ++k) { s = s + p[k]; cdf[k] = s; c[k] = 0.0f; if (p[k] > p[m]) m = k; }
+        const float total = cdf[K - 1];
+        const float pm = p[m], rest = total - pm;
+        const float aa = pm / total, odds = rest / pm;
+        float pw = 1.0f, base = aa;
+        for (int e = T; e; e >>= 1) { if (e & 1) pw = pw * base; base = base * base; }
+        uint32_t w[4]; int g = 0;
+        if (pw >= 1e-30f) {
+            const float u = philox_uniform((uint32_t)a, image_id, key, w, &g);
+            int j = 0;
+            float cd = pw, f = pw;
+            while (u >= cd && j < T) { f = f * ((float)(T - j) / (float)(j + 1)) * odds; ++j; cd = cd + f; }
+            c[m] = (float)(T - j);
+            const int last = (m == K - 1) ? K - 2 : K - 1;
+            for (int i = 0; i < j; ++i) {
+                const float x = philox_uniform((uint32_t)a, image_id, key, w, &g) * rest;
+                float acc = 0.0f;
+                int cls = last;
+                for (int k = 0; k < K; ++k) {
+                    if (k == m) continue;
+                    acc = acc + p[k];
+                    if (x < acc) { cls = k; break; }
+                }
+                c[cls] = c[cls] + 1.0f;
+            }
+        } else {
+            for (int t = 0; t < T; ++t) {
+                const float x = philox_uniform((uint32_t)a, image_id, key, w, &g) * total;
                 int cls = K - 1;
                 for (int k = 0; k < K - 1; ++k) if (x < cdf[k]) { cls = k; break; }
                 c[cls] = c[cls] + 1.0f;
