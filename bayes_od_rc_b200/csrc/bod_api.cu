@@ -142,7 +142,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     TAKE(stale, B * cap * 4);
     TAKE(cur, B * cap * 4);
     TAKE(begin, B * cap * 4);
-    TAKE(pend, B * cap * kMaskWords * 4);
+    TAKE(pend, B * cap * kPendStride * 4);
     TAKE(nms_idx, B * D * 4);
     TAKE(nms_score, B * D * 4);
     TAKE(centre_anchor, B * D * 4);
@@ -234,7 +234,7 @@ static int run_range(bod_ctx* c, int b0, int nb, const float* cls, const float* 
     K3Args k3{};
     k3.corners = k2.corners; k3.score = k2.score; k3.num_survivors = sc.num_survivors; k3.surv_anchor = k2.surv_anchor;
     k3.stale = c->stale + b0 * cap; k3.cur = c->cur + b0 * cap; k3.begin = c->begin + b0 * cap;
-    k3.pend = c->pend + b0 * cap * kMaskWords;
+    k3.pend = c->pend + b0 * cap * kPendStride;
     k3.nms_idx = c->nms_idx + b0 * D; k3.nms_score = c->nms_score + b0 * D; k3.centre_anchor = c->centre_anchor + b0 * D;
     k3.num_dets = c->num_dets + b0; k3.member = c->member + b0 * D * c->words;
     k3.B = nb; k3.capacity = c->capacity; k3.Dmax = c->Dmax; k3.words = c->words;

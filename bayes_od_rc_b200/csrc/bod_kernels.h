@@ -68,7 +68,7 @@ struct K3Args {
     float* stale;     // score as of the candidate's last queue update
     float* cur;       // up-to-date score
     int32_t* begin;   // suppress_begin_index
-    uint32_t* pend;   // [B,cap,kMaskWords] selected boxes with a non-unit weight
+    uint32_t* pend;   // [B,cap,kPendStride] pending-selection bitmask (generic) / weight cache (fast kernel)
     // outputs
     int32_t* nms_idx;           // [B,Dmax]
     float* nms_score;           // [B,Dmax]

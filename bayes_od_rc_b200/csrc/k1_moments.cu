@@ -10,12 +10,14 @@
 //
 // This is the only stage that must touch every anchor: it streams the whole
 // [B,N,A,K] logits tensor exactly once (4*N*A*K bytes per image), so it IS the
-// HBM roofline of the path.  Data movement: one CTA owns a tile of
-// kTileAnchors consecutive anchors of one image; for every MC sample the
-// tile's [tile,K] slab is a contiguous span of global memory that is bulk-copied
-// into shared memory by the TMA engine (cp.async.bulk + mbarrier, all N slabs in
-// flight at once), so no thread issues a load and rows of any K (8, 11, 4, ...)
-// are consumed conflict-free from shared memory.
+// HBM roofline of the path.  Data movement: the unit of work is a tile of
+// kTileAnchors consecutive anchors of one image; for every MC sample the tile's
+// [tile,K] slab is a contiguous span of global memory.  Persistent CTAs (two per
+// SM) walk the tiles; one producer thread per CTA bulk-copies slab after slab
+// into a ring of shared-memory stages with the TMA engine (cp.async.bulk +
+// full/empty mbarriers), running up to NSTAGE slabs ahead of the eight consumer
+// warps, so ~200 KB per SM are always in flight, no thread issues a global load
+// and rows of any K (8, 11, 4, ...) are consumed conflict-free from shared memory.
 #include "bod_common.cuh"
 #include "bod_kernels.h"
 
@@ -41,6 +43,12 @@ BOD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_LOOP;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+BOD_DEVINL void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+BOD_DEVINL void consumer_barrier() {   // named barrier 1: the kTileAnchors consumer threads only
+    asm volatile("bar.sync 1, %0;" ::"n"(kTileAnchors) : "memory");
 }
 BOD_DEVINL void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -283,6 +291,148 @@ k1_moments_kernel(K1Args a, int NC) {
     if (tid == 0) a.tile_count[(size_t)b * a.tiles + tile] = total;
 }
 
+// ---------------------------------------------------------------------------
+// persistent, warp-specialised pipeline (the production path)
+// ---------------------------------------------------------------------------
+constexpr int kMaxStages = 32;
+constexpr int kConsumerWarps = kTileAnchors / 32;
+
+template <int K>
+__global__ void __launch_bounds__(kTileAnchors + 32, 2)
+k1_moments_pipe_kernel(K1Args a, int NS) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+    __shared__ int warp_count[2][kConsumerWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = a.N, tiles = a.tiles;
+    const int total_tiles = a.B * tiles;
+    constexpr size_t slab_stride = (size_t)kTileAnchors * K;      // floats per stage
+    float* ring = reinterpret_cast<float*>(smem_raw);
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerWarps); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ---- producer: one thread feeds the ring, up to NS slabs ahead of the consumers ----
+        if (lane == 0) {
+            int stage = 0, round = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int b = t / tiles, tile = t - b * tiles;
+                const int a0 = tile * kTileAnchors;
+                const int rows = min(kTileAnchors, a.A - a0);
+                const uint32_t bytes = (uint32_t)rows * K * 4u;
+                const float* src = a.cls + ((size_t)b * N * a.A + a0) * K;
+                for (int n = 0; n < N; ++n) {
+                    if (round > 0) mbar_wait(&empty_bar[stage], (uint32_t)((round - 1) & 1));
+                    mbar_expect_tx(&full_bar[stage], bytes);
+                    bulk_g2s(ring + stage * slab_stride, src + (size_t)n * a.A * K, bytes, &full_bar[stage]);
+                    if (++stage == NS) { stage = 0; ++round; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: one thread per anchor of the tile ----
+    int stage = 0, phase = 0, tcount = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
+        const int b = t / tiles, tile = t - b * tiles;
+        const int a0 = tile * kTileAnchors;
+        const int rows = min(kTileAnchors, a.A - a0);
+        const int anchor = a0 + tid;
+        const bool valid = tid < rows;
+
+        float cnt[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) cnt[k] = 0.0f;
+        if (a.counts_in != nullptr && valid) {              // parity mode: counts to inject
+            const float* c = a.counts_in + ((size_t)b * a.A + anchor) * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) cnt[k] = __ldg(c + k);
+        }
+
+        // H2: softmax per sample, mean over samples (fast-math allowed here)
+        float p[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) p[k] = 0.0f;
+        for (int n = 0; n < N; ++n) {
+            mbar_wait(&full_bar[stage], (uint32_t)phase);
+            if (valid) {
+                const float* row = ring + stage * slab_stride + tid * K;
+                float x[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) x[k] = row[k];
+                float m = x[0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) m = fmaxf(m, x[k]);
+                float s = 0.0f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) { x[k] = __expf(x[k] - m); s += x[k]; }
+                const float inv = __frcp_rn(s);
+#pragma unroll
+                for (int k = 0; k < K; ++k) p[k] = __fmaf_rn(x[k], inv, p[k]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);   // this warp is done with the stage
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        if (valid) {
+            const float invN = 1.0f / (float)N;
+#pragma unroll
+            for (int k = 0; k < K; ++k) p[k] *= invN;
+            if (a.probs_out != nullptr) {
+                float* o = a.probs_out + ((size_t)b * a.A + anchor) * K;
+#pragma unroll
+                for (int k = 0; k < K; ++k) o[k] = p[k];
+            }
+        }
+
+        // H3: categorical draw counts
+        if (a.counts_in == nullptr && valid) {
+            philox_counts<K>(p, (uint32_t)anchor, a.image_id_base + (uint32_t)b,
+                             make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws, cnt);
+            if (a.sampled_out != nullptr) {
+                float* o = a.sampled_out + ((size_t)b * a.A + anchor) * K;
+#pragma unroll
+                for (int k = 0; k < K; ++k) o[k] = cnt[k];
+            }
+        }
+
+        // H4: first-maximum argmax != background, stable compaction inside the tile
+        bool keep = false;
+        if (valid) {
+            int am = 0;
+            float best = cnt[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k) if (cnt[k] > best) { best = cnt[k]; am = k; }
+            keep = (am != K - 1);
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        int* wc = warp_count[tcount & 1];                    // double-buffered: one barrier per tile
+        if (lane == 0) wc[warp] = __popc(ballot);
+        consumer_barrier();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) {
+            const int c = wc[w];
+            base += (w < warp) ? c : 0;
+            total += c;
+        }
+        if (keep) {
+            const int slot = a0 + base + __popc(ballot & ((1u << lane) - 1u));   // per-tile slot region
+            a.slot_anchor[(size_t)b * a.A + slot] = anchor;
+            float* o = a.slot_counts + ((size_t)b * a.A + slot) * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) o[k] = cnt[k];
+        }
+        if (tid == 0) a.tile_count[(size_t)b * tiles + tile] = total;
+    }
+}
+
 template <int K>
 static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     // samples per ring stage: two stages of <= ~50 KB keep two CTAs resident per SM
@@ -297,9 +447,19 @@ static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     dim3 grid(a.tiles, a.B), block(kTileAnchors);
     cudaError_t e;
     if (aligned) {
-        e = cudaFuncSetAttribute(k1_moments_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // persistent pipeline: two CTAs per SM, each with a ring of NS one-sample slabs (<= ~100 KB)
+        int NS = (int)((100u * 1024u) / slab);
+        if (NS > kMaxStages) NS = kMaxStages;
+        if (NS < 2) NS = 2;
+        const size_t ring = (size_t)NS * slab;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int ctas = 2 * sms;
+        if (ctas > a.B * a.tiles) ctas = a.B * a.tiles;
+        e = cudaFuncSetAttribute(k1_moments_pipe_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
         if (e != cudaSuccess) return e;
-        k1_moments_kernel<K, true><<<grid, block, smem, st>>>(a, NC);
+        k1_moments_pipe_kernel<K><<<ctas, kTileAnchors + 32, ring, st>>>(a, NS);
     } else {
         e = cudaFuncSetAttribute(k1_moments_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -38,7 +38,7 @@
 namespace bod {
 
 constexpr int kK3Threads = 512;
-constexpr int kFastS = 10240;         // candidates the shared-memory kernel holds
+constexpr int kFastS = 8192;          // candidates the shared-memory kernel holds
 constexpr int kListMax = 3072;        // compacted overlap list (uint16 indices)
 
 BOD_DEVINL unsigned long long make_key(float score, int idx) {
@@ -77,7 +77,7 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
     float* stale = a.stale + (size_t)b * a.capacity;
     float* cur = a.cur + (size_t)b * a.capacity;
     int32_t* begin = a.begin + (size_t)b * a.capacity;
-    uint32_t* pend = a.pend + (size_t)b * a.capacity * kMaskWords;
+    uint32_t* pend = a.pend + (size_t)b * a.capacity * kPendStride;
     uint32_t* member = a.member + (size_t)b * Dmax * a.words;
     const bool is_soft = a.soft_nms_sigma > 0.0f;
     const float scale = is_soft ? -0.5f / a.soft_nms_sigma : 0.0f;
@@ -89,7 +89,7 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
         stale[s] = sc;
         begin[s] = 0;
 #pragma unroll
-        for (int w = 0; w < kMaskWords; ++w) pend[(size_t)s * kMaskWords + w] = 0u;
+        for (int w = 0; w < kMaskWords; ++w) pend[(size_t)s * kPendStride + w] = 0u;
         const bool in_queue = sc > -INFINITY;        // scores_data[i] > score_threshold (-inf): NaN stays out
         cur[s] = in_queue ? sc : -INFINITY;          // -inf is never enqueued => usable as "not in queue"
         if (in_queue) { const unsigned long long k = make_key(sc, s); best = k > best ? k : best; }
@@ -134,7 +134,7 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
                         const float sim = tf_iou(bs, bx);
                         const float w = nms_weight(sim, scale, is_soft, thr);
                         if (w != 1.0f) {
-                            uint32_t* pm = pend + (size_t)s * kMaskWords;
+                            uint32_t* pm = pend + (size_t)s * kPendStride;
                             pm[r >> 5] |= 1u << (r & 31);
                             const int bg = begin[s];
                             float v = t;
@@ -164,8 +164,10 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
 }
 
 // ---------------------------------------------------------------------------
-// fast kernel
+// fast kernel: all per-candidate state that a round touches lives in shared memory
 // ---------------------------------------------------------------------------
+constexpr int kWCache = kPendStride; // cached non-unit weights per candidate (global, L2 resident)
+
 struct K3Smem {
     unsigned long long best[2];
     unsigned long long warp_best[2][32];
@@ -182,35 +184,38 @@ k3_softnms_kernel(K3Args a, int smem_S) {
     const int S = a.num_survivors[b];
     if (S > smem_S) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
 
-    float4* corn = reinterpret_cast<float4*>(dyn);                       // [smem_S]
+    const int W = smem_S / 32;                                           // words per bit row
+    float4* corn = reinterpret_cast<float4*>(dyn);                       // [smem_S] corners
     float* ucur = reinterpret_cast<float*>(corn + smem_S);               // [smem_S] up-to-date score, -inf = not queued
-    uint32_t* dirty = reinterpret_cast<uint32_t*>(ucur + smem_S);        // [smem_S/32] u != stale
-    uint32_t* touched = dirty + smem_S / 32;                             // [smem_S/32] pend[] initialised
-    uint16_t* list = reinterpret_cast<uint16_t*>(touched + smem_S / 32); // [kListMax]
+    float* stl = ucur + smem_S;                                          // [smem_S] score as of the last queue update
+    uint32_t* dirty = reinterpret_cast<uint32_t*>(stl + smem_S);         // [W] u != stale
+    uint32_t* mrow = dirty + W;                                          // [2][W] membership row being built
+    uint16_t* list = reinterpret_cast<uint16_t*>(mrow + 2 * W);          // [kListMax] overlapping candidates
+    uint8_t* beg = reinterpret_cast<uint8_t*>(list + kListMax);          // [smem_S] suppress_begin_index
+    uint8_t* nw = beg + smem_S;                                          // [smem_S] cached weights since `beg`
 
     const int Dmax = a.Dmax;
     const float4* corners = a.corners + (size_t)b * a.capacity;
     const float* score = a.score + (size_t)b * a.capacity;
-    float* stale = a.stale + (size_t)b * a.capacity;
-    int32_t* begin = a.begin + (size_t)b * a.capacity;
-    uint32_t* pend = a.pend + (size_t)b * a.capacity * kMaskWords;
+    // weight cache: weights of the selections in [beg, now) with a non-unit weight, oldest first
+    float* wcache = reinterpret_cast<float*>(a.pend) + (size_t)b * a.capacity * kPendStride;
     uint32_t* member = a.member + (size_t)b * Dmax * a.words;
     const bool is_soft = a.soft_nms_sigma > 0.0f;
     const float scale = is_soft ? -0.5f / a.soft_nms_sigma : 0.0f;
     const float thr = a.iou_threshold;
-    const int S32 = (S + 31) & ~31;
+    const int S32 = (S + 31) & ~31, nwords = S32 >> 5;
 
     // ---- load ----
     if (tid == 0) { sm.best[0] = sm.best[1] = 0ull; sm.list_n[0] = sm.list_n[1] = 0; }
-    for (int w = tid; w < (S32 >> 5); w += kK3Threads) { dirty[w] = 0u; touched[w] = 0u; }
+    for (int w = tid; w < nwords; w += kK3Threads) { dirty[w] = 0u; mrow[w] = 0u; mrow[W + w] = 0u; }
     unsigned long long best = 0ull;
     for (int s = tid; s < S; s += kK3Threads) {
         corn[s] = corners[s];
         const float sc = score[s];
         const bool in_queue = sc > -INFINITY;         // scores_data[i] > score_threshold (-inf); NaN stays out
         ucur[s] = in_queue ? sc : -INFINITY;
-        stale[s] = sc;
-        begin[s] = 0;
+        stl[s] = sc;
+        beg[s] = 0; nw[s] = 0;
         if (in_queue) { const unsigned long long k = make_key(sc, s); best = k > best ? k : best; }
     }
     __syncthreads();                                   // sm.best initialised before the atomics below
@@ -219,38 +224,47 @@ k3_softnms_kernel(K3Args a, int smem_S) {
     __syncthreads();
 
     // the slow part of a round, for one candidate s that (possibly) overlaps the new centre
-    auto process = [&](int s, int r, const float4 bx, unsigned long long* next_best) {
+    auto process = [&](int s, int r, const float4 bx, uint32_t* mr, unsigned long long* next_best) {
         const float4 bs = corn[s];
-        if (repo_iou(bs, bx) > thr)                                            // :316, strict >
-            atomicOr(&member[(size_t)r * a.words + (s >> 5)], 1u << (s & 31));
-        float u = ucur[s];
-        if (!(u > -INFINITY)) return;                                          // selected earlier / never queued
+        const float u0 = ucur[s];
+        const int n = nw[s];
+        // prefetch the cached weights while the IoUs and the exp are computed
+        float wc[kWCache] = {};
+        const float4* wp = reinterpret_cast<const float4*>(wcache + (size_t)s * kWCache);
+        if (u0 > -INFINITY && n > 0) {
+#pragma unroll
+            for (int q = 0; q < kWCache / 4; ++q) {
+                const float4 v = (4 * q < n) ? __ldcg(wp + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+                wc[4 * q] = v.x; wc[4 * q + 1] = v.y; wc[4 * q + 2] = v.z; wc[4 * q + 3] = v.w;
+            }
+        }
+        if (repo_iou(bs, bx) > thr) atomicOr(&mr[s >> 5], 1u << (s & 31));       // :316, strict >
+        if (!(u0 > -INFINITY)) return;                                            // selected earlier / never queued
         const float sim = tf_iou(bs, bx);
         const float w = nms_weight(sim, scale, is_soft, thr);
+        float u = u0;
         if (w != 1.0f) {
-            uint32_t* pm = pend + (size_t)s * kMaskWords;
-            const uint32_t bit = 1u << (s & 31);
-            if (!(touched[s >> 5] & bit)) {
+            // u = stale * w * (cached weights, newest first)
+            float v = stl[s] * w;
+            if (n < kWCache) {
 #pragma unroll
-                for (int q = 0; q < kMaskWords; ++q) pm[q] = 0u;
-                atomicOr(&touched[s >> 5], bit);
-            }
-            pm[r >> 5] |= 1u << (r & 31);
-            const int bg = begin[s];
-            float v = stale[s];
-            for (int q = r >> 5; q >= (bg >> 5); --q) {                        // pending selections, newest first
-                uint32_t bits = pm[q];
-                if (q == (bg >> 5)) bits &= ~((1u << (bg & 31)) - 1u);
-                while (bits) {
-                    const int j = (q << 5) + 31 - __clz(bits);
-                    bits &= ~(1u << (j & 31));
+                for (int q = kWCache - 1; q >= 0; --q) if (q < n) v = v * wc[q];
+                wcache[(size_t)s * kWCache + n] = w;
+                nw[s] = (uint8_t)(n + 1);
+            } else {
+                // cache full (more than kWCache overlapping centres since the last update): recompute
+                // every weight from the selected boxes; slot kWCache-1.. are not stored any more
+                v = stl[s];
+                for (int j = r; j >= (int)beg[s]; --j) {
                     const float sj = (j == r) ? sim : tf_iou(bs, sm.sel_box[j]);
-                    v = v * nms_weight(sj, scale, is_soft, thr);
+                    const float wj = nms_weight(sj, scale, is_soft, thr);
+                    if (wj != 1.0f) v = v * wj;
                 }
+                nw[s] = (uint8_t)kWCache;                                          // stays in overflow mode
             }
-            u = (!is_soft && w == 0.0f) ? -INFINITY : v;                       // hard-NMS: removed for good
+            u = (!is_soft && w == 0.0f) ? -INFINITY : v;                           // hard-NMS: removed for good
             ucur[s] = u;
-            atomicOr(&dirty[s >> 5], bit);
+            atomicOr(&dirty[s >> 5], 1u << (s & 31));
         }
         if (u > -INFINITY) atomicMax(next_best, make_key(u, s));
     };
@@ -259,9 +273,10 @@ k3_softnms_kernel(K3Args a, int smem_S) {
     for (; r < Dmax; ++r) {
         const int cur_buf = r & 1, nxt_buf = cur_buf ^ 1;
         const unsigned long long kx = sm.best[cur_buf];
-        if (kx == 0ull) break;                                                 // queue empty
+        if (kx == 0ull) break;                                                     // queue empty
         const int x = key_index(kx);
         const float4 bx = corn[x];
+        uint32_t* mr = mrow + cur_buf * W;
         if (tid == 0) {
             sm.sel_box[r] = bx;
             sm.list_n[nxt_buf] = 0;        // last round's list: everyone finished reading it before the barrier
@@ -269,10 +284,16 @@ k3_softnms_kernel(K3Args a, int smem_S) {
             a.nms_score[(size_t)b * Dmax + r] = key_score(kx);
             a.centre_anchor[(size_t)b * Dmax + r] = a.surv_anchor[(size_t)b * a.capacity + x];
         }
+        // flush the membership row of the previous round, then clear it for round r+1
+        if (r > 0) {
+            uint32_t* pr = mrow + nxt_buf * W;
+            for (int w = tid; w < nwords; w += kK3Threads) { member[(size_t)(r - 1) * a.words + w] = pr[w]; pr[w] = 0u; }
+        }
         const bool bx_ok = (bx.x <= bx.z) && (bx.y <= bx.w);
 
         // ---- pass A: overlap tests, commits, arg-max of the untouched candidates ----
         best = 0ull;
+#pragma unroll 2
         for (int s = tid; s < S32; s += kK3Threads) {
             bool maybe = false, inline_it = false;
             uint32_t clear = 0u;
@@ -288,19 +309,16 @@ k3_softnms_kernel(K3Args a, int smem_S) {
                 const bool wellformed = bx_ok && (bs.x <= bs.z) && (bs.y <= bs.w);
                 maybe = !wellformed || (((xI2 - xI1) + 1.0f > 0.0f) && ((yI2 - yI1) + 1.0f > 0.0f));
                 if (in_queue && ((dirty[s >> 5] >> (s & 31)) & 1u)) {
-                    if (make_key(stale[s], s) > kx) {                          // TF popped it before x: update is final
-                        stale[s] = u; begin[s] = r; clear = 1u;
+                    if (make_key(stl[s], s) > kx) {                                // TF popped it before x: update is final
+                        stl[s] = u; beg[s] = (uint8_t)r; nw[s] = 0; clear = 1u;
                     }
                 }
                 if (in_queue && !maybe) { const unsigned long long k = make_key(u, s); best = k > best ? k : best; }
             }
-            // this warp owns word s>>5 of `dirty` and of the member row during pass A
+            // this warp owns word s>>5 of `dirty` during pass A
             const unsigned clr = __ballot_sync(0xffffffffu, clear);
             const unsigned bal = __ballot_sync(0xffffffffu, maybe);
-            if (lane == 0) {
-                if (clr) dirty[s >> 5] &= ~clr;
-                member[(size_t)r * a.words + (s >> 5)] = 0u;
-            }
+            if (clr && lane == 0) dirty[s >> 5] &= ~clr;
             if (bal) {
                 int base = 0;
                 const int leader = __ffs(bal) - 1;
@@ -308,9 +326,9 @@ k3_softnms_kernel(K3Args a, int smem_S) {
                 base = __shfl_sync(0xffffffffu, base, leader);
                 const int pos = base + __popc(bal & ((1u << lane) - 1u));
                 if (maybe) { if (pos < kListMax) list[pos] = (uint16_t)s; else inline_it = true; }
-                if (__any_sync(0xffffffffu, inline_it)) {                      // list overflow: handle in place
+                if (__any_sync(0xffffffffu, inline_it)) {                          // list overflow: handle in place
                     __syncwarp();
-                    if (inline_it) process(s, r, bx, &sm.best[nxt_buf]);
+                    if (inline_it) process(s, r, bx, mr, &sm.best[nxt_buf]);
                 }
             }
         }
@@ -321,8 +339,13 @@ k3_softnms_kernel(K3Args a, int smem_S) {
         // ---- pass B: the compacted overlapping candidates ----
         if (tid == 0) sm.best[cur_buf] = 0ull;      // every thread has read kx; refilled from the next round's pass A on
         const int n = min(sm.list_n[cur_buf], kListMax);
-        for (int e = tid; e < n; e += kK3Threads) process((int)list[e], r, bx, &sm.best[nxt_buf]);
+        for (int e = tid; e < n; e += kK3Threads) process((int)list[e], r, bx, mr, &sm.best[nxt_buf]);
         __syncthreads();
+    }
+    // flush the last membership row
+    if (r > 0) {
+        const uint32_t* pr = mrow + ((r - 1) & 1) * W;
+        for (int w = tid; w < nwords; w += kK3Threads) member[(size_t)(r - 1) * a.words + w] = pr[w];
     }
     if (tid == 0) a.num_dets[b] = r;
     for (int d = r + tid; d < Dmax; d += kK3Threads) {       // padding rows
@@ -335,7 +358,7 @@ k3_softnms_kernel(K3Args a, int smem_S) {
 cudaError_t launch_k3(const K3Args& a, cudaStream_t st) {
     int smem_S = a.capacity < kFastS ? a.capacity : kFastS;
     smem_S = (smem_S + 31) & ~31;
-    const size_t smem = (size_t)smem_S * (16 + 4) + (size_t)(smem_S / 32) * 8 + (size_t)kListMax * 2;
+    const size_t smem = (size_t)smem_S * (16 + 4 + 4 + 1 + 1) + (size_t)(smem_S / 32) * 12 + (size_t)kListMax * 2;
     cudaError_t e = cudaFuncSetAttribute(k3_softnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k3_softnms_kernel<<<a.B, kK3Threads, smem, st>>>(a, smem_S);
