@@ -32,6 +32,7 @@ struct bod_ctx {
     float* score = nullptr; float4* corners = nullptr; float* info = nullptr;
     // K3 scratch + outputs
     float* stale = nullptr; float* cur = nullptr; int32_t* begin = nullptr; uint32_t* pend = nullptr;
+    float* pw = nullptr; uint8_t* pj = nullptr; int fastS = 0, pstride = 0;
     int32_t* nms_idx = nullptr; float* nms_score = nullptr; int32_t* centre_anchor = nullptr; int32_t* num_dets = nullptr;
     uint32_t* member = nullptr;
     // K4 outputs
@@ -48,6 +49,8 @@ struct bod_ctx {
     cudaEvent_t ev_copy[4] = {nullptr};
     bool ran = false, used_sampler = false, timing = true, last_timed = false;
     int launches = 0;
+    int k1_debug = 0;                 // BOD_K1_DEBUG (diagnostics)
+    long long* k3_dbg = nullptr;      // BOD_K3_DEBUG (diagnostics): [B][8] cycle counters
 };
 
 static int fail(bod_ctx* c, int code, const char* fmt, ...) {
@@ -99,7 +102,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     if (cfg->N < 2) return bad("N (mc_dropout_samples) must be >= 2: the sample covariance divides by N-1");
     if (cfg->A < 1) return bad("A must be positive");
     if (!k1_supports(cfg->K)) return bad("unsupported K (classes + background)");
-    if (cfg->max_output_size < 1 || cfg->max_output_size > kMaxOut) return bad("max_output_size must be in [1,256]");
+    if (cfg->max_output_size < 1 || cfg->max_output_size > 255) return bad("max_output_size must be in [1,255]");
     if (cfg->cov_layout < 0 || cfg->cov_layout > 2) return bad("bad cov_layout");
     if (!(cfg->iou_threshold >= 0.0f)) return bad("iou_threshold must be >= 0");
     if (!(cfg->soft_nms_sigma >= 0.0f)) return bad("soft_nms_sigma must be >= 0");
@@ -143,6 +146,10 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     TAKE(cur, B * cap * 4);
     TAKE(begin, B * cap * 4);
     TAKE(pend, B * cap * kPendStride * 4);
+    c->fastS = k3_fast_capacity(c->capacity);
+    c->pstride = (c->Dmax + 3) & ~3;
+    TAKE(pw, (size_t)B * c->fastS * c->pstride * 4);
+    TAKE(pj, (size_t)B * c->fastS * c->pstride);
     TAKE(nms_idx, B * D * 4);
     TAKE(nms_score, B * D * 4);
     TAKE(centre_anchor, B * D * 4);
@@ -166,6 +173,8 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     for (auto& set : c->evring) for (auto& ev : set) cudaEventCreate(&ev);
     for (auto& ev : c->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
+    if (const char* d = getenv("BOD_K1_DEBUG")) c->k1_debug = atoi(d);
+    if (getenv("BOD_K3_DEBUG")) { cudaMalloc(&c->k3_dbg, (size_t)B * 8 * sizeof(long long)); cudaMemset(c->k3_dbg, 0, (size_t)B * 8 * sizeof(long long)); }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { snprintf(create_err, sizeof create_err, "init: %s", cudaGetErrorString(e)); bod_destroy(c); return BOD_ERR_CUDA; }
     *out = c;
@@ -201,6 +210,7 @@ static int run_range(bod_ctx* c, int b0, int nb, const float* cls, const float* 
     k1.tile_count = c->tile_count + (size_t)b0 * c->tiles;
     k1.B = nb; k1.N = g.N; k1.A = g.A; k1.K = g.K; k1.tiles = c->tiles;
     k1.num_draws = g.num_draws; k1.seed = g.seed; k1.image_id_base = g.image_id_base + (uint32_t)b0;
+    k1.debug = c->k1_debug;
     CU(c, launch_k1(k1, st));
     if (record) CU(c, cudaEventRecord(c->ev[1], st));
 
@@ -235,10 +245,13 @@ static int run_range(bod_ctx* c, int b0, int nb, const float* cls, const float* 
     k3.corners = k2.corners; k3.score = k2.score; k3.num_survivors = sc.num_survivors; k3.surv_anchor = k2.surv_anchor;
     k3.stale = c->stale + b0 * cap; k3.cur = c->cur + b0 * cap; k3.begin = c->begin + b0 * cap;
     k3.pend = c->pend + b0 * cap * kPendStride;
+    k3.pw = c->pw + (size_t)b0 * c->fastS * c->pstride; k3.pj = c->pj + (size_t)b0 * c->fastS * c->pstride;
+    k3.fastS = c->fastS; k3.pstride = c->pstride;
     k3.nms_idx = c->nms_idx + b0 * D; k3.nms_score = c->nms_score + b0 * D; k3.centre_anchor = c->centre_anchor + b0 * D;
     k3.num_dets = c->num_dets + b0; k3.member = c->member + b0 * D * c->words;
     k3.B = nb; k3.capacity = c->capacity; k3.Dmax = c->Dmax; k3.words = c->words;
     k3.iou_threshold = g.iou_threshold; k3.soft_nms_sigma = g.soft_nms_sigma;
+    k3.dbg = c->k3_dbg ? c->k3_dbg + (size_t)b0 * 8 : nullptr;
     CU(c, launch_k3(k3, st));
     if (record) CU(c, cudaEventRecord(c->ev[4], st));
 
@@ -383,6 +396,15 @@ extern "C" int bod_fetch_sampled_counts(bod_ctx* c, int32_t b, float* counts) {
     if (rc) return rc;
     const size_t n = (size_t)c->cfg.A * c->cfg.K;
     CU(c, cudaMemcpy(counts, c->sampled + b * n, n * 4, cudaMemcpyDeviceToHost));
+    return BOD_OK;
+}
+
+// diagnostics (not part of the public header): per-image soft-NMS phase cycle counters
+extern "C" int bod_debug_k3_counters(bod_ctx* c, long long* out) {
+    if (!c || !out || !c->k3_dbg) return BOD_ERR_STATE;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    CU(c, cudaMemcpy(out, c->k3_dbg, (size_t)c->cfg.B * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return BOD_OK;
 }
 

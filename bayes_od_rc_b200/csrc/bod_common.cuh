@@ -19,7 +19,7 @@ constexpr int kTileAnchors = 256;   // anchors per moments-kernel tile (and per 
 constexpr int kMaxK = 64;           // classes + background supported
 constexpr int kMaxOut = 256;        // max_output_size supported (selected-mask words = 8)
 constexpr int kMaskWords = kMaxOut / 32;
-constexpr int kPendStride = 16;     // 32-bit words of soft-NMS scratch per candidate (bitmask or weight cache)
+constexpr int kPendStride = 8;      // 32-bit words of soft-NMS scratch per candidate (generic kernel bitmask)
 
 // ---------------------------------------------------------------------------
 // correctly rounded binary32 exp / log (via binary64; 1 ulp of binary64 error

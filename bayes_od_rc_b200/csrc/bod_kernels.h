@@ -18,6 +18,7 @@ struct K1Args {
     int num_draws;
     uint64_t seed;
     uint32_t image_id_base;
+    int debug;               // diagnostics only: 1 = skip sampler/compaction, 2 = also skip the softmax
 };
 cudaError_t launch_k1(const K1Args& a, cudaStream_t st);
 bool k1_supports(int K);
@@ -68,7 +69,10 @@ struct K3Args {
     float* stale;     // score as of the candidate's last queue update
     float* cur;       // up-to-date score
     int32_t* begin;   // suppress_begin_index
-    uint32_t* pend;   // [B,cap,kPendStride] pending-selection bitmask (generic) / weight cache (fast kernel)
+    uint32_t* pend;   // [B,cap,kPendStride] pending-selection bitmask (generic kernel)
+    float* pw;        // [B,fastS,pstride] pending soft-NMS weights per candidate (fast kernel)
+    uint8_t* pj;      // [B,fastS,pstride] their selection indices
+    int fastS, pstride;
     // outputs
     int32_t* nms_idx;           // [B,Dmax]
     float* nms_score;           // [B,Dmax]
@@ -77,8 +81,10 @@ struct K3Args {
     uint32_t* member;           // [B,Dmax,words]
     int B, capacity, Dmax, words;
     float iou_threshold, soft_nms_sigma;
+    long long* dbg;             // diagnostics: [B][8] cycle counters per phase, or nullptr
 };
 cudaError_t launch_k3(const K3Args& a, cudaStream_t st);
+int k3_fast_capacity(int capacity);   // candidates the shared-memory soft-NMS kernel holds for this capacity
 
 // ---- K4: per-cluster Bayesian fusion ----------------------------------------
 struct K4Args {

@@ -88,9 +88,15 @@ struct PhiloxStream {
     }
 };
 
+// Returns false when the anchor is known to be background-dominant without the
+// per-class counts (only possible with `need_counts` false): the dominant class
+// is the background column and it received more than half of the draws, so the
+// first-maximum argmax (inference_utils.py:48-51) is the background and the
+// anchor is dropped; its counts are never read again.  Otherwise cnt[] holds the
+// full multinomial counts.
 template <int K>
-BOD_DEVINL void philox_counts(const float (&p)[K], uint32_t anchor, uint32_t image, uint2 key, int T,
-                              float (&cnt)[K]) {
+BOD_DEVINL bool philox_counts(const float (&p)[K], uint32_t anchor, uint32_t image, uint2 key, int T,
+                              bool need_counts, float (&cnt)[K]) {
     float cdf[K];
     float s = 0.0f, pm = p[0];
     int m = 0;
@@ -114,6 +120,7 @@ BOD_DEVINL void philox_counts(const float (&p)[K], uint32_t anchor, uint32_t ima
             ++j;
             cd = __fadd_rn(cd, f);
         }
+        if (!need_counts && m == K - 1 && 2 * j < T) return false;     // background keeps a strict majority
         // running sums of p over the classes != m (adding 0 for m is exact)
         float acc[K];
         float t = 0.0f;
@@ -141,6 +148,7 @@ BOD_DEVINL void philox_counts(const float (&p)[K], uint32_t anchor, uint32_t ima
             for (int k = 0; k < K; ++k) cnt[k] = __fadd_rn(cnt[k], (c == k) ? 1.0f : 0.0f);
         }
     }
+    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -251,9 +259,11 @@ k1_moments_kernel(K1Args a, int NC) {
     }
 
     // H3: categorical draw counts
+    bool maybe_fg = true;
     if (a.counts_in == nullptr && valid) {
-        philox_counts<K>(p, (uint32_t)anchor, a.image_id_base + (uint32_t)b,
-                         make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws, cnt);
+        maybe_fg = philox_counts<K>(p, (uint32_t)anchor, a.image_id_base + (uint32_t)b,
+                                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws,
+                                        a.sampled_out != nullptr, cnt);
         if (a.sampled_out != nullptr) {
             float* o = a.sampled_out + ((size_t)b * a.A + anchor) * K;
 #pragma unroll
@@ -263,7 +273,7 @@ k1_moments_kernel(K1Args a, int NC) {
 
     // H4: first-maximum argmax != background, stable compaction inside the tile
     bool keep = false;
-    if (valid) {
+    if (valid && maybe_fg) {
         int am = 0;
         float best = cnt[0];
 #pragma unroll
@@ -297,8 +307,10 @@ k1_moments_kernel(K1Args a, int NC) {
 constexpr int kMaxStages = 32;
 constexpr int kConsumerWarps = kTileAnchors / 32;
 
+constexpr int kPipeCtasPerSM = 3;   // resident CTAs per SM: their finalise phases overlap each other's streaming
+
 template <int K>
-__global__ void __launch_bounds__(kTileAnchors + 32, 2)
+__global__ void __launch_bounds__(kTileAnchors + 32, kPipeCtasPerSM)
 k1_moments_pipe_kernel(K1Args a, int NS) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
@@ -361,7 +373,7 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
         for (int k = 0; k < K; ++k) p[k] = 0.0f;
         for (int n = 0; n < N; ++n) {
             mbar_wait(&full_bar[stage], (uint32_t)phase);
-            if (valid) {
+            if (valid && a.debug < 2) {
                 const float* row = ring + stage * slab_stride + tid * K;
                 float x[K];
 #pragma unroll
@@ -391,10 +403,17 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
             }
         }
 
+        if (a.debug >= 1) {                                  // diagnostics: data movement (+ softmax) only
+            if (valid && p[0] == 12345.0f) a.slot_anchor[0] = 1;
+            continue;
+        }
+
         // H3: categorical draw counts
+        bool maybe_fg = true;
         if (a.counts_in == nullptr && valid) {
-            philox_counts<K>(p, (uint32_t)anchor, a.image_id_base + (uint32_t)b,
-                             make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws, cnt);
+            maybe_fg = philox_counts<K>(p, (uint32_t)anchor, a.image_id_base + (uint32_t)b,
+                                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws,
+                                        a.sampled_out != nullptr, cnt);
             if (a.sampled_out != nullptr) {
                 float* o = a.sampled_out + ((size_t)b * a.A + anchor) * K;
 #pragma unroll
@@ -404,7 +423,7 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
 
         // H4: first-maximum argmax != background, stable compaction inside the tile
         bool keep = false;
-        if (valid) {
+        if (valid && maybe_fg) {
             int am = 0;
             float best = cnt[0];
 #pragma unroll
@@ -447,15 +466,15 @@ static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     dim3 grid(a.tiles, a.B), block(kTileAnchors);
     cudaError_t e;
     if (aligned) {
-        // persistent pipeline: two CTAs per SM, each with a ring of NS one-sample slabs (<= ~100 KB)
-        int NS = (int)((100u * 1024u) / slab);
+        // persistent pipeline: kPipeCtasPerSM CTAs per SM, each with a ring of NS one-sample slabs
+        int NS = (int)(((216u * 1024u) / kPipeCtasPerSM - 1024u) / slab);
         if (NS > kMaxStages) NS = kMaxStages;
         if (NS < 2) NS = 2;
         const size_t ring = (size_t)NS * slab;
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int ctas = 2 * sms;
+        int ctas = kPipeCtasPerSM * sms;
         if (ctas > a.B * a.tiles) ctas = a.B * a.tiles;
         e = cudaFuncSetAttribute(k1_moments_pipe_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
         if (e != cudaSuccess) return e;

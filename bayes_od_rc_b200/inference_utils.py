@@ -165,7 +165,7 @@ def bayes_od_clustering(predicted_boxes_class_counts, predicted_boxes_means, pre
     counts = np.ascontiguousarray(predicted_boxes_class_counts, np.float32)
     S, K = counts.shape
     centres = np.asarray(cluster_centers, np.int32).reshape(-1)
-    cfg = BayesODConfig(max_output_size=256)
+    cfg = BayesODConfig(max_output_size=255)
     cap = 1 << max(5, int(np.ceil(np.log2(max(S, 1)))))        # bucket the capacity: few distinct workspaces
     eng = _engine(1, 2, cap, K, cfg)
     return eng.cluster_host(counts, predicted_boxes_means, predicted_boxes_covs, centres, affinity_matrix,

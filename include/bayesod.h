@@ -68,7 +68,7 @@ typedef struct bod_config {
     int32_t  gaussian_prior;     /* bayes_od_config.gaussian_prior.type                    */
     float    isotropic_variance; /* bayes_od_config.gaussian_prior.isotropic_variance      */
     int32_t  ranking_method;     /* bayes_od_config.ranking_method                         */
-    int32_t  max_output_size;    /* nms_config.max_output_size (<= 256)                    */
+    int32_t  max_output_size;    /* nms_config.max_output_size (<= 255)                    */
     float    iou_threshold;      /* nms_config.iou_threshold; also the affinity threshold
                                     of bayes_od_clustering (run_inference.py:149)          */
     float    soft_nms_sigma;     /* nms_config.soft_nms_sigma                              */

@@ -60,6 +60,12 @@ CONFIGS = {
                       dict(ranking_method="joint_entropy"), 2),
     "no_gaussian_prior": (dict(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=36),
                           dict(gaussian_prior="None"), 1),
+    # one big object: every survivor overlaps every other one, so soft-NMS candidates pile up dozens of
+    # pending weights (exercises the replay of lazy commits and the pending-list overflow path)
+    "dense_cluster": (dict(im_h=96, im_w=160, N=6, K=8, g_min=1, g_max=1, box_lo=70., box_hi=90., fg_iou=0.25, config_id=38),
+                      dict(), 3),
+    "dense_cluster_sigma": (dict(im_h=96, im_w=160, N=6, K=8, g_min=2, g_max=2, box_lo=60., box_hi=90., fg_iou=0.25, config_id=39),
+                            dict(soft_nms_sigma=0.3, max_output_size=200), 2),
     "odd_A_k7": (dict(im_h=70, im_w=90, N=5, K=7, g_min=3, g_max=4, box_hi=60., config_id=37), dict(), 2),
 }
 
@@ -118,6 +124,20 @@ def test_philox_sampler_matches_restatement():
         # and the rest of the path on those counts is bit-exact again
         r = oracle.run_image(oc, batch["cls"][b], batch["box"][b], batch["cov"][b], batch["anchors"], c)
         compare_image_with_oracle(eng, res, b, r, spec.K)
+
+
+def test_sampler_fast_path_equals_full_counts():
+    """Without emit_probs the sampler skips the per-class draws of background-majority anchors;
+    the survivors and everything downstream must not change."""
+    spec = synthetic.SceneSpec(im_h=192, im_w=320, N=10, K=11, g_min=6, g_max=10, box_hi=150., config_id=44)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, 3, with_counts=False))
+    oc = oracle.OracleConfig(seed=7)
+    _, res_full = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], None, emit_probs=True)
+    _, res_fast = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], None, emit_probs=False)
+    assert res_full.num_survivors.min() > 50
+    for k in ("num_dets", "num_survivors", "means", "covs", "cat_param", "cat_count", "nms_indices", "centre_anchor_idx",
+              "centre_scores"):
+        assert_bit_equal(getattr(res_fast, k), getattr(res_full, k), k)
 
 
 def test_generated_anchors_bit_exact():
