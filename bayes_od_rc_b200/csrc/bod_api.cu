@@ -264,7 +264,7 @@ static int run_range(bod_ctx* c, int b0, int nb, const float* cls, const float* 
     k4.calibration = g.cov_calibration;
     CU(c, launch_k4(k4, st));
     if (record) CU(c, cudaEventRecord(c->ev[5], st));
-    c->launches += launches + 2;   // + K3, K4
+    c->launches += launches + 3;   // + soft-NMS, membership, K4
     return BOD_OK;
 }
 

@@ -15,7 +15,7 @@
 
 namespace bod {
 
-constexpr int kTileAnchors = 256;   // anchors per moments-kernel tile (and per compaction tile)
+constexpr int kTileAnchors = 128;   // anchors per moments-kernel tile (and per compaction tile)
 constexpr int kMaxK = 64;           // classes + background supported
 constexpr int kMaxOut = 256;        // max_output_size supported (selected-mask words = 8)
 constexpr int kMaskWords = kMaxOut / 32;
@@ -139,6 +139,7 @@ BOD_DEVINL float tf_iou(const float4 bi, const float4 bj) {
     const float iymin = fmaxf(ymin_i, ymin_j), ixmin = fmaxf(xmin_i, xmin_j);
     const float iymax = fminf(ymax_i, ymax_j), ixmax = fminf(xmax_i, xmax_j);
     const float inter = fmaxf(iymax - iymin, 0.0f) * fmaxf(ixmax - ixmin, 0.0f);
+    if (inter == 0.0f) return 0.0f;              // 0 / (positive) = +0: skip the division
     return inter / (area_i + area_j - inter);
 }
 

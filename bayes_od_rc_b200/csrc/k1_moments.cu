@@ -26,6 +26,10 @@ namespace bod {
 // ---------------------------------------------------------------------------
 // mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS.*, UBLKCP)
 // ---------------------------------------------------------------------------
+// fast math of the softmax (tolerance-checked output): MUFU.EX2 / MUFU.RCP
+BOD_DEVINL float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+BOD_DEVINL float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 BOD_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 BOD_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -38,11 +42,11 @@ BOD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE;\n"
         "bra WAIT_LOOP;\n"
         "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep, do not spin
 }
 BOD_DEVINL void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -67,6 +71,10 @@ BOD_DEVINL void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, u
 // (p_m^T < 1e-30) fall back to T plain inverse-cdf draws.  Every operation is an
 // explicitly rounded binary32 intrinsic so the CPU restatement is bit-identical.
 // ---------------------------------------------------------------------------
+// (T - j) / (j + 1) for j < kRatioTab, filled by the launcher for the configured number of draws T
+constexpr int kRatioTab = 64;
+__constant__ float c_binom_ratio[kRatioTab];
+
 struct PhiloxStream {
     uint4 w;
     uint32_t anchor, image;
@@ -107,8 +115,8 @@ BOD_DEVINL bool philox_counts(const float (&p)[K], uint32_t anchor, uint32_t ima
     }
     const float total = cdf[K - 1];
     const float rest = __fsub_rn(total, pm);
-    const float aa = __fdiv_rn(pm, total), odds = __fdiv_rn(rest, pm);
-    float pw = 1.0f, base = aa;
+    const float odds = __fmul_rn(rest, __frcp_rn(pm));
+    float pw = 1.0f, base = pm;
     for (int e = T; e; e >>= 1) { if (e & 1) pw = __fmul_rn(pw, base); base = __fmul_rn(base, base); }
     PhiloxStream rng{make_uint4(0, 0, 0, 0), anchor, image, key, 0};
     if (pw >= 1e-30f) {
@@ -116,7 +124,8 @@ BOD_DEVINL bool philox_counts(const float (&p)[K], uint32_t anchor, uint32_t ima
         int j = 0;
         float cd = pw, f = pw;
         while (u >= cd && j < T) {
-            f = __fmul_rn(__fmul_rn(f, __fdiv_rn((float)(T - j), (float)(j + 1))), odds);
+            const float ratio = (j < kRatioTab) ? c_binom_ratio[j] : __fdiv_rn((float)(T - j), (float)(j + 1));
+            f = __fmul_rn(__fmul_rn(f, ratio), odds);
             ++j;
             cd = __fadd_rn(cd, f);
         }
@@ -235,9 +244,10 @@ k1_moments_kernel(K1Args a, int NC) {
 #pragma unroll
                 for (int k = 1; k < K; ++k) m = fmaxf(m, x[k]);
                 float s = 0.0f;
+                const float m2 = m * -1.4426950408889634f;                 // exp(x - m) = 2^(x*log2e - m*log2e)
 #pragma unroll
-                for (int k = 0; k < K; ++k) { x[k] = __expf(x[k] - m); s += x[k]; }
-                const float inv = __frcp_rn(s);
+                for (int k = 0; k < K; ++k) { x[k] = ex2_approx(__fmaf_rn(x[k], 1.4426950408889634f, m2)); s += x[k]; }
+                const float inv = rcp_approx(s);
 #pragma unroll
                 for (int k = 0; k < K; ++k) p[k] = __fmaf_rn(x[k], inv, p[k]);
             }
@@ -307,7 +317,7 @@ k1_moments_kernel(K1Args a, int NC) {
 constexpr int kMaxStages = 32;
 constexpr int kConsumerWarps = kTileAnchors / 32;
 
-constexpr int kPipeCtasPerSM = 3;   // resident CTAs per SM: their finalise phases overlap each other's streaming
+constexpr int kPipeCtasPerSM = 6;   // resident CTAs per SM: their finalise phases overlap each other's streaming
 
 template <int K>
 __global__ void __launch_bounds__(kTileAnchors + 32, kPipeCtasPerSM)
@@ -382,9 +392,10 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
 #pragma unroll
                 for (int k = 1; k < K; ++k) m = fmaxf(m, x[k]);
                 float s = 0.0f;
+                const float m2 = m * -1.4426950408889634f;                 // exp(x - m) = 2^(x*log2e - m*log2e)
 #pragma unroll
-                for (int k = 0; k < K; ++k) { x[k] = __expf(x[k] - m); s += x[k]; }
-                const float inv = __frcp_rn(s);
+                for (int k = 0; k < K; ++k) { x[k] = ex2_approx(__fmaf_rn(x[k], 1.4426950408889634f, m2)); s += x[k]; }
+                const float inv = rcp_approx(s);
 #pragma unroll
                 for (int k = 0; k < K; ++k) p[k] = __fmaf_rn(x[k], inv, p[k]);
             }
@@ -487,7 +498,22 @@ static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static int g_ratio_T[64] = {0};
+
 cudaError_t launch_k1(const K1Args& a, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_ratio_T[dev] != a.num_draws) {
+        float tab[kRatioTab];
+        for (int j = 0; j < kRatioTab; ++j) {
+            volatile float num = (float)(a.num_draws - j), den = (float)(j + 1);
+            tab[j] = num / den;
+        }
+        cudaError_t e0 = cudaMemcpyToSymbolAsync(c_binom_ratio, tab, sizeof tab, 0, cudaMemcpyHostToDevice, st);
+        if (e0 != cudaSuccess) return e0;
+        cudaStreamSynchronize(st);              // `tab` is a stack temporary; happens once per device / T
+        g_ratio_T[dev] = a.num_draws;
+    }
     switch (a.K) {
 #define BOD_CASE(KK) case KK: return launch_k<KK>(a, st);
         BOD_CASE(2) BOD_CASE(3) BOD_CASE(4) BOD_CASE(5) BOD_CASE(6) BOD_CASE(7) BOD_CASE(8) BOD_CASE(9)

@@ -56,12 +56,11 @@ BOD_DEVINL float nms_weight(float sim, float scale, bool is_soft, float thr) {
 }
 
 BOD_DEVINL unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
-        v = o > v ? o : v;
-    }
-    return v;
+    // two REDUX ops: max of the score halves, then max of the (inverted) index halves among the winners
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, (hi == mh) ? lo : 0u);
+    return ((unsigned long long)mh << 32) | (unsigned long long)ml;
 }
 
 // ---------------------------------------------------------------------------
@@ -196,7 +195,6 @@ struct K3Smem {
     unsigned long long top_w[kK3Warps][kTop];    // per-warp top keys of a round
     unsigned long long sel_key[kMaxOut];         // key (score, -index) of every selected centre
     float4 sel_box[kMaxOut];
-    float wpair[kTop][kTop];                     // soft-NMS weights among the examined candidates
     int seg_n[kK3Warps];                         // entries in each warp's list segment
     int batch_n;                                 // centres selected in this round
     int malformed;
@@ -206,7 +204,6 @@ struct K3Const {                                  // kernel-lifetime constants o
     const float4* corn; float* ucur; float* stl; uint8_t* npend;
     float* pw; uint8_t* pj; int pstride;          // pending (weight, selection) lists, [S][pstride]
     const unsigned long long* sel_key; const float4* sel_box;
-    uint32_t* member; int words;
     float scale, thr; int is_soft;
 };
 
@@ -244,37 +241,32 @@ BOD_DEVINL int first_pop_round(const unsigned long long* sel_key, unsigned long 
     return lo;
 }
 
-// The slow part of a round for one candidate s that (geometrically) overlaps the batch centres whose
-// bits are set in `mask` (centre k of the batch is selection r0 + k).
+// The slow part of a round for one QUEUED candidate s whose box intersects the batch centres whose bits
+// are set in `mask` (centre k of the batch is selection r0 + k).
 __device__ __noinline__ void k3_process(const K3Const* C, const int r0, const uint32_t mask, const int s) {
     const float4 bs = C->corn[s];
     float u = C->ucur[s];
     const float scale = C->scale, thr = C->thr;
     const bool is_soft = C->is_soft != 0;
-    const bool queued = u > -INFINITY;
     int n = C->npend[s];
     float* wrow = C->pw + (size_t)s * C->pstride;
     uint8_t* jrow = C->pj + (size_t)s * C->pstride;
     // issue the loads of the newest pending weights first: their latency overlaps the IoU / exp arithmetic
     const float4* wrow4 = reinterpret_cast<const float4*>(wrow);
     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-    int blk = (n - 1) >> 2;
-    float4 cur = (queued && n > 0) ? wrow4[blk] : one4;
-    float4 nxt = (queued && blk > 0) ? wrow4[blk - 1] : one4;
+    const int blk = (n - 1) >> 2;
+    float4 cur = (n > 0) ? wrow4[blk] : one4;
+    float4 nxt = (blk > 0) ? wrow4[blk - 1] : one4;
     float st = C->stl[s];
-    bool changed = false, folded = false, alive = queued, first = true;
+    bool changed = false, folded = false, first = true;
 
     for (uint32_t rem = mask; rem; rem &= rem - 1) {
         const int r = r0 + __ffs(rem) - 1;
-        const float4 bx = C->sel_box[r];
-        if (repo_iou(bs, bx) > thr)                                                // :316, strict >
-            atomicOr(&C->member[(size_t)r * C->words + (s >> 5)], 1u << (s & 31));
-        if (!alive) continue;                                                      // selected / never queued / removed
-        const float sim = tf_iou(bs, bx);
+        const float sim = tf_iou(bs, C->sel_box[r]);
         const float w = nms_weight_fast(sim, scale, is_soft, thr);
         if (w == 1.0f) continue;                                                   // untouched by this centre
         changed = true;
-        if (!is_soft && w == 0.0f) { u = -INFINITY; alive = false; continue; }     // hard-NMS: removed for good
+        if (!is_soft && w == 0.0f) { u = -INFINITY; break; }                       // hard-NMS: removed for good
         const unsigned long long kxr = C->sel_key[r];
         if (n > 0 && make_key(st, s) > kxr) {
             // rare: TF popped this candidate at least once since its list was last touched: replay
@@ -368,18 +360,16 @@ k3_softnms_kernel(K3Args a, int smem_S) {
     const int Dmax = a.Dmax;
     const float4* corners = a.corners + (size_t)b * a.capacity;
     const float* score = a.score + (size_t)b * a.capacity;
-    uint32_t* member = a.member + (size_t)b * Dmax * a.words;
     const bool is_soft = a.soft_nms_sigma > 0.0f;
     const float scale = is_soft ? -0.5f / a.soft_nms_sigma : 0.0f;
     const float thr = a.iou_threshold;
-    const int S32 = (S + 31) & ~31, nwords = S32 >> 5;
+    const int S32 = (S + 31) & ~31;
 
     if (tid == 0) {
         kc.corn = corn; kc.ucur = ucur; kc.stl = stl; kc.npend = npend;
         kc.pstride = a.pstride;
         kc.pw = a.pw + (size_t)b * a.fastS * a.pstride; kc.pj = a.pj + (size_t)b * a.fastS * a.pstride;
         kc.sel_key = sm.sel_key; kc.sel_box = sm.sel_box;
-        kc.member = member; kc.words = a.words;
         kc.scale = scale; kc.thr = thr; kc.is_soft = is_soft ? 1 : 0;
         sm.malformed = 0;
     }
@@ -395,8 +385,6 @@ k3_softnms_kernel(K3Args a, int smem_S) {
         stl[s] = sc;
         npend[s] = 0;
     }
-    const int Duse = min(Dmax, S);
-    for (int i = tid; i < Duse * nwords; i += kK3Threads) member[(size_t)(i / nwords) * a.words + (i % nwords)] = 0u;
     __syncthreads();
     const bool all_maybe = sm.malformed != 0;
 
@@ -435,7 +423,8 @@ k3_softnms_kernel(K3Args a, int smem_S) {
 #pragma unroll
             for (int q = 1; q < kTop; ++q) myk = (lane == q) ? t2[q] : myk;
             if (lane >= kTop) myk = 0ull;
-            // pairwise weights among the examined candidates: pair (q, i), i < q, on lane (q*(q-1)/2 + i)
+            // pairwise weights among the examined candidates: pair (q, i), i < q, on lane q*(q-1)/2 + i
+            float wp = 1.0f;
             {
                 int q = 1, base = 0;
                 while (base + q <= lane) { base += q; ++q; }             // lane -> (q, i)
@@ -444,13 +433,12 @@ k3_softnms_kernel(K3Args a, int smem_S) {
                     unsigned long long kq = t2[0], ki = t2[0];
 #pragma unroll
                     for (int z = 1; z < kTop; ++z) { kq = (q == z) ? t2[z] : kq; ki = (i == z) ? t2[z] : ki; }
-                    float w = 1.0f;
                     if (kq != 0ull && ki != 0ull)
-                        w = nms_weight_fast(tf_iou(corn[key_index(kq)], corn[key_index(ki)]), scale, is_soft, thr);
-                    sm.wpair[q][i] = w;
+                        wp = nms_weight_fast(tf_iou(corn[key_index(kq)], corn[key_index(ki)]), scale, is_soft, thr);
                 }
             }
-            __syncwarp();
+            static_assert(kTop * (kTop - 1) / 2 <= 32, "one lane per candidate pair");
+            const uint32_t nonunit = __ballot_sync(0xffffffffu, wp != 1.0f);
             int m = 0;
             uint32_t acc = 0u;                                           // accepted candidates (bit q)
             if (t2[0] != 0ull) {
@@ -460,13 +448,14 @@ k3_softnms_kernel(K3Args a, int smem_S) {
                 for (int q = 1; q < kTop; ++q) {
                     if (t2[q] == 0ull || r + m >= Dmax || m >= kBatch) break;
                     const float sq = key_score(t2[q]);
-                    float wmin = 1.0f;
-                    for (int i = 0; i < q; ++i) if ((acc >> i) & 1u) wmin = fminf(wmin, sm.wpair[q][i]);
-                    if (wmin == 1.0f) {
+                    const int base = q * (q - 1) / 2;
+                    const uint32_t hit = (nonunit >> base) & acc & ((1u << q) - 1u);   // accepted centres it overlaps
+                    if (hit == 0u) {
                         if (!(sq > ub_max)) break;                       // a skipped candidate might still outrank it
                         acc |= 1u << q; ++m;
                     } else {
-                        ub_max = fmaxf(ub_max, sq * wmin * 1.00001f);
+                        const float w = __shfl_sync(0xffffffffu, wp, base + __ffs(hit) - 1);
+                        ub_max = fmaxf(ub_max, sq * w * 1.00001f);
                     }
                 }
             }
@@ -497,16 +486,16 @@ k3_softnms_kernel(K3Args a, int smem_S) {
 #pragma unroll 2
         for (int s = tid; s < S32; s += kK3Threads) {
             uint32_t mask = 0u;
-            if (s < S) {
+            if (s < S && ucur[s] > -INFINITY) {
                 const float4 bs = corn[s];
-                // no overlap even with the +1 pixel convention ((hi - lo) + 1 > 0  <=>  hi - lo > -1 in
-                // binary32) => TF IoU = 0 (weight exactly 1) and repo IoU <= 0: the centre does nothing here
+                // TF's intersection area is max(dy,0)*max(dx,0): no positive intersection => IoU = 0 and the
+                // weight is exactly 1, the centre does nothing to this candidate
 #pragma unroll
                 for (int q = 0; q < kBatch; ++q) {
                     if (q < m) {
                         const float dx = fminf(bs.w, bxs[q].w) - fmaxf(bs.y, bxs[q].y);
                         const float dy = fminf(bs.z, bxs[q].z) - fmaxf(bs.x, bxs[q].x);
-                        if ((dx > -1.0f && dy > -1.0f) || all_maybe) mask |= 1u << q;
+                        if ((dx > 0.0f && dy > 0.0f) || all_maybe) mask |= 1u << q;
                     }
                 }
             }
@@ -553,6 +542,37 @@ k3_softnms_kernel(K3Args a, int smem_S) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// cluster membership (inference_utils.py:214-215 + :316): bit s of row d <=>
+// bbox_iou_vuvu(survivor s, centre d) > threshold, for the D centre columns only.
+// One CTA per (centre, image); fully parallel, off the sequential path.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k3_membership_kernel(K3Args a) {
+    const int d = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    if (d >= a.num_dets[b]) return;
+    const int S = a.num_survivors[b];
+    const float4* corners = a.corners + (size_t)b * a.capacity;
+    uint32_t* row = a.member + ((size_t)b * a.Dmax + d) * a.words;
+    const float4 bx = corners[a.nms_idx[(size_t)b * a.Dmax + d]];
+    const bool bx_ok = (bx.x <= bx.z) && (bx.y <= bx.w);
+    const float thr = a.iou_threshold;
+    const int S32 = (S + 31) & ~31;
+    for (int s = tid; s < S32; s += 256) {
+        bool mem = false;
+        if (s < S) {
+            const float4 bs = corners[s];
+            // no overlap even with the +1 pixel convention ((hi - lo) + 1 > 0 <=> hi - lo > -1 in binary32)
+            // => intersection 0 => IoU <= 0 <= threshold
+            const float dx = fminf(bs.w, bx.w) - fmaxf(bs.y, bx.y);
+            const float dy = fminf(bs.z, bx.z) - fmaxf(bs.x, bx.x);
+            const bool wellformed = bx_ok && (bs.x <= bs.z) && (bs.y <= bs.w);
+            if (!wellformed || (dx > -1.0f && dy > -1.0f)) mem = repo_iou(bs, bx) > thr;   // strict >
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, mem);
+        if (lane == 0) row[s >> 5] = bal;
+    }
+}
+
 int k3_fast_capacity(int capacity) {
     int s = capacity < kFastS ? capacity : kFastS;
     return (s + 31) & ~31;
@@ -575,6 +595,9 @@ cudaError_t launch_k3(const K3Args& a, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(k3_softnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k3_softnms_kernel<<<a.B, kK3Threads, smem, st>>>(a, smem_S);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k3_membership_kernel<<<dim3(a.Dmax, a.B), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -10,30 +10,34 @@
 //   :351-352   cat_param = mean of the kept scores, cat_count = sum of the kept counts
 //   :361       Sigma_f * 70
 //
-// One warp per (image, centre).  Lanes invert the covariances of 32 members at a
-// time in parallel; the sums over members stay sequential in ascending survivor
-// order (one lane per matrix entry walks the member bits), which keeps the result
-// bit-identical to a sequential host loop while the expensive part (the 4x4
-// inverses) runs 32 wide.
+// One warp per (image, centre).  The member bits of a cluster are scattered over
+// the survivor index space, so they are first compacted into an ascending index
+// list; then 32 members at a time are handled densely: lanes invert the members'
+// covariances in parallel, while the sums over members stay sequential in
+// ascending survivor order (one lane per matrix entry walks the chunk), which
+// keeps the result bit-identical to a sequential host loop while the expensive
+// part (the 4x4 inverses, the KL terms) runs 32 wide.
 #include "bod_common.cuh"
 #include "bod_kernels.h"
 
 namespace bod {
 
 constexpr int kK4Warps = 4;
+constexpr int kK4List = 1024;       // member indices buffered per warp (larger clusters are streamed in segments)
 
 // KL(pk || qk) as scipy.stats.entropy computes it: both re-normalised, rel_entr summed.
+// pk is passed already normalised (it is the same for every member of a cluster).
 template <int K>
-BOD_DEVINL float kl_div(const float (&pk_raw)[K], const float (&qk_raw)[K]) {
-    float sp = 0.0f, sq = 0.0f, acc = 0.0f;
+BOD_DEVINL float kl_div_norm(const float (&p)[K], const float (&qk_raw)[K]) {
+    float sq = 0.0f, acc = 0.0f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) { sp = sp + pk_raw[k]; sq = sq + qk_raw[k]; }
+    for (int k = 0; k < K; ++k) sq = sq + qk_raw[k];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const float p = pk_raw[k] / sp, q = qk_raw[k] / sq;
+        const float pk = p[k], q = qk_raw[k] / sq;
         float t;
-        if (p > 0.0f && q > 0.0f) t = p * log_cr(p / q);
-        else if (p == 0.0f && q >= 0.0f) t = 0.0f;
+        if (pk > 0.0f && q > 0.0f) t = (pk == q) ? 0.0f : pk * log_cr(pk / q);   // log(1) = 0 exactly: p * 0 = 0
+        else if (pk == 0.0f && q >= 0.0f) t = 0.0f;
         else t = INFINITY;
         acc = acc + t;
     }
@@ -44,6 +48,7 @@ template <int K>
 __global__ void __launch_bounds__(kK4Warps * 32)
 k4_fusion_kernel(K4Args a) {
     __shared__ float stage[kK4Warps][32][21];     // per lane: 16 precision entries + 4 weighted-mean entries (+pad)
+    __shared__ uint32_t mlist[kK4Warps][kK4List]; // ascending member indices of the segment being processed
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = blockIdx.x * kK4Warps + warp, b = blockIdx.y;
@@ -63,76 +68,134 @@ k4_fusion_kernel(K4Args a) {
     const float4* sig = reinterpret_cast<const float4*>(a.sig_post) + (size_t)b * a.capacity * 4;
     const int centre = a.nms_idx[(size_t)b * a.Dmax + d];
     float (*st)[21] = stage[warp];
+    uint32_t* ml = mlist[warp];
 
-    // centre's normalised score (:339-340)
-    float cs[K];
+    // cluster size first (the KL ranking is only needed for more than 3 members, :338)
+    int m = 0;
+    for (int w = lane; w < nwords; w += 32) m += __popc(row[w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    const bool need_kl = m > 3;
+
+    // centre's raw counts and its normalised, re-normalised score (:339-340 and scipy's pk / sum(pk))
+    float cc[K], cp[K];
     {
-        const float* cc = cnt + (size_t)centre * K;
-        float ccs = 0.0f;
+        const float* c0 = cnt + (size_t)centre * K;
+        float ccs = 0.0f, sp = 0.0f;
 #pragma unroll
-        for (int k = 0; k < K; ++k) ccs = ccs + cc[k];
+        for (int k = 0; k < K; ++k) { cc[k] = c0[k]; ccs = ccs + cc[k]; }
 #pragma unroll
-        for (int k = 0; k < K; ++k) cs[k] = cc[k] / ccs;
+        for (int k = 0; k < K; ++k) { cp[k] = cc[k] / ccs; sp = sp + cp[k]; }
+#pragma unroll
+        for (int k = 0; k < K; ++k) cp[k] = cp[k] / sp;
     }
 
     float acc = 0.0f;            // lanes 0..15: precision-sum entry, lanes 16..19: weighted-mean-sum entry
-    int m = 0;
-    float best_kl[3] = {0.0f, 0.0f, 0.0f};
-    int best_s[3] = {-1, -1, -1};
+    // running top-3 by (KL, survivor index); replicated on every lane
+    float best_kl[3] = {INFINITY, INFINITY, INFINITY};
+    int best_s[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
     int nbest = 0;
 
-    for (int w = 0; w < nwords; ++w) {
-        const uint32_t bits = row[w];
-        if (bits == 0u) continue;                 // warp-uniform
-        const int s = (w << 5) + lane;
-        float kl = 0.0f;
-        if ((bits >> lane) & 1u) {
-            float Sg[4][4], P[4][4], x[4], y[4];
+    for (int w0 = 0; w0 < nwords;) {
+        // ---- compact the member bits of the next words into an ascending index list ----
+        int filled = 0, w = w0;
+        for (; w < nwords; w += 32) {
+            const int wi = w + lane;
+            const uint32_t bits = (wi < nwords) ? row[wi] : 0u;
+            int c = __popc(bits), pre = c;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 r = sig[(size_t)s * 4 + i];
-                Sg[i][0] = r.x; Sg[i][1] = r.y; Sg[i][2] = r.z; Sg[i][3] = r.w;
-            }
-            inv4(Sg, P);                                                       // :321-322
-            const float4 mv = mu[s];
-            x[0] = mv.x; x[1] = mv.y; x[2] = mv.z; x[3] = mv.w;
-            mv4(P, x, y);                                                      // :327-329
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) st[lane][4 * i + j] = P[i][j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) st[lane][16 + i] = y[i];
-            // member's normalised score and its KL from the centre (:335-336, 344)
-            float sc[K];
-            const float* c = cnt + (size_t)s * K;
-            float su = 0.0f;
-#pragma unroll
-            for (int k = 0; k < K; ++k) su = su + c[k];
-#pragma unroll
-            for (int k = 0; k < K; ++k) sc[k] = c[k] / su;
-            kl = kl_div<K>(cs, sc);
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += y; }
+            const int tot = __shfl_sync(0xffffffffu, pre, 31);
+            if (filled + tot > kK4List) break;                     // segment full: process what we have first
+            int pos = filled + pre - c;
+            for (uint32_t rem = bits; rem; rem &= rem - 1) ml[pos++] = (uint32_t)((wi << 5) + __ffs(rem) - 1);
+            filled += tot;
         }
+        if (w == w0) {
+            // a single 32-word stripe holds more members than the buffer (cannot happen with kK4List >= 1024)
+            return;
+        }
+        w0 = w;
         __syncwarp();
-        // sequential (ascending survivor) accumulation, one lane per entry (:324, :330)
-        if (lane < 20) {
-            for (uint32_t rem = bits; rem; rem &= rem - 1) acc = acc + st[__ffs(rem) - 1][lane];
-        }
-        // running top-3 by (KL, survivor index), strict < so that earlier members win ties
-        for (uint32_t rem = bits; rem; rem &= rem - 1) {
-            const int l = __ffs(rem) - 1;
-            const float v = __shfl_sync(0xffffffffu, kl, l);
-            const int sv = (w << 5) + l;
-            int pos = nbest;
-            while (pos > 0 && v < best_kl[pos - 1]) --pos;
-            if (pos < 3) {
-                for (int q = (nbest < 3 ? nbest : 2); q > pos; --q) { best_kl[q] = best_kl[q - 1]; best_s[q] = best_s[q - 1]; }
-                best_kl[pos] = v; best_s[pos] = sv;
-                if (nbest < 3) ++nbest;
+
+        // ---- 32 members at a time ----
+        for (int base = 0; base < filled; base += 32) {
+            const int nb = min(32, filled - base);
+            float kl = INFINITY;
+            int s = 0x7fffffff;
+            if (lane < nb) {
+                s = (int)ml[base + lane];
+                float Sg[4][4], P[4][4], x[4], y[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 r = sig[(size_t)s * 4 + i];
+                    Sg[i][0] = r.x; Sg[i][1] = r.y; Sg[i][2] = r.z; Sg[i][3] = r.w;
+                }
+                inv4(Sg, P);                                                       // :321-322
+                const float4 mv = mu[s];
+                x[0] = mv.x; x[1] = mv.y; x[2] = mv.z; x[3] = mv.w;
+                mv4(P, x, y);                                                      // :327-329
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st[lane][4 * i + j] = P[i][j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st[lane][16 + i] = y[i];
+                if (need_kl) {
+                    // member's normalised score and its KL from the centre (:335-336, 344)
+                    float c[K];
+                    const float* cs = cnt + (size_t)s * K;
+                    bool same = true;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { c[k] = cs[k]; same = same && (c[k] == cc[k]); }
+                    if (same) {
+                        kl = 0.0f;                     // identical counts: every term is p * log(1) = 0
+#pragma unroll
+                        for (int k = 0; k < K; ++k) if (!(cp[k] >= 0.0f)) kl = NAN;    // (NaN counts propagate)
+                    } else {
+                        float su = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) su = su + c[k];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) c[k] = c[k] / su;
+                        kl = kl_div_norm<K>(cp, c);
+                    }
+                }
             }
+            __syncwarp();
+            // sequential (ascending survivor) accumulation, one lane per entry (:324, :330)
+            if (lane < 20) {
+                for (int e = 0; e < nb; ++e) acc = acc + st[e][lane];
+            }
+            if (need_kl) {
+                // chunk-local three smallest (KL, index), merged into the running three; strict < keeps
+                // the earlier member on ties (np.argpartition's tie order is implementation-defined)
+                float ckl = kl;
+                int cs_ = s;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    // lexicographic arg-min of (ckl, cs_) across the warp; NaN never wins
+                    float bk = ckl; int bs = cs_;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                        const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                        if (ok < bk || (ok == bk && os < bs) || (!(bk == bk) && ok == ok)) { bk = ok; bs = os; }
+                    }
+                    if (bs == 0x7fffffff) break;                                   // chunk exhausted
+                    if (cs_ == bs) { ckl = INFINITY; cs_ = 0x7fffffff; }           // consumed
+                    // insert into the running top-3 (ascending KL, ties -> earlier index stays first)
+                    int pos = nbest;
+                    while (pos > 0 && bk < best_kl[pos - 1]) --pos;
+                    if (pos < 3) {
+                        for (int q = (nbest < 3 ? nbest : 2); q > pos; --q) { best_kl[q] = best_kl[q - 1]; best_s[q] = best_s[q - 1]; }
+                        best_kl[pos] = bk; best_s[pos] = bs;
+                        if (nbest < 3) ++nbest;
+                    } else break;                                                  // the rest of the chunk is not smaller either
+                }
+            }
+            __syncwarp();
         }
-        m += __popc(bits);
-        __syncwarp();
     }
 
     const size_t orow = (size_t)b * a.Dmax + d;

@@ -228,10 +228,11 @@ void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint3
  *     five 23-bit fields (bits [0,23), [23,46), .. of the little-endian word);
  *     the i-th uniform of the anchor is (field_i + 0.5) * 2^-23, i = 5j + f.
  *   cdf[k] = p[0]+..+p[k], total = cdf[K-1]; m = first argmax of p.
- *   dominant-class split: a = p[m]/total, pw = a^T by square-and-multiply.
- *   if pw >= 1e-30:  the number of draws NOT landing on m is Binomial(T, 1-a),
+ *   dominant-class split: pw = p[m]^T by square-and-multiply (the mean of N softmax
+ *   rows sums to 1 within a few ulp, so p[m] is used as the probability of m).
+ *   if pw >= 1e-30:  the number of draws NOT landing on m is Binomial(T, 1-p[m]),
  *       sampled by inversion from 0 upward with the first uniform
- *       (f_0 = pw, f_{j+1} = f_j * ((T-j)/(j+1)) * ((total-p[m])/p[m]));
+ *       (f_0 = pw, f_{j+1} = f_j * ((T-j)/(j+1)) * ((total-p[m]) * (1/p[m])));
  *       each of those draws then picks a class k != m with the next uniform u:
  *       first k != m with u*(total-p[m]) < running sum of p over k != m
  *       (last class != m as the fallback); cnt[m] = T - others.
@@ -263,8 +264,8 @@ void orc_philox_counts(const float* probs, int A, int K, int T, uint64_t seed,
         for (int k = 0; k < K; ++k) { s = s + p[k]; cdf[k] = s; c[k] = 0.0f; if (p[k] > p[m]) m = k; }
         const float total = cdf[K - 1];
         const float pm = p[m], rest = total - pm;
-        const float aa = pm / total, odds = rest / pm;
-        float pw = 1.0f, base = aa;
+        const float odds = rest * (1.0f / pm);
+        float pw = 1.0f, base = pm;
         for (int e = T; e; e >>= 1) { if (e & 1) pw = pw * base; base = base * base; }
         uint32_t w[4]; int g = 0;
         if (pw >= 1e-30f) {
