@@ -66,6 +66,7 @@ SYMBOLS = {
     "bod_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "bod_run": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
     "bod_run_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(BodHostResults)]),
+    "bod_last_host_traffic": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bod_cluster_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_float, C.POINTER(BodHostResults)]),
     "bod_fetch": (C.c_int, [C.c_void_p, C.POINTER(BodHostResults)]),

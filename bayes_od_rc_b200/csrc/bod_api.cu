@@ -49,6 +49,8 @@ struct bod_ctx {
     cudaEvent_t ev_copy[4] = {nullptr};
     bool ran = false, used_sampler = false, timing = true, last_timed = false;
     int launches = 0;
+    int64_t h2d_copied = 0, h2d_mapped_rows = 0, d2h_copied = 0;   // traffic of the last bod_run_host
+    bool host_copy_all = false;       // BOD_HOST_COPY_ALL: never read box/cov in place from pinned host memory
     int k1_debug = 0;                 // BOD_K1_DEBUG (diagnostics)
     long long* k3_dbg = nullptr;      // BOD_K3_DEBUG (diagnostics): [B][8] cycle counters
 };
@@ -174,6 +176,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     for (auto& ev : c->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
     if (const char* d = getenv("BOD_K1_DEBUG")) c->k1_debug = atoi(d);
+    c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
     if (getenv("BOD_K3_DEBUG")) { cudaMalloc(&c->k3_dbg, (size_t)B * 8 * sizeof(long long)); cudaMemset(c->k3_dbg, 0, (size_t)B * 8 * sizeof(long long)); }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { snprintf(create_err, sizeof create_err, "init: %s", cudaGetErrorString(e)); bod_destroy(c); return BOD_ERR_CUDA; }
@@ -453,9 +456,23 @@ extern "C" int bod_stage_ms_accum(bod_ctx* c, float sum_ms[6], int32_t* runs) {
 }
 
 // ---------------------------------------------------------------------------
-// host-buffer entry: H2D in image chunks on a copy stream, compute chunk i while
-// chunk i+1 is in flight, D2H of the padded result blocks.
+// host-buffer entry.  Every anchor's class logits must be inspected, so `cls`
+// is staged host->device in image chunks on a copy stream while the previous
+// chunk computes.  The box deltas and covariance rows are only needed for the
+// S survivors (~2% of the anchors): when `box` / `cov` live in pinned (page-locked,
+// device-mapped) host memory, K2 gathers those rows in place over PCIe instead
+// of copying the whole [B,N,A,4] and [B,N,A,16] tensors (64% of the input bytes).
+// Pageable buffers fall back to plain copies.
 // ---------------------------------------------------------------------------
+static const float* mapped_device_pointer(const float* host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) return static_cast<const float*>(at.devicePointer);
+    if (at.type == cudaMemoryTypeManaged) return host;
+    return nullptr;
+}
+
 extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, const float* cov, const float* anchors,
                             const float* counts, bod_host_results* out) {
     int rc = check_inputs(c, cls, box, cov, anchors);
@@ -465,32 +482,49 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
     const bod_config& g = c->cfg;
     const size_t B = g.B, N = g.N, A = g.A, K = g.K;
     const size_t cw = cov_width(g.cov_layout);
+    // box / cov: read in place when the caller's buffers are device-mapped and 16-byte aligned
+    const float* box_m = c->host_copy_all ? nullptr : mapped_device_pointer(box);
+    const float* cov_m = (cw && !c->host_copy_all) ? mapped_device_pointer(cov) : nullptr;
+    if (box_m && (reinterpret_cast<uintptr_t>(box_m) & 15u)) box_m = nullptr;
+    if (cov_m && (reinterpret_cast<uintptr_t>(cov_m) & 15u)) cov_m = nullptr;
     if (!c->in_cls) {
         CU(c, cudaMalloc(&c->in_cls, B * N * A * K * 4));
-        CU(c, cudaMalloc(&c->in_box, B * N * A * 16));
-        if (cw) CU(c, cudaMalloc(&c->in_cov, B * N * A * cw * 4));
         CU(c, cudaMalloc(&c->in_anchors, A * 16));
         CU(c, cudaMalloc(&c->in_counts, B * A * K * 4));
     }
+    if (!box_m && !c->in_box) CU(c, cudaMalloc(&c->in_box, B * N * A * 16));
+    if (cw && !cov_m && !c->in_cov) CU(c, cudaMalloc(&c->in_cov, B * N * A * cw * 4));
     cudaStream_t cs = c->copy_stream, st = c->own_stream;
     c->launches = 0;
     c->last_timed = false;
-    if (anchors) CU(c, cudaMemcpyAsync(c->in_anchors, anchors, A * 16, cudaMemcpyHostToDevice, cs));
-    // chunks of images: small enough to overlap, large enough to fill the GPU
+    c->h2d_copied = 0; c->h2d_mapped_rows = 0; c->d2h_copied = 0;
+    if (anchors) { CU(c, cudaMemcpyAsync(c->in_anchors, anchors, A * 16, cudaMemcpyHostToDevice, cs)); c->h2d_copied += A * 16; }
+    // chunks of images: small enough to overlap copy and compute, large enough to fill the GPU
     const int chunk = (B >= 8) ? (int)((B + 3) / 4) : (int)B;
     int nev = 0;
     for (size_t b0 = 0; b0 < B; b0 += chunk) {
         const size_t nb = (b0 + chunk <= B) ? chunk : B - b0;
         CU(c, cudaMemcpyAsync(c->in_cls + b0 * N * A * K, cls + b0 * N * A * K, nb * N * A * K * 4, cudaMemcpyHostToDevice, cs));
-        if (counts) CU(c, cudaMemcpyAsync(c->in_counts + b0 * A * K, counts + b0 * A * K, nb * A * K * 4, cudaMemcpyHostToDevice, cs));
-        CU(c, cudaMemcpyAsync(c->in_box + b0 * N * A * 4, box + b0 * N * A * 4, nb * N * A * 16, cudaMemcpyHostToDevice, cs));
-        if (cw) CU(c, cudaMemcpyAsync(c->in_cov + b0 * N * A * cw, cov + b0 * N * A * cw, nb * N * A * cw * 4, cudaMemcpyHostToDevice, cs));
+        c->h2d_copied += nb * N * A * K * 4;
+        if (counts) {
+            CU(c, cudaMemcpyAsync(c->in_counts + b0 * A * K, counts + b0 * A * K, nb * A * K * 4, cudaMemcpyHostToDevice, cs));
+            c->h2d_copied += nb * A * K * 4;
+        }
+        if (!box_m) {
+            CU(c, cudaMemcpyAsync(c->in_box + b0 * N * A * 4, box + b0 * N * A * 4, nb * N * A * 16, cudaMemcpyHostToDevice, cs));
+            c->h2d_copied += nb * N * A * 16;
+        }
+        if (cw && !cov_m) {
+            CU(c, cudaMemcpyAsync(c->in_cov + b0 * N * A * cw, cov + b0 * N * A * cw, nb * N * A * cw * 4, cudaMemcpyHostToDevice, cs));
+            c->h2d_copied += nb * N * A * cw * 4;
+        }
         cudaEvent_t ev = c->ev_copy[nev++ & 3];
         CU(c, cudaEventRecord(ev, cs));
         CU(c, cudaStreamWaitEvent(st, ev, 0));
-        rc = run_range(c, (int)b0, (int)nb, c->in_cls + b0 * N * A * K, c->in_box + b0 * N * A * 4,
-                       cw ? c->in_cov + b0 * N * A * cw : nullptr, anchors ? c->in_anchors : nullptr,
-                       counts ? c->in_counts + b0 * A * K : nullptr, st, false);
+        rc = run_range(c, (int)b0, (int)nb, c->in_cls + b0 * N * A * K,
+                       box_m ? box_m + b0 * N * A * 4 : c->in_box + b0 * N * A * 4,
+                       cw ? (cov_m ? cov_m + b0 * N * A * cw : c->in_cov + b0 * N * A * cw) : nullptr,
+                       anchors ? c->in_anchors : nullptr, counts ? c->in_counts + b0 * A * K : nullptr, st, false);
         if (rc) return rc;
     }
     c->last_stream = st; c->ran = true; c->used_sampler = (counts == nullptr);
@@ -503,6 +537,26 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
         CU(c, cudaMemset(c->status, 0, 4));
         return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
     }
+    // rows read in place from mapped host memory: N * (16 [+ 4*cw]) bytes per survivor
+    if (box_m || cov_m) {
+        std::vector<int32_t> ns(B);
+        CU(c, cudaMemcpy(ns.data(), c->num_survivors, B * 4, cudaMemcpyDeviceToHost));
+        int64_t S = 0;
+        for (size_t b = 0; b < B; ++b) S += ns[b];
+        c->h2d_mapped_rows = S * (int64_t)N * ((box_m ? 16 : 0) + (cov_m ? (int64_t)cw * 4 : 0));
+    }
+    {
+        const size_t D = c->Dmax;
+        c->d2h_copied = (int64_t)(B * 4 * 2 + B * D * (16 + 64 + 2 * K * 4 + 12));
+    }
+    return BOD_OK;
+}
+
+extern "C" int bod_last_host_traffic(const bod_ctx* c, int64_t* h2d_copied, int64_t* h2d_gathered, int64_t* d2h) {
+    if (!c) return BOD_ERR_INVALID;
+    if (h2d_copied) *h2d_copied = c->h2d_copied;
+    if (h2d_gathered) *h2d_gathered = c->h2d_mapped_rows;
+    if (d2h) *d2h = c->d2h_copied;
     return BOD_OK;
 }
 

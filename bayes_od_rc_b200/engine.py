@@ -280,6 +280,12 @@ class BayesODEngine:
         self._check(self.lib.bod_run_host(self._ctx, p_cls, p_box, p_cov, p_anc, p_cnt, C.byref(self._hres)))
         return self._h
 
+    def host_traffic(self) -> dict:
+        """Bytes the last run_host moved (copied H2D, gathered in place from pinned memory, copied D2H)."""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.bod_last_host_traffic(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(h2d_copied=a.value, h2d_gathered=b.value, d2h=c.value)
+
     def cluster_host(self, counts, means, covs, centres, affinity, affinity_threshold):
         """bayes_od_clustering for one image from host arrays (bod_cluster_host)."""
         counts = np.ascontiguousarray(counts, np.float32)

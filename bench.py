@@ -231,9 +231,10 @@ def main():
             out = run_e2e()
         torch.cuda.synchronize()
         te = time.perf_counter() - te0
-        h2d = (cls.numel() + box.numel() + cov.numel() + anchors.numel()) * 4
-        d2h = sum(v.nbytes for v in out.values())
-        e2e = dict(seconds=te, steps=n_e2e, h2d=h2d, d2h=d2h)
+        tr = eng.host_traffic()
+        e2e = dict(seconds=te, steps=n_e2e, h2d=tr["h2d_copied"] + tr["h2d_gathered"], d2h=tr["d2h"],
+                   h2d_copied=tr["h2d_copied"], h2d_gathered=tr["h2d_gathered"],
+                   host_bytes=(cls.numel() + box.numel() + cov.numel() + anchors.numel()) * 4)
     sampler.stop()
 
     # ---- max over ranks ----
@@ -270,7 +271,7 @@ def main():
                        "bytes_min_per_image": int(bmin), "path_roofline_frac": round(path_frac, 4)},
             "gpu_launches": launches_per_step * args.steps,
             "stage_ms": {k: round(v / max(stage_runs, 1), 4) for k, v in stage_sum.items()},
-            "roofline": {"bound": "hbm", "kernel": "k1_moments_kernel", "achieved": round(achieved, 1) if achieved else None,
+            "roofline": {"bound": "hbm", "kernel": "k1_moments_pipe_kernel", "achieved": round(achieved, 1) if achieved else None,
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": round(k1_ms, 4)},
@@ -280,7 +281,11 @@ def main():
             e2e_value = world * B * e2e["steps"] / e2e_seconds
             line["e2e"] = {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]), "steps": e2e["steps"],
-                           "api": "bod_run_host (pinned host buffers -> padded host result blocks)"}
+                           "h2d_copied": int(e2e["h2d_copied"]), "h2d_gathered_in_place": int(e2e["h2d_gathered"]),
+                           "host_input_bytes": int(e2e["host_bytes"]),
+                           "api": "bod_run_host: pinned host buffers -> padded host result blocks; cls is copied in "
+                                  "image chunks overlapped with compute, box/cov rows of the survivors are "
+                                  "gathered in place from pinned memory"}
         # ---- CPU baseline: the oracle port on the host cores, bounded sample ----
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cls, box, cov, anchors, wl, args.cpu_sample, first_image)

@@ -161,10 +161,17 @@ int bod_run(bod_ctx* ctx, const float* cls, const float* box, const float* cov,
             const float* anchors, const float* counts, void* cuda_stream);
 
 /* Same call with HOST buffers (what a caller holding numpy arrays makes):
- * stages the inputs host->device in image chunks overlapped with compute,
- * runs the path and copies the padded results back into `out`.  Synchronous. */
+ * stages `cls` host->device in image chunks overlapped with compute, runs the
+ * path and copies the padded results back into `out`.  `box` and `cov` are only
+ * needed for the survivors: if they live in pinned (device-mapped) host memory
+ * their rows are gathered in place over PCIe, otherwise they are copied too.
+ * Synchronous. */
 int bod_run_host(bod_ctx* ctx, const float* cls, const float* box, const float* cov,
                  const float* anchors, const float* counts, bod_host_results* out);
+
+/* Bytes the last bod_run_host moved: copied host->device, read in place from
+ * pinned host memory by the survivor gather, copied device->host. */
+int bod_last_host_traffic(const bod_ctx* ctx, int64_t* h2d_copied, int64_t* h2d_gathered, int64_t* d2h);
 
 /* Second half of the drop-in on its own: bayes_od_clustering(...) for ONE image
  * from host arrays (inference_utils.py:285-364).  `affinity` is the [S,S]
