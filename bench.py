@@ -255,6 +255,13 @@ def main():
         k1_ms = stage_sum["moments_filter"] / max(stage_runs, 1)
         k1_bytes = 4.0 * N * A * K * B            # algorithmic bytes of ONE K1 launch: the [B,N,A,K] logits, read once
         achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+        traffic = None                            # dram bytes of one K1 launch from the committed ncu --set full capture
+        tp = os.path.join(ROOT, "profiles", "k1_traffic_r1.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get("workload") == args.workload and B == wl["B"]:
+                traffic = int(tj["dram_bytes_per_launch"])
         cw = 16
         bmin = bytes_min_per_image(N, A, K, S_mean, D_mean, cw)
         path_frac = (bmin * B / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak
@@ -273,7 +280,7 @@ def main():
             "stage_ms": {k: round(v / max(stage_runs, 1), 4) for k, v in stage_sum.items()},
             "roofline": {"bound": "hbm", "kernel": "k1_moments_pipe_kernel", "achieved": round(achieved, 1) if achieved else None,
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": round(k1_ms, 4)},
             "clocks": sampler.summary(t0, t1),
         }

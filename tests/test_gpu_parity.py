@@ -221,3 +221,41 @@ def test_full_size_bdd_image_bit_exact():
                              with_probs=False)
         assert 1000 < len(r.keep) < 10000
         compare_image_with_oracle(eng, res, b, r, 8, check_probs=False)
+
+
+@pytest.mark.parametrize("name", ["bdd_covar_k8", "kitti_k4_n8", "no_survivor"])
+def test_dropin_inference_utils(name):
+    """The reference-facing pair (same names / arguments / return structure as
+    inference_utils.py:13-217 and :285-364), driven the way run_inference.py:137-161 drives it."""
+    import torch
+    from bayes_od_rc_b200 import inference_utils as fast
+    g = load_golden(name)
+    meta = g["meta"]
+    pred = {fast.ANCHORS_CLASS_PREDICTIONS_KEY: torch.from_numpy(g["cls"]).cuda(),
+            fast.ANCHORS_BOX_PREDICTIONS_KEY: torch.from_numpy(g["box"]).cuda(),
+            fast.ANCHORS_COVAR_PREDICTIONS_KEY: torch.from_numpy(g["cov"]).cuda()}
+    model = lambda image, train_val_test="testing": pred      # noqa: E731
+    h, w = meta["image_shape"]
+    sample_dict = {fast.IMAGE_NORMALIZED_KEY: np.zeros((1, h, w, 3), np.float32), fast.ANCHORS_KEY: g["anchors"][None],
+                   fast.ORIGINAL_IM_SIZE_KEY: np.asarray([[meta["orig_size"][0], meta["orig_size"][1], 3]], np.int32)}
+    cfg = meta["cfg"]
+    out = fast.bayes_od_inference(model, sample_dict, cfg["bayes_od_config"], cfg["nms_config"],
+                                  use_full_covar=cfg["use_full_covar"], dataset_name=meta["dataset_name"],
+                                  counts=g["counts"])
+    counts, means, covs, nms_indices, iou_mat = [o.numpy() for o in out]          # run_inference.py:141-145
+    S, D = len(g["cnt_post"]), len(g["nms_indices"])
+    assert counts.shape == (S, g["cls"].shape[2]) and means.shape == (S, 4, 1) and covs.shape == (S, 4, 4)
+    assert np.array_equal(nms_indices, g["nms_indices"])
+    if means.size > 0:                                                               # run_inference.py:147
+        assert np.array_equal(counts, g["cnt_post"])
+        assert within_tol(means, g["mu_post"]).all()
+        fs, fm, fc, fn = fast.bayes_od_clustering(counts, means, covs, nms_indices, iou_mat,
+                                                  affinity_threshold=cfg["nms_config"]["iou_threshold"])
+        assert fm.shape == (D, 4, 1) and fc.shape == (D, 4, 4) and fs.shape == fn.shape == (D, counts.shape[1])
+        assert all(a.dtype == np.float32 for a in (fs, fm, fc, fn))
+        assert within_tol(fm, g["final_means"]).all()
+        assert np.squeeze(fm, axis=2).shape == (D, 4)                                # run_inference.py:151
+        with pytest.raises(ValueError):
+            fast.bayes_od_clustering(counts, means, covs, nms_indices, iou_mat, affinity_threshold=0.7)
+    else:
+        assert nms_indices.size == 0
