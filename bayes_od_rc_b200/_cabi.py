@@ -33,7 +33,7 @@ class BodConfig(C.Structure):
         ("num_draws", C.c_int32), ("seed", C.c_uint64), ("image_id_base", C.c_uint32),
         ("score_threshold", C.c_float), ("pre_nms_top_k", C.c_int32),
         ("anchor_mode", C.c_int32), ("im_h", C.c_int32), ("im_w", C.c_int32),
-        ("max_survivors", C.c_int32), ("emit_probs", C.c_int32),
+        ("max_survivors", C.c_int32), ("emit_probs", C.c_int32), ("pipeline_depth", C.c_int32),
     ]
 
 
@@ -65,6 +65,7 @@ SYMBOLS = {
     "bod_last_error": (C.c_char_p, [C.c_void_p]),
     "bod_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "bod_run": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "bod_wait_results": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bod_run_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(BodHostResults)]),
     "bod_last_host_traffic": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bod_cluster_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

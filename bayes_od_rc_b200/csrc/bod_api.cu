@@ -15,6 +15,27 @@
 
 using namespace bod;
 
+// Everything one run writes.  A context owns one lane (cfg.pipeline_depth <= 1) or two: with two, run i+1
+// may stream its logits (K1, scan, K2 on the head stream) while run i is still selecting centres and fusing
+// clusters (K3, membership, K4 on the tail stream), each on its own set of buffers.
+struct Lane {
+    // K1 outputs
+    int32_t* slot_anchor = nullptr; float* slot_counts = nullptr; int32_t* tile_count = nullptr;
+    int32_t* tile_off = nullptr; int32_t* num_survivors = nullptr;
+    // K2 outputs
+    int32_t* surv_anchor = nullptr; float* cnt_post = nullptr; float* mu_post = nullptr; float* sig_post = nullptr;
+    float* score = nullptr; float4* corners = nullptr; float* info = nullptr;
+    // K3 scratch + outputs
+    float* stale = nullptr; float* cur = nullptr; int32_t* begin = nullptr; uint32_t* pend = nullptr;
+    float* pw = nullptr; uint8_t* pj = nullptr;
+    int32_t* nms_idx = nullptr; float* nms_score = nullptr; int32_t* centre_anchor = nullptr; int32_t* num_dets = nullptr;
+    uint32_t* member = nullptr;
+    // K4 outputs
+    float* out_means = nullptr; float* out_covs = nullptr; float* out_param = nullptr; float* out_count = nullptr;
+    cudaEvent_t head_done = nullptr, tail_done = nullptr;
+    bool tail_pending = false;        // a tail has been issued on this lane (tail_done is meaningful)
+};
+
 struct bod_ctx {
     bod_config cfg;
     int device = 0;
@@ -23,27 +44,23 @@ struct bod_ctx {
     // one slab of device memory, carved up below
     unsigned char* slab = nullptr;
     size_t slab_bytes = 0;
-    // K1 outputs
-    int32_t* slot_anchor = nullptr; float* slot_counts = nullptr; int32_t* tile_count = nullptr;
-    int32_t* tile_off = nullptr; int32_t* num_survivors = nullptr; int32_t* status = nullptr;
+    Lane lane[2];
+    int nlanes = 1, cur = 0;          // cur: lane of the last issued run
+    int32_t* status = nullptr;
+    uint32_t* ticket = nullptr;       // K1's dynamic tile scheduler: monotonically increasing ticket counter
+    uint32_t ticket_next = 0;         // its value once every launch issued so far has finished
     float* probs = nullptr; float* sampled = nullptr;
-    // K2 outputs
-    int32_t* surv_anchor = nullptr; float* cnt_post = nullptr; float* mu_post = nullptr; float* sig_post = nullptr;
-    float* score = nullptr; float4* corners = nullptr; float* info = nullptr;
-    // K3 scratch + outputs
-    float* stale = nullptr; float* cur = nullptr; int32_t* begin = nullptr; uint32_t* pend = nullptr;
-    float* pw = nullptr; uint8_t* pj = nullptr; int fastS = 0, pstride = 0;
-    int32_t* nms_idx = nullptr; float* nms_score = nullptr; int32_t* centre_anchor = nullptr; int32_t* num_dets = nullptr;
-    uint32_t* member = nullptr;
-    // K4 outputs
-    float* out_means = nullptr; float* out_covs = nullptr; float* out_param = nullptr; float* out_count = nullptr;
+    int fastS = 0, pstride = 0;
     // device staging of host inputs (bod_run_host), allocated on first use
     float* in_cls = nullptr; float* in_box = nullptr; float* in_cov = nullptr; float* in_anchors = nullptr; float* in_counts = nullptr;
-    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
     cudaStream_t last_stream = nullptr;
-    // stage-timing events: a ring of the last kEvRing runs, 6 events each
+    cudaEvent_t ev_in = nullptr;
+    // stage-timing events: a ring of the last kEvRing runs, 7 events each
+    // (0 start, 1 K1, 2 scan, 3 K2, 4 soft-NMS + membership, 5 K4, 6 start of the tail)
     static constexpr int kEvRing = 128;
-    cudaEvent_t evring[kEvRing][6] = {{nullptr}};
+    static constexpr int kEvPerRun = 7;
+    cudaEvent_t evring[kEvRing][kEvPerRun] = {{nullptr}};
     cudaEvent_t* ev = nullptr;            // event set of the run being issued
     long long runs_recorded = 0, runs_reported = 0;
     cudaEvent_t ev_copy[4] = {nullptr};
@@ -125,42 +142,47 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     const size_t cap = (size_t)c->capacity, D = (size_t)c->Dmax;
 
     // carve the slab
+    c->nlanes = (cfg->pipeline_depth >= 2) ? 2 : 1;
+    c->fastS = k3_fast_capacity(c->capacity);
+    c->pstride = (c->Dmax + 3) & ~3;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     struct Piece { void** p; size_t o; };
     std::vector<Piece> pieces;
-#define TAKE(ptr, bytes) pieces.push_back(Piece{reinterpret_cast<void**>(&c->ptr), take(bytes)})
-    TAKE(slot_anchor, (size_t)B * A * 4);
-    TAKE(slot_counts, (size_t)B * A * K * 4);
-    TAKE(tile_count, (size_t)B * c->tiles * 4);
-    TAKE(tile_off, (size_t)B * (c->tiles + 1) * 4);
-    TAKE(num_survivors, (size_t)B * 4);
-    TAKE(status, 256);
-    if (cfg->emit_probs) { TAKE(probs, (size_t)B * A * K * 4); TAKE(sampled, (size_t)B * A * K * 4); }
-    TAKE(surv_anchor, B * cap * 4);
-    TAKE(cnt_post, B * cap * K * 4);
-    TAKE(mu_post, B * cap * 16);
-    TAKE(sig_post, B * cap * 64);
-    TAKE(score, B * cap * 4);
-    TAKE(corners, B * cap * 16);
-    TAKE(info, B * cap * 8);
-    TAKE(stale, B * cap * 4);
-    TAKE(cur, B * cap * 4);
-    TAKE(begin, B * cap * 4);
-    TAKE(pend, B * cap * kPendStride * 4);
-    c->fastS = k3_fast_capacity(c->capacity);
-    c->pstride = (c->Dmax + 3) & ~3;
-    TAKE(pw, (size_t)B * c->fastS * c->pstride * 4);
-    TAKE(pj, (size_t)B * c->fastS * c->pstride);
-    TAKE(nms_idx, B * D * 4);
-    TAKE(nms_score, B * D * 4);
-    TAKE(centre_anchor, B * D * 4);
-    TAKE(num_dets, (size_t)B * 4);
-    TAKE(member, B * D * c->words * 4);
-    TAKE(out_means, B * D * 16);
-    TAKE(out_covs, B * D * 64);
-    TAKE(out_param, B * D * K * 4);
-    TAKE(out_count, B * D * K * 4);
+#define TAKE(ptr, bytes) pieces.push_back(Piece{reinterpret_cast<void**>(&ptr), take(bytes)})
+    TAKE(c->status, 256);
+    TAKE(c->ticket, 256);
+    if (cfg->emit_probs) { TAKE(c->probs, (size_t)B * A * K * 4); TAKE(c->sampled, (size_t)B * A * K * 4); }
+    for (int l = 0; l < c->nlanes; ++l) {
+        Lane& L = c->lane[l];
+        TAKE(L.slot_anchor, (size_t)B * A * 4);
+        TAKE(L.slot_counts, (size_t)B * A * K * 4);
+        TAKE(L.tile_count, (size_t)B * c->tiles * 4);
+        TAKE(L.tile_off, (size_t)B * (c->tiles + 1) * 4);
+        TAKE(L.num_survivors, (size_t)B * 4);
+        TAKE(L.surv_anchor, B * cap * 4);
+        TAKE(L.cnt_post, B * cap * K * 4);
+        TAKE(L.mu_post, B * cap * 16);
+        TAKE(L.sig_post, B * cap * 64);
+        TAKE(L.score, B * cap * 4);
+        TAKE(L.corners, B * cap * 16);
+        TAKE(L.info, B * cap * 8);
+        TAKE(L.stale, B * cap * 4);
+        TAKE(L.cur, B * cap * 4);
+        TAKE(L.begin, B * cap * 4);
+        TAKE(L.pend, B * cap * kPendStride * 4);
+        TAKE(L.pw, (size_t)B * c->fastS * c->pstride * 4);
+        TAKE(L.pj, (size_t)B * c->fastS * c->pstride);
+        TAKE(L.nms_idx, B * D * 4);
+        TAKE(L.nms_score, B * D * 4);
+        TAKE(L.centre_anchor, B * D * 4);
+        TAKE(L.num_dets, (size_t)B * 4);
+        TAKE(L.member, B * D * c->words * 4);
+        TAKE(L.out_means, B * D * 16);
+        TAKE(L.out_covs, B * D * 64);
+        TAKE(L.out_param, B * D * K * 4);
+        TAKE(L.out_count, B * D * K * 4);
+    }
 #undef TAKE
     c->slab_bytes = off;
     e = cudaMalloc(&c->slab, off);
@@ -172,6 +194,12 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     cudaMemset(c->slab, 0, off);
     cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->tail_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
+    for (int l = 0; l < c->nlanes; ++l) {
+        cudaEventCreateWithFlags(&c->lane[l].head_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->lane[l].tail_done, cudaEventDisableTiming);
+    }
     for (auto& set : c->evring) for (auto& ev : set) cudaEventCreate(&ev);
     for (auto& ev : c->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
@@ -192,45 +220,53 @@ extern "C" void bod_destroy(bod_ctx* c) {
     for (float* p : {c->in_cls, c->in_box, c->in_cov, c->in_anchors, c->in_counts}) if (p) cudaFree(p);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    for (auto& L : c->lane) { if (L.head_done) cudaEventDestroy(L.head_done); if (L.tail_done) cudaEventDestroy(L.tail_done); }
     for (auto& set : c->evring) for (auto& ev : set) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
     delete c;
 }
 
-// Launch the stage kernels for images [b0, b0+nb) of the context's batch.
-static int run_range(bod_ctx* c, int b0, int nb, const float* cls, const float* box, const float* cov,
-                     const float* anchors, const float* counts, cudaStream_t st, bool record) {
+// Launch the stage kernels for images [b0, b0+nb) of the context's batch on lane L.  The head (K1, scan,
+// K2) goes to stream `hs`, the tail (soft-NMS, membership, K4) to `ts`; hs == ts runs them back to back.
+static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, const float* box, const float* cov,
+                     const float* anchors, const float* counts, cudaStream_t hs, cudaStream_t ts, bool record) {
     const bod_config& g = c->cfg;
-    const size_t A = g.A, K = g.K, N = g.N, cap = c->capacity, D = c->Dmax;
+    const size_t A = g.A, K = g.K, cap = c->capacity, D = c->Dmax;
     const int cw = cov_width(g.cov_layout);
 
-    if (record) CU(c, cudaEventRecord(c->ev[0], st));
+    if (record) CU(c, cudaEventRecord(c->ev[0], hs));
     K1Args k1{};
     k1.cls = cls; k1.counts_in = counts;
     k1.probs_out = c->probs ? c->probs + b0 * A * K : nullptr;
     k1.sampled_out = (c->sampled && !counts) ? c->sampled + b0 * A * K : nullptr;
-    k1.slot_anchor = c->slot_anchor + b0 * A; k1.slot_counts = c->slot_counts + b0 * A * K;
-    k1.tile_count = c->tile_count + (size_t)b0 * c->tiles;
+    k1.slot_anchor = L.slot_anchor + b0 * A; k1.slot_counts = L.slot_counts + b0 * A * K;
+    k1.tile_count = L.tile_count + (size_t)b0 * c->tiles;
     k1.B = nb; k1.N = g.N; k1.A = g.A; k1.K = g.K; k1.tiles = c->tiles;
     k1.num_draws = g.num_draws; k1.seed = g.seed; k1.image_id_base = g.image_id_base + (uint32_t)b0;
     k1.debug = c->k1_debug;
-    CU(c, launch_k1(k1, st));
-    if (record) CU(c, cudaEventRecord(c->ev[1], st));
+    k1.ticket = c->ticket; k1.ticket_base = c->ticket_next;
+    c->ticket_next += k1_tickets_per_launch(k1);           // K1 launches of a context never overlap each other
+    CU(c, launch_k1(k1, hs));
+    if (record) CU(c, cudaEventRecord(c->ev[1], hs));
 
     ScanArgs sc{};
-    sc.tile_count = k1.tile_count; sc.tile_off = c->tile_off + (size_t)b0 * (c->tiles + 1);
-    sc.num_survivors = c->num_survivors + b0; sc.status = c->status;
+    sc.tile_count = k1.tile_count; sc.tile_off = L.tile_off + (size_t)b0 * (c->tiles + 1);
+    sc.num_survivors = L.num_survivors + b0; sc.status = c->status;
     sc.B = nb; sc.tiles = c->tiles; sc.capacity = c->capacity;
-    CU(c, launch_scan(sc, st));
-    if (record) CU(c, cudaEventRecord(c->ev[2], st));
+    CU(c, launch_scan(sc, hs));
+    if (record) CU(c, cudaEventRecord(c->ev[2], hs));
 
+    // K2 overwrites what the previous tail on this lane (two runs ago) reads
+    if (hs != ts && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
     K2Args k2{};
     k2.box = box; k2.cov = cw ? cov : nullptr; k2.anchors = anchors;
     k2.slot_anchor = k1.slot_anchor; k2.slot_counts = k1.slot_counts; k2.tile_off = sc.tile_off;
     k2.num_survivors = sc.num_survivors;
-    k2.surv_anchor = c->surv_anchor + b0 * cap; k2.cnt_post = c->cnt_post + b0 * cap * K;
-    k2.mu_post = c->mu_post + b0 * cap * 4; k2.sig_post = c->sig_post + b0 * cap * 16;
-    k2.score = c->score + b0 * cap; k2.corners = c->corners + b0 * cap; k2.info = c->info + b0 * cap * 2;
+    k2.surv_anchor = L.surv_anchor + b0 * cap; k2.cnt_post = L.cnt_post + b0 * cap * K;
+    k2.mu_post = L.mu_post + b0 * cap * 4; k2.sig_post = L.sig_post + b0 * cap * 16;
+    k2.score = L.score + b0 * cap; k2.corners = L.corners + b0 * cap; k2.info = L.info + b0 * cap * 2;
     k2.B = nb; k2.N = g.N; k2.A = g.A; k2.K = g.K; k2.tiles = c->tiles; k2.capacity = c->capacity;
     k2.cov_layout = g.cov_layout; k2.use_full_covar = g.use_full_covar;
     k2.dirichlet_prior = g.dirichlet_prior; k2.gaussian_prior = g.gaussian_prior;
@@ -239,34 +275,40 @@ static int run_range(bod_ctx* c, int b0, int nb, const float* cls, const float* 
                          g.dirichlet_prior != BOD_PRIOR_NONE) ? 1 : 0;
     k2.isotropic_variance = g.isotropic_variance; k2.scale_v = g.scale_v; k2.scale_u = g.scale_u;
     k2.anchor_mode = g.anchor_mode; k2.im_h = g.im_h; k2.im_w = g.im_w;
-    CU(c, launch_k2(k2, st));
+    CU(c, launch_k2(k2, hs));
     int launches = 3;
-    if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, st)); ++launches; }
-    if (record) CU(c, cudaEventRecord(c->ev[3], st));
+    if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, hs)); ++launches; }
+    if (record) CU(c, cudaEventRecord(c->ev[3], hs));
+    if (hs != ts) {
+        CU(c, cudaEventRecord(L.head_done, hs));
+        CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));
+    }
+    if (record) CU(c, cudaEventRecord(c->ev[6], ts));
 
     K3Args k3{};
     k3.corners = k2.corners; k3.score = k2.score; k3.num_survivors = sc.num_survivors; k3.surv_anchor = k2.surv_anchor;
-    k3.stale = c->stale + b0 * cap; k3.cur = c->cur + b0 * cap; k3.begin = c->begin + b0 * cap;
-    k3.pend = c->pend + b0 * cap * kPendStride;
-    k3.pw = c->pw + (size_t)b0 * c->fastS * c->pstride; k3.pj = c->pj + (size_t)b0 * c->fastS * c->pstride;
+    k3.stale = L.stale + b0 * cap; k3.cur = L.cur + b0 * cap; k3.begin = L.begin + b0 * cap;
+    k3.pend = L.pend + b0 * cap * kPendStride;
+    k3.pw = L.pw + (size_t)b0 * c->fastS * c->pstride; k3.pj = L.pj + (size_t)b0 * c->fastS * c->pstride;
     k3.fastS = c->fastS; k3.pstride = c->pstride;
-    k3.nms_idx = c->nms_idx + b0 * D; k3.nms_score = c->nms_score + b0 * D; k3.centre_anchor = c->centre_anchor + b0 * D;
-    k3.num_dets = c->num_dets + b0; k3.member = c->member + b0 * D * c->words;
+    k3.nms_idx = L.nms_idx + b0 * D; k3.nms_score = L.nms_score + b0 * D; k3.centre_anchor = L.centre_anchor + b0 * D;
+    k3.num_dets = L.num_dets + b0; k3.member = L.member + b0 * D * c->words;
     k3.B = nb; k3.capacity = c->capacity; k3.Dmax = c->Dmax; k3.words = c->words;
     k3.iou_threshold = g.iou_threshold; k3.soft_nms_sigma = g.soft_nms_sigma;
     k3.dbg = c->k3_dbg ? c->k3_dbg + (size_t)b0 * 8 : nullptr;
-    CU(c, launch_k3(k3, st));
-    if (record) CU(c, cudaEventRecord(c->ev[4], st));
+    CU(c, launch_k3(k3, ts));
+    if (record) CU(c, cudaEventRecord(c->ev[4], ts));
 
     K4Args k4{};
     k4.cnt_post = k2.cnt_post; k4.mu_post = k2.mu_post; k4.sig_post = k2.sig_post; k4.num_survivors = sc.num_survivors;
     k4.nms_idx = k3.nms_idx; k4.num_dets = k3.num_dets; k4.member = k3.member;
-    k4.out_means = c->out_means + b0 * D * 4; k4.out_covs = c->out_covs + b0 * D * 16;
-    k4.out_param = c->out_param + b0 * D * K; k4.out_count = c->out_count + b0 * D * K;
+    k4.out_means = L.out_means + b0 * D * 4; k4.out_covs = L.out_covs + b0 * D * 16;
+    k4.out_param = L.out_param + b0 * D * K; k4.out_count = L.out_count + b0 * D * K;
     k4.B = nb; k4.K = g.K; k4.capacity = c->capacity; k4.Dmax = c->Dmax; k4.words = c->words;
     k4.calibration = g.cov_calibration;
-    CU(c, launch_k4(k4, st));
-    if (record) CU(c, cudaEventRecord(c->ev[5], st));
+    CU(c, launch_k4(k4, ts));
+    if (record) CU(c, cudaEventRecord(c->ev[5], ts));
+    if (hs != ts) { CU(c, cudaEventRecord(L.tail_done, ts)); L.tail_pending = true; }
     c->launches += launches + 3;   // + soft-NMS, membership, K4
     return BOD_OK;
 }
@@ -290,11 +332,36 @@ extern "C" int bod_run(bod_ctx* c, const float* cls, const float* box, const flo
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     c->launches = 0;
     c->ev = c->evring[c->runs_recorded % bod_ctx::kEvRing];
-    rc = run_range(c, 0, c->cfg.B, cls, box, cov, anchors, counts, st, c->timing);
-    if (rc) return rc;
+    if (c->nlanes == 1) {
+        c->cur = 0;
+        rc = run_range(c, c->lane[0], 0, c->cfg.B, cls, box, cov, anchors, counts, st, st, c->timing);
+        if (rc) return rc;
+        c->last_stream = st;
+    } else {
+        // pipelined: the head runs on the context's own stream once the caller's stream has reached this
+        // point; the tail floats on a second stream.  The caller's stream only waits for the head (the
+        // last reader of the inputs); results are complete at bod_fetch / bod_wait_results.
+        c->cur ^= 1;
+        Lane& L = c->lane[c->cur];
+        CU(c, cudaEventRecord(c->ev_in, st));
+        CU(c, cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
+        rc = run_range(c, L, 0, c->cfg.B, cls, box, cov, anchors, counts, c->own_stream, c->tail_stream, c->timing);
+        if (rc) return rc;
+        CU(c, cudaStreamWaitEvent(st, L.head_done, 0));
+        c->last_stream = c->tail_stream;
+    }
     if (c->timing) ++c->runs_recorded;
     c->last_timed = c->timing;
-    c->last_stream = st; c->ran = true; c->used_sampler = (counts == nullptr);
+    c->ran = true; c->used_sampler = (counts == nullptr);
+    return BOD_OK;
+}
+
+extern "C" int bod_wait_results(bod_ctx* c, void* cuda_stream) {
+    if (!c) return BOD_ERR_INVALID;
+    if (!c->ran) return fail(c, BOD_ERR_STATE, "no bod_run has been issued on this context");
+    CU(c, cudaSetDevice(c->device));
+    Lane& L = c->lane[c->cur];
+    if (c->nlanes > 1 && L.tail_pending) CU(c, cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(cuda_stream), L.tail_done, 0));
     return BOD_OK;
 }
 
@@ -313,7 +380,8 @@ static int sync_and_status(bod_ctx* c) {
 
 static int copy_results(bod_ctx* c, bod_host_results* out, cudaStream_t st) {
     const size_t B = c->cfg.B, D = c->Dmax, K = c->cfg.K;
-#define D2H(dst, src, bytes) if (out->dst) CU(c, cudaMemcpyAsync(out->dst, c->src, (bytes), cudaMemcpyDeviceToHost, st))
+    const Lane& L = c->lane[c->cur];
+#define D2H(dst, src, bytes) if (out->dst) CU(c, cudaMemcpyAsync(out->dst, L.src, (bytes), cudaMemcpyDeviceToHost, st))
     D2H(num_dets, num_dets, B * 4);
     D2H(num_survivors, num_survivors, B * 4);
     D2H(means, out_means, B * D * 16);
@@ -339,9 +407,10 @@ extern "C" int bod_fetch(bod_ctx* c, bod_host_results* out) {
 
 extern "C" int bod_device_results_of(bod_ctx* c, bod_device_results* out) {
     if (!c || !out) return BOD_ERR_INVALID;
-    out->num_dets = c->num_dets; out->num_survivors = c->num_survivors;
-    out->means = c->out_means; out->covs = c->out_covs; out->cat_param = c->out_param; out->cat_count = c->out_count;
-    out->nms_indices = c->nms_idx; out->centre_anchor_idx = c->centre_anchor; out->centre_scores = c->nms_score;
+    const Lane& L = c->lane[c->cur];          // the lane of the last issued run
+    out->num_dets = L.num_dets; out->num_survivors = L.num_survivors;
+    out->means = L.out_means; out->covs = L.out_covs; out->cat_param = L.out_param; out->cat_count = L.out_count;
+    out->nms_indices = L.nms_idx; out->centre_anchor_idx = L.centre_anchor; out->centre_scores = L.nms_score;
     return BOD_OK;
 }
 
@@ -350,12 +419,13 @@ extern "C" int bod_fetch_survivors(bod_ctx* c, int32_t b, bod_host_survivors* ou
     int rc = sync_and_status(c);
     if (rc) return rc;
     int32_t S = 0;
-    CU(c, cudaMemcpy(&S, c->num_survivors + b, 4, cudaMemcpyDeviceToHost));
+    const Lane& L = c->lane[c->cur];
+    CU(c, cudaMemcpy(&S, L.num_survivors + b, 4, cudaMemcpyDeviceToHost));
     out->count = S;
     if (S > out->capacity) return fail(c, BOD_ERR_INVALID, "bod_fetch_survivors: capacity %d < S %d", out->capacity, S);
     const size_t cap = c->capacity, K = c->cfg.K, s = (size_t)S;
     if (S == 0) return BOD_OK;
-#define D2H(dst, src, off, bytes) if (out->dst) CU(c, cudaMemcpy(out->dst, c->src + (off), (bytes), cudaMemcpyDeviceToHost))
+#define D2H(dst, src, off, bytes) if (out->dst) CU(c, cudaMemcpy(out->dst, L.src + (off), (bytes), cudaMemcpyDeviceToHost))
     D2H(anchor_idx, surv_anchor, b * cap, s * 4);
     D2H(counts, cnt_post, b * cap * K, s * K * 4);
     D2H(means, mu_post, b * cap * 4, s * 16);
@@ -371,12 +441,13 @@ extern "C" int bod_fetch_members(bod_ctx* c, int32_t b, uint32_t* mask, int32_t 
     int rc = sync_and_status(c);
     if (rc) return rc;
     int32_t S = 0, D = 0;
-    CU(c, cudaMemcpy(&S, c->num_survivors + b, 4, cudaMemcpyDeviceToHost));
-    CU(c, cudaMemcpy(&D, c->num_dets + b, 4, cudaMemcpyDeviceToHost));
+    const Lane& L = c->lane[c->cur];
+    CU(c, cudaMemcpy(&S, L.num_survivors + b, 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&D, L.num_dets + b, 4, cudaMemcpyDeviceToHost));
     const int nw = (S + 31) / 32;
     if (words_per_row < nw) return fail(c, BOD_ERR_INVALID, "bod_fetch_members: words_per_row %d < %d", words_per_row, nw);
     if (D == 0 || nw == 0) return BOD_OK;
-    CU(c, cudaMemcpy2D(mask, (size_t)words_per_row * 4, c->member + (size_t)b * c->Dmax * c->words, (size_t)c->words * 4,
+    CU(c, cudaMemcpy2D(mask, (size_t)words_per_row * 4, L.member + (size_t)b * c->Dmax * c->words, (size_t)c->words * 4,
                        (size_t)nw * 4, D, cudaMemcpyDeviceToHost));
     return BOD_OK;
 }
@@ -424,7 +495,7 @@ extern "C" int bod_last_stage_ms(bod_ctx* c, float ms[6]) {
     if (rc) return rc;
     if (!c->last_timed || c->runs_recorded == 0) return fail(c, BOD_ERR_STATE, "the last run recorded no stage events");
     cudaEvent_t* ev = c->evring[(c->runs_recorded - 1) % bod_ctx::kEvRing];
-    for (int i = 0; i < 5; ++i) CU(c, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    for (int i = 0; i < 5; ++i) CU(c, cudaEventElapsedTime(&ms[i], ev[i == 3 ? 6 : i], ev[i + 1]));
     CU(c, cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
     return BOD_OK;
 }
@@ -447,7 +518,7 @@ extern "C" int bod_stage_ms_accum(bod_ctx* c, float sum_ms[6], int32_t* runs) {
     for (long long r = first; r < c->runs_recorded; ++r) {
         cudaEvent_t* ev = c->evring[r % bod_ctx::kEvRing];
         float ms = 0.0f;
-        for (int i = 0; i < 5; ++i) { CU(c, cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); sum_ms[i] += ms; }
+        for (int i = 0; i < 5; ++i) { CU(c, cudaEventElapsedTime(&ms, ev[i == 3 ? 6 : i], ev[i + 1])); sum_ms[i] += ms; }
         CU(c, cudaEventElapsedTime(&ms, ev[0], ev[5])); sum_ms[5] += ms;
         ++*runs;
     }
@@ -495,6 +566,9 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
     if (!box_m && !c->in_box) CU(c, cudaMalloc(&c->in_box, B * N * A * 16));
     if (cw && !cov_m && !c->in_cov) CU(c, cudaMalloc(&c->in_cov, B * N * A * cw * 4));
     cudaStream_t cs = c->copy_stream, st = c->own_stream;
+    if (c->nlanes > 1) CU(c, cudaStreamSynchronize(c->tail_stream));    // drain pipelined runs; this entry is synchronous
+    c->cur = 0;
+    Lane& L = c->lane[0];
     c->launches = 0;
     c->last_timed = false;
     c->h2d_copied = 0; c->h2d_mapped_rows = 0; c->d2h_copied = 0;
@@ -521,10 +595,10 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
         cudaEvent_t ev = c->ev_copy[nev++ & 3];
         CU(c, cudaEventRecord(ev, cs));
         CU(c, cudaStreamWaitEvent(st, ev, 0));
-        rc = run_range(c, (int)b0, (int)nb, c->in_cls + b0 * N * A * K,
+        rc = run_range(c, L, (int)b0, (int)nb, c->in_cls + b0 * N * A * K,
                        box_m ? box_m + b0 * N * A * 4 : c->in_box + b0 * N * A * 4,
                        cw ? (cov_m ? cov_m + b0 * N * A * cw : c->in_cov + b0 * N * A * cw) : nullptr,
-                       anchors ? c->in_anchors : nullptr, counts ? c->in_counts + b0 * A * K : nullptr, st, false);
+                       anchors ? c->in_anchors : nullptr, counts ? c->in_counts + b0 * A * K : nullptr, st, st, false);
         if (rc) return rc;
     }
     c->last_stream = st; c->ran = true; c->used_sampler = (counts == nullptr);
@@ -540,7 +614,7 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
     // rows read in place from mapped host memory: N * (16 [+ 4*cw]) bytes per survivor
     if (box_m || cov_m) {
         std::vector<int32_t> ns(B);
-        CU(c, cudaMemcpy(ns.data(), c->num_survivors, B * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(ns.data(), L.num_survivors, B * 4, cudaMemcpyDeviceToHost));
         int64_t S = 0;
         for (size_t b = 0; b < B; ++b) S += ns[b];
         c->h2d_mapped_rows = S * (int64_t)N * ((box_m ? 16 : 0) + (cov_m ? (int64_t)cw * 4 : 0));
@@ -575,6 +649,9 @@ extern "C" int bod_cluster_host(bod_ctx* c, int32_t S, const float* counts, cons
         if (centres[d] < 0 || centres[d] >= S) return fail(c, BOD_ERR_INVALID, "bod_cluster_host: centre index out of range");
     CU(c, cudaSetDevice(c->device));
     cudaStream_t st = c->own_stream;
+    if (c->nlanes > 1) CU(c, cudaStreamSynchronize(c->tail_stream));
+    c->cur = 0;
+    Lane& L = c->lane[0];
     const size_t K = c->cfg.K, Dm = c->Dmax;
     c->launches = 0;
     int rc = BOD_OK;
@@ -584,21 +661,21 @@ extern "C" int bod_cluster_host(bod_ctx* c, int32_t S, const float* counts, cons
         for (int s = 0; s < S; ++s)
             if (affinity[(size_t)s * S + centres[d]] > affinity_threshold) mask[(size_t)d * c->words + (s >> 5)] |= 1u << (s & 31);
     if (S > 0) {
-        CU(c, cudaMemcpyAsync(c->cnt_post, counts, (size_t)S * K * 4, cudaMemcpyHostToDevice, st));
-        CU(c, cudaMemcpyAsync(c->mu_post, means, (size_t)S * 16, cudaMemcpyHostToDevice, st));
-        CU(c, cudaMemcpyAsync(c->sig_post, covs, (size_t)S * 64, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemcpyAsync(L.cnt_post, counts, (size_t)S * K * 4, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemcpyAsync(L.mu_post, means, (size_t)S * 16, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemcpyAsync(L.sig_post, covs, (size_t)S * 64, cudaMemcpyHostToDevice, st));
     }
     if (D > 0) {
-        CU(c, cudaMemcpyAsync(c->nms_idx, centres, (size_t)D * 4, cudaMemcpyHostToDevice, st));
-        CU(c, cudaMemcpyAsync(c->member, mask.data(), (size_t)D * c->words * 4, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemcpyAsync(L.nms_idx, centres, (size_t)D * 4, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemcpyAsync(L.member, mask.data(), (size_t)D * c->words * 4, cudaMemcpyHostToDevice, st));
     }
-    CU(c, cudaMemcpyAsync(c->num_survivors, &S, 4, cudaMemcpyHostToDevice, st));
-    CU(c, cudaMemcpyAsync(c->num_dets, &D, 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(L.num_survivors, &S, 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(L.num_dets, &D, 4, cudaMemcpyHostToDevice, st));
     CU(c, cudaStreamSynchronize(st));          // `mask`, S, D are stack/heap temporaries
     K4Args k4{};
-    k4.cnt_post = c->cnt_post; k4.mu_post = c->mu_post; k4.sig_post = c->sig_post; k4.num_survivors = c->num_survivors;
-    k4.nms_idx = c->nms_idx; k4.num_dets = c->num_dets; k4.member = c->member;
-    k4.out_means = c->out_means; k4.out_covs = c->out_covs; k4.out_param = c->out_param; k4.out_count = c->out_count;
+    k4.cnt_post = L.cnt_post; k4.mu_post = L.mu_post; k4.sig_post = L.sig_post; k4.num_survivors = L.num_survivors;
+    k4.nms_idx = L.nms_idx; k4.num_dets = L.num_dets; k4.member = L.member;
+    k4.out_means = L.out_means; k4.out_covs = L.out_covs; k4.out_param = L.out_param; k4.out_count = L.out_count;
     k4.B = 1; k4.K = (int)K; k4.capacity = c->capacity; k4.Dmax = (int)Dm; k4.words = c->words;
     k4.calibration = c->cfg.cov_calibration;
     CU(c, launch_k4(k4, st));

@@ -19,7 +19,11 @@ struct K1Args {
     uint64_t seed;
     uint32_t image_id_base;
     int debug;               // diagnostics only: 1 = skip sampler/compaction, 2 = also skip the softmax
+    uint32_t* ticket;        // dynamic tile scheduler: global ticket counter (never reset) ...
+    uint32_t ticket_base;    // ... and its value when this launch starts
 };
+// tickets a launch of launch_k1 consumes (tiles + one failing fetch per CTA); 0 for the non-pipelined fallback
+uint32_t k1_tickets_per_launch(const K1Args& a);
 cudaError_t launch_k1(const K1Args& a, cudaStream_t st);
 bool k1_supports(int K);
 

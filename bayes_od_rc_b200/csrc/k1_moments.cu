@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(kTileAnchors + 32, kPipeCtasPerSM)
 k1_moments_pipe_kernel(K1Args a, int NS) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+    __shared__ int stage_tile[kMaxStages];            // tile whose first slab sits in the stage (-1: no more work)
     __shared__ int warp_count[2][kConsumerWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -339,17 +340,27 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
     __syncthreads();
 
     if (warp == kConsumerWarps) {
-        // ---- producer: one thread feeds the ring, up to NS slabs ahead of the consumers ----
+        // ---- producer: one thread feeds the ring, up to NS slabs ahead of the consumers.  Tiles come
+        // from a global ticket counter, so CTAs that start late (SMs busy with another stream's
+        // kernels) simply take fewer tiles ----
         if (lane == 0) {
             int stage = 0, round = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int b = t / tiles, tile = t - b * tiles;
+            for (;;) {
+                const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
+                if (round > 0) mbar_wait(&empty_bar[stage], (uint32_t)((round - 1) & 1));
+                if (t >= (uint32_t)total_tiles) {                 // no work left: tell the consumers
+                    stage_tile[stage] = -1;
+                    mbar_arrive(&full_bar[stage]);
+                    break;
+                }
+                stage_tile[stage] = (int)t;
+                const int b = (int)t / tiles, tile = (int)t - b * tiles;
                 const int a0 = tile * kTileAnchors;
                 const int rows = min(kTileAnchors, a.A - a0);
                 const uint32_t bytes = (uint32_t)rows * K * 4u;
                 const float* src = a.cls + ((size_t)b * N * a.A + a0) * K;
                 for (int n = 0; n < N; ++n) {
-                    if (round > 0) mbar_wait(&empty_bar[stage], (uint32_t)((round - 1) & 1));
+                    if (n > 0 && round > 0) mbar_wait(&empty_bar[stage], (uint32_t)((round - 1) & 1));
                     mbar_expect_tx(&full_bar[stage], bytes);
                     bulk_g2s(ring + stage * slab_stride, src + (size_t)n * a.A * K, bytes, &full_bar[stage]);
                     if (++stage == NS) { stage = 0; ++round; }
@@ -360,8 +371,11 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
     }
 
     // ---- consumers: one thread per anchor of the tile ----
-    int stage = 0, phase = 0, tcount = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
+    int stage = 0, phase = 0;
+    for (int tcount = 0;; ++tcount) {
+        mbar_wait(&full_bar[stage], (uint32_t)phase);        // first slab of the next tile, or the end marker
+        const int t = stage_tile[stage];
+        if (t < 0) break;
         const int b = t / tiles, tile = t - b * tiles;
         const int a0 = tile * kTileAnchors;
         const int rows = min(kTileAnchors, a.A - a0);
@@ -382,7 +396,7 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
 #pragma unroll
         for (int k = 0; k < K; ++k) p[k] = 0.0f;
         for (int n = 0; n < N; ++n) {
-            mbar_wait(&full_bar[stage], (uint32_t)phase);
+            if (n > 0) mbar_wait(&full_bar[stage], (uint32_t)phase);
             if (valid && a.debug < 2) {
                 const float* row = ring + stage * slab_stride + tid * K;
                 float x[K];
@@ -463,6 +477,22 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
     }
 }
 
+static bool k1_aligned(const K1Args& a) {
+    return ((reinterpret_cast<uintptr_t>(a.cls) & 15u) == 0) && (((size_t)a.A * a.K) % 4 == 0) &&
+           ((kTileAnchors * a.K) % 4 == 0);
+}
+static int k1_pipe_ctas(const K1Args& a) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int ctas = kPipeCtasPerSM * sms;
+    if (ctas > a.B * a.tiles) ctas = a.B * a.tiles;
+    return ctas;
+}
+uint32_t k1_tickets_per_launch(const K1Args& a) {
+    return k1_aligned(a) ? (uint32_t)(a.B * a.tiles + k1_pipe_ctas(a)) : 0u;
+}
+
 template <int K>
 static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     // samples per ring stage: two stages of <= ~50 KB keep two CTAs resident per SM
@@ -472,8 +502,7 @@ static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     if (NC > a.N) NC = a.N;
     const size_t smem = 2 * (size_t)NC * slab;
     // bulk copies need 16-byte aligned sources and sizes for every (image, sample, tile)
-    const bool aligned = ((reinterpret_cast<uintptr_t>(a.cls) & 15u) == 0) && (((size_t)a.A * K) % 4 == 0) &&
-                         ((kTileAnchors * K) % 4 == 0);
+    const bool aligned = k1_aligned(a);
     dim3 grid(a.tiles, a.B), block(kTileAnchors);
     cudaError_t e;
     if (aligned) {
@@ -482,11 +511,7 @@ static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
         if (NS > kMaxStages) NS = kMaxStages;
         if (NS < 2) NS = 2;
         const size_t ring = (size_t)NS * slab;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int ctas = kPipeCtasPerSM * sms;
-        if (ctas > a.B * a.tiles) ctas = a.B * a.tiles;
+        const int ctas = k1_pipe_ctas(a);
         e = cudaFuncSetAttribute(k1_moments_pipe_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
         if (e != cudaSuccess) return e;
         k1_moments_pipe_kernel<K><<<ctas, kTileAnchors + 32, ring, st>>>(a, NS);

@@ -46,6 +46,7 @@ class BayesODConfig:
     im_w: int = 0
     max_survivors: int = 0
     emit_probs: bool = False
+    pipeline_depth: int = 1
 
     @classmethod
     def from_reference(cls, bayes_od_config: dict, nms_config: dict, use_full_covar: bool = False, **kw):
@@ -71,7 +72,8 @@ class BayesODConfig:
             cov_calibration=self.cov_calibration, num_draws=self.num_draws, seed=self.seed,
             image_id_base=self.image_id_base, score_threshold=self.score_threshold,
             pre_nms_top_k=self.pre_nms_top_k, anchor_mode=self.anchor_mode, im_h=self.im_h, im_w=self.im_w,
-            max_survivors=self.max_survivors, emit_probs=int(self.emit_probs))
+            max_survivors=self.max_survivors, emit_probs=int(self.emit_probs),
+            pipeline_depth=int(self.pipeline_depth))
 
 
 # --------------------------------------------------------------------------
@@ -241,6 +243,10 @@ class BayesODEngine:
         p_cnt = device_ptr(counts, B * A * K, keep) if counts is not None else None
         self._keep = (cls, box, cov, anchors, counts, keep)          # keep the buffers alive until fetch
         self._check(self.lib.bod_run(self._ctx, p_cls, p_box, p_cov, p_anc, p_cnt, C.c_void_p(int(stream) or None)))
+
+    def wait_results(self, stream=0):
+        """Make ``stream`` wait for the results of the last run (pipeline_depth = 2 only; bod_wait_results)."""
+        self._check(self.lib.bod_wait_results(self._ctx, C.c_void_p(int(stream) or None)))
 
     def fetch(self) -> Results:
         self._check(self.lib.bod_fetch(self._ctx, C.byref(self._hres)))

@@ -137,6 +137,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = auto)")
+    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+                    help="bod_config.pipeline_depth: 2 = step i+1's K1/K2 overlap step i's soft-NMS/fusion")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
@@ -182,7 +184,7 @@ def main():
 
     cfg = BayesODConfig(use_full_covar=wl["use_full_covar"], cov_layout=_cabi.COV_FULL16, seed=1234,
                         image_id_base=first_image, scale_v=wl.get("scale_v", 1.0), scale_u=wl.get("scale_u", 1.0),
-                        max_survivors=min(A, 32768))
+                        max_survivors=min(A, 32768), pipeline_depth=args.pipeline)
     eng = BayesODEngine(B, N, A, K, cfg, device=local_rank)
     stream = torch.cuda.Stream(device=dev)
 
@@ -207,6 +209,7 @@ def main():
     ev0.record(stream)
     for _ in range(args.steps):
         step()
+    eng.wait_results(stream.cuda_stream)         # pipelined: the stream has only waited for the heads so far
     ev1.record(stream)
     barrier()
     t1 = time.perf_counter()
@@ -216,6 +219,27 @@ def main():
     S_mean = float(res.num_survivors.mean())
     D_mean = float(res.num_dets.mean())
     launches_per_step = eng.launch_count
+
+    # ---- for reference: the same steps issued one after the other (no overlap between steps) ----
+    serial = None
+    if args.pipeline > 1:
+        import dataclasses
+        eng1 = BayesODEngine(B, N, A, K, dataclasses.replace(cfg, pipeline_depth=1), device=local_rank)
+        n1 = max(3, min(args.steps, 20))
+        for _ in range(3):
+            eng1.run(cls, box, cov, anchors, None, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        eng1.stage_ms_accum()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(n1):
+            eng1.run(cls, box, cov, anchors, None, stream=stream.cuda_stream)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        ssum, sruns = eng1.stage_ms_accum()
+        serial = {"ms_per_step": round(s0.elapsed_time(s1) / n1, 4), "steps": n1,
+                  "stage_ms": {k: round(v / max(sruns, 1), 4) for k, v in ssum.items()}}
+        eng1.close()
 
     # ---- end to end: pinned host inputs -> bod_run_host -> host results ----
     e2e = None
@@ -274,6 +298,7 @@ def main():
                                    f"use_full_covar={wl['use_full_covar']} cov=[N,A,4,4] philox-sampler seed=1234",
                        "images_per_gpu": B, "global_batch": B * world, "parallelism": f"image-shard x{world}, no collective",
                        "l2": "inputs (%.2f GB per step) larger than L2" % ((cls.numel() + box.numel() + cov.numel()) * 4 / 1e9),
+                       "pipeline_depth": args.pipeline,
                        "mean_survivors": round(S_mean, 1), "mean_dets": round(D_mean, 1),
                        "bytes_min_per_image": int(bmin), "path_roofline_frac": round(path_frac, 4)},
             "gpu_launches": launches_per_step * args.steps,
@@ -284,6 +309,8 @@ def main():
                          "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": round(k1_ms, 4)},
             "clocks": sampler.summary(t0, t1),
         }
+        if serial:
+            line["serial"] = serial           # pipeline_depth = 1: whole steps back to back, stage times undisturbed
         if e2e:
             e2e_value = world * B * e2e["steps"] / e2e_seconds
             line["e2e"] = {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(e2e["h2d"]),

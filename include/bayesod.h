@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BOD_ABI_VERSION 3
+#define BOD_ABI_VERSION 4
 
 typedef enum bod_status {
     BOD_OK            = 0,
@@ -86,6 +86,13 @@ typedef struct bod_config {
     int32_t  im_h, im_w;         /* image shape for BOD_ANCHORS_GENERATE                   */
     int32_t  max_survivors;      /* per-image survivor capacity; 0 => A                    */
     int32_t  emit_probs;         /* keep the [B,A,K] mean class probabilities (parity)     */
+    int32_t  pipeline_depth;     /* 0/1: every bod_run is issued whole, in order, on the
+                                    caller's stream.  2: two sets of buffers; run i+1 streams
+                                    its logits (K1, scan, K2) while run i is still selecting
+                                    centres and fusing (soft-NMS, K4) on a second internal
+                                    stream.  The caller's stream then only waits for the
+                                    part that reads the inputs; results are complete at
+                                    bod_fetch or after bod_wait_results                      */
 } bod_config;
 
 typedef struct bod_ctx bod_ctx;
@@ -107,7 +114,8 @@ typedef struct bod_host_results {
     float*   centre_scores;     /* [B,Dmax]     soft-NMS score at selection time          */
 } bod_host_results;
 
-/* The same blocks as device pointers (valid until the next bod_run on ctx),
+/* The same blocks as device pointers (valid until the next bod_run on ctx; with
+ * pipeline_depth = 2 until the run after the next),
  * for consumers that stay on the GPU (e.g. an NCCL all-gather of detections). */
 typedef struct bod_device_results {
     const int32_t* num_dets;
@@ -159,6 +167,12 @@ int64_t bod_workspace_bytes(const bod_ctx* ctx);
  */
 int bod_run(bod_ctx* ctx, const float* cls, const float* box, const float* cov,
             const float* anchors, const float* counts, void* cuda_stream);
+
+/* Make `cuda_stream` wait (on the device, without blocking the host) until the
+ * results of the last bod_run are complete.  Only needed with pipeline_depth = 2
+ * by consumers that read bod_device_results_of on their own stream; a no-op
+ * otherwise (the run is already ordered on the caller's stream). */
+int bod_wait_results(bod_ctx* ctx, void* cuda_stream);
 
 /* Same call with HOST buffers (what a caller holding numpy arrays makes):
  * stages `cls` host->device in image chunks overlapped with compute, runs the
