@@ -27,7 +27,7 @@ struct Lane {
     float* score = nullptr; float4* corners = nullptr; float* info = nullptr;
     // K3 scratch + outputs
     float* stale = nullptr; float* cur = nullptr; int32_t* begin = nullptr; uint32_t* pend = nullptr;
-    float* pw = nullptr; uint8_t* pj = nullptr;
+    float* pw = nullptr;
     int32_t* nms_idx = nullptr; float* nms_score = nullptr; int32_t* centre_anchor = nullptr; int32_t* num_dets = nullptr;
     uint32_t* member = nullptr;
     // K4 outputs
@@ -70,6 +70,8 @@ struct bod_ctx {
     bool host_copy_all = false;       // BOD_HOST_COPY_ALL: never read box/cov in place from pinned host memory
     int k1_debug = 0;                 // BOD_K1_DEBUG (diagnostics)
     long long* k3_dbg = nullptr;      // BOD_K3_DEBUG (diagnostics): [B][8] cycle counters
+    bool k2_on_tail = false;          // pipelined mode: issue K2 with the tail (BOD_K2_TAIL=1, experiment)
+    int k3_seg_cap = -1, k3_psm_max = -1;   // BOD_K3_SEGCAP / BOD_K3_PSM_MAX (tests: reach the overflow paths on small inputs)
 };
 
 static int fail(bod_ctx* c, int code, const char* fmt, ...) {
@@ -172,7 +174,6 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
         TAKE(L.begin, B * cap * 4);
         TAKE(L.pend, B * cap * kPendStride * 4);
         TAKE(L.pw, (size_t)B * c->fastS * c->pstride * 4);
-        TAKE(L.pj, (size_t)B * c->fastS * c->pstride);
         TAKE(L.nms_idx, B * D * 4);
         TAKE(L.nms_score, B * D * 4);
         TAKE(L.centre_anchor, B * D * 4);
@@ -194,7 +195,13 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     cudaMemset(c->slab, 0, off);
     cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&c->tail_stream, cudaStreamNonBlocking);
+    {
+        int lo = 0, hi = 0;                                  // the tail is latency-bound and short: let its CTAs go first
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char* pr = getenv("BOD_TAIL_PRIORITY");
+        const int tail_prio = (pr && atoi(pr) == 0) ? lo : hi;
+        cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, tail_prio);
+    }
     cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
     for (int l = 0; l < c->nlanes; ++l) {
         cudaEventCreateWithFlags(&c->lane[l].head_done, cudaEventDisableTiming);
@@ -205,6 +212,9 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
     if (const char* d = getenv("BOD_K1_DEBUG")) c->k1_debug = atoi(d);
     c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
+    if (const char* d = getenv("BOD_K2_TAIL")) c->k2_on_tail = atoi(d) != 0;
+    if (const char* d = getenv("BOD_K3_SEGCAP")) { int v = atoi(d); if (v >= 0) c->k3_seg_cap = v; }
+    if (const char* d = getenv("BOD_K3_PSM_MAX")) c->k3_psm_max = atoi(d);
     if (getenv("BOD_K3_DEBUG")) { cudaMalloc(&c->k3_dbg, (size_t)B * 8 * sizeof(long long)); cudaMemset(c->k3_dbg, 0, (size_t)B * 8 * sizeof(long long)); }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { snprintf(create_err, sizeof create_err, "init: %s", cudaGetErrorString(e)); bod_destroy(c); return BOD_ERR_CUDA; }
@@ -259,7 +269,14 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
     if (record) CU(c, cudaEventRecord(c->ev[2], hs));
 
     // K2 overwrites what the previous tail on this lane (two runs ago) reads
-    if (hs != ts && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
+    const bool k2_tail = (hs != ts) && c->k2_on_tail;
+    cudaStream_t k2s = k2_tail ? ts : hs;
+    if (k2_tail) {
+        CU(c, cudaEventRecord(L.head_done, hs));
+        CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));     // same-stream order already covers the lane's previous tail
+    } else if (hs != ts && L.tail_pending) {
+        CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
+    }
     K2Args k2{};
     k2.box = box; k2.cov = cw ? cov : nullptr; k2.anchors = anchors;
     k2.slot_anchor = k1.slot_anchor; k2.slot_counts = k1.slot_counts; k2.tile_off = sc.tile_off;
@@ -275,11 +292,11 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
                          g.dirichlet_prior != BOD_PRIOR_NONE) ? 1 : 0;
     k2.isotropic_variance = g.isotropic_variance; k2.scale_v = g.scale_v; k2.scale_u = g.scale_u;
     k2.anchor_mode = g.anchor_mode; k2.im_h = g.im_h; k2.im_w = g.im_w;
-    CU(c, launch_k2(k2, hs));
+    CU(c, launch_k2(k2, k2s));
     int launches = 3;
-    if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, hs)); ++launches; }
-    if (record) CU(c, cudaEventRecord(c->ev[3], hs));
-    if (hs != ts) {
+    if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, k2s)); ++launches; }
+    if (record) CU(c, cudaEventRecord(c->ev[3], k2s));
+    if (hs != ts && !k2_tail) {
         CU(c, cudaEventRecord(L.head_done, hs));
         CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));
     }
@@ -289,13 +306,14 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
     k3.corners = k2.corners; k3.score = k2.score; k3.num_survivors = sc.num_survivors; k3.surv_anchor = k2.surv_anchor;
     k3.stale = L.stale + b0 * cap; k3.cur = L.cur + b0 * cap; k3.begin = L.begin + b0 * cap;
     k3.pend = L.pend + b0 * cap * kPendStride;
-    k3.pw = L.pw + (size_t)b0 * c->fastS * c->pstride; k3.pj = L.pj + (size_t)b0 * c->fastS * c->pstride;
+    k3.pw = L.pw + (size_t)b0 * c->fastS * c->pstride;
     k3.fastS = c->fastS; k3.pstride = c->pstride;
     k3.nms_idx = L.nms_idx + b0 * D; k3.nms_score = L.nms_score + b0 * D; k3.centre_anchor = L.centre_anchor + b0 * D;
     k3.num_dets = L.num_dets + b0; k3.member = L.member + b0 * D * c->words;
     k3.B = nb; k3.capacity = c->capacity; k3.Dmax = c->Dmax; k3.words = c->words;
     k3.iou_threshold = g.iou_threshold; k3.soft_nms_sigma = g.soft_nms_sigma;
     k3.dbg = c->k3_dbg ? c->k3_dbg + (size_t)b0 * 8 : nullptr;
+    k3.seg_cap = c->k3_seg_cap; k3.psm_max = c->k3_psm_max;
     CU(c, launch_k3(k3, ts));
     if (record) CU(c, cudaEventRecord(c->ev[4], ts));
 
@@ -309,7 +327,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
     CU(c, launch_k4(k4, ts));
     if (record) CU(c, cudaEventRecord(c->ev[5], ts));
     if (hs != ts) { CU(c, cudaEventRecord(L.tail_done, ts)); L.tail_pending = true; }
-    c->launches += launches + 3;   // + soft-NMS, membership, K4
+    c->launches += launches + 2;   // + soft-NMS (with the membership bits), K4
     return BOD_OK;
 }
 

@@ -74,8 +74,7 @@ struct K3Args {
     float* cur;       // up-to-date score
     int32_t* begin;   // suppress_begin_index
     uint32_t* pend;   // [B,cap,kPendStride] pending-selection bitmask (generic kernel)
-    float* pw;        // [B,fastS,pstride] pending soft-NMS weights per candidate (fast kernel)
-    uint8_t* pj;      // [B,fastS,pstride] their selection indices
+    float* pw;        // [B,fastS,pstride] spill rows of the pending soft-NMS weights (fast kernel)
     int fastS, pstride;
     // outputs
     int32_t* nms_idx;           // [B,Dmax]
@@ -86,6 +85,8 @@ struct K3Args {
     int B, capacity, Dmax, words;
     float iou_threshold, soft_nms_sigma;
     long long* dbg;             // diagnostics: [B][8] cycle counters per phase, or nullptr
+    int seg_cap;                // pair-list entries per warp and round (-1: the kernel's own; tests shrink it to reach the in-place path)
+    int psm_max;                // cap on the pending weights kept in shared memory per candidate (-1: none; tests)
 };
 cudaError_t launch_k3(const K3Args& a, cudaStream_t st);
 int k3_fast_capacity(int capacity);   // candidates the shared-memory soft-NMS kernel holds for this capacity

@@ -18,6 +18,7 @@
 // full/empty mbarriers), running up to NSTAGE slabs ahead of the eight consumer
 // warps, so ~200 KB per SM are always in flight, no thread issues a global load
 // and rows of any K (8, 11, 4, ...) are consumed conflict-free from shared memory.
+#include <cstdlib>
 #include "bod_common.cuh"
 #include "bod_kernels.h"
 
@@ -481,11 +482,19 @@ static bool k1_aligned(const K1Args& a) {
     return ((reinterpret_cast<uintptr_t>(a.cls) & 15u) == 0) && (((size_t)a.A * a.K) % 4 == 0) &&
            ((kTileAnchors * a.K) % 4 == 0);
 }
+static int k1_ctas_per_sm() {
+    static int v = 0;
+    if (v == 0) {
+        v = kPipeCtasPerSM;
+        if (const char* e = getenv("BOD_K1_CTAS")) { const int x = atoi(e); if (x >= 1 && x <= kPipeCtasPerSM) v = x; }
+    }
+    return v;
+}
 static int k1_pipe_ctas(const K1Args& a) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int ctas = kPipeCtasPerSM * sms;
+    int ctas = k1_ctas_per_sm() * sms;
     if (ctas > a.B * a.tiles) ctas = a.B * a.tiles;
     return ctas;
 }
@@ -507,7 +516,7 @@ static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     cudaError_t e;
     if (aligned) {
         // persistent pipeline: kPipeCtasPerSM CTAs per SM, each with a ring of NS one-sample slabs
-        int NS = (int)(((216u * 1024u) / kPipeCtasPerSM - 1024u) / slab);
+        int NS = (int)(((216u * 1024u) / k1_ctas_per_sm() - 1024u) / slab);
         if (NS > kMaxStages) NS = kMaxStages;
         if (NS < 2) NS = 2;
         const size_t ring = (size_t)NS * slab;

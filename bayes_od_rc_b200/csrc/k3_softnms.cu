@@ -37,8 +37,8 @@
 
 namespace bod {
 
-constexpr int kK3Threads = 512;
-constexpr int kFastS = 7680;          // candidates the shared-memory kernel holds
+constexpr int kK3Threads = 1024;
+constexpr int kFastS = 7424;          // candidates the shared-memory kernel holds
 
 BOD_DEVINL unsigned long long make_key(float score, int idx) {
     return ((unsigned long long)float_key(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
@@ -162,57 +162,87 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
 }
 
 // ---------------------------------------------------------------------------
-// fast kernel: everything a round touches for every candidate lives in shared
-// memory; the pending-weight lists live in global memory (L2 resident).
+// fast kernel: everything a round touches lives in shared memory.
 //
-// (1) Commits are LAZY.  The eager formulation above must, every round, look at
-// each candidate with pending weights to see whether TF would have popped it
-// before x (stale key > kx) and, if so, fold its pending weights into the stale
-// score.  Because the selection keys kx_0 > kx_1 > ... are decreasing, that
-// history can be replayed exactly the next time the candidate is touched: with
-// pending selections j_0 < j_1 < ..., the first pop happens at the smallest round
-// rr in (j_0, now] with key(stale) > kx_rr and folds every pending j < rr
-// (newest first), and so on.
-// (2) Selections are BATCHED.  With every score up to date, walk the candidates in
+// (1) Selections are BATCHED.  With every score up to date, walk the candidates in
 // key order y_1 > y_2 > ...  y_1 is the next centre.  A later y_q whose weight
 // against every centre accepted so far is exactly 1 keeps its score while every
 // other score can only drop, so it is the next centre too, provided no skipped
 // candidate (one that does overlap an accepted centre) can still outrank it; a
-// skipped candidate's new score is at most score * weight * (1 + 1e-5).  A round
+// skipped candidate's new score is at most score * weight * (1 + 5e-5).  A round
 // therefore selects up to kBatch centres at once, bit-identically to one by one.
-// A round is: (C) block-wide top-kTop of the current scores + acceptance,
-// (A) one lean geometric overlap test of every candidate against the batch,
-// compacted into per-warp list segments, (B) IoU / exp / replay for the
-// overlapping candidates only.  No atomics on the critical path.
+// (2) Update epochs are resolved when a candidate is touched.  Each candidate
+// keeps the weights it has collected since TF last popped it ("pending", oldest
+// first), its score as of that pop (stale) and its up-to-date score
+// u = stale * w_newest * ... * w_oldest.  TF pops a candidate with pending
+// weights right before selection j iff key(stale) > key(selection j) -- the
+// selection keys decrease -- and then folds every pending weight into the stale
+// score, newest first.  A candidate overlapping the round's batch walks the
+// <= kBatch selections of the batch in order; pops that happened in rounds that
+// did not touch it fold the same (whole) pending list and are caught by the
+// first comparison of its next walk.
+// (3) The block-wide top-kTop of the NEXT round is folded into the same passes:
+// every thread tracks the best two keys it has seen (untouched candidates in
+// pass A, updated ones in pass B); warps merge by popping heads (REDUX), warp 0
+// merges the warps' lists.  A list is cut where a thread runs out of tracked
+// keys (its third best is unknown), and the acceptance walk stops at the largest
+// such cut -- fewer centres in that round, never a wrong one.
+// (4) The expensive arithmetic runs one (candidate, centre) PAIR per thread.
+// A round is: acceptance (warp 0) | pass A: one lean geometric overlap test of
+// every candidate against the batch, overlapping pairs compacted into per-warp
+// list segments | pass B1: IoU + exp for every listed pair, and the pair's
+// cluster-membership bit (bbox_iou_vuvu > threshold, inference_utils.py:316) |
+// pass B2: the epoch walk of every listed candidate over its precomputed
+// weights.  Four block barriers per round, no global memory on the critical
+// path: the first psm pending weights of every candidate live in shared memory
+// (psm is chosen per image from its survivor count), the rest spill to global.
 // ---------------------------------------------------------------------------
 constexpr int kK3Warps = kK3Threads / 32;
-constexpr int kSegCap = 256;          // overlap-list entries per warp and round
-constexpr int kTop = 8;               // candidates examined per round
-constexpr int kBatch = 8;             // centres selected per round at most
+constexpr int kSegCap = 4096 / kK3Warps; // (candidate, centre) pairs listed per warp and round
+constexpr int kTop1 = 128 / kK3Warps;  // keys every warp lists per round
+constexpr int kTop = 16;              // candidates examined per round
+constexpr int kBatch = 16;            // centres selected per round at most
+constexpr int kExpTab = 129;
 
 struct K3Smem {
     unsigned long long warp_best[2][32];         // generic kernel scratch
-    unsigned long long top_w[kK3Warps][kTop];    // per-warp top keys of a round
+    unsigned long long top_w[kK3Warps][kTop1];   // per-warp top keys (descending, 0 = none)
+    unsigned long long bound_w[kK3Warps];        // every key of the warp that is not in top_w is below this (0: there is none)
     unsigned long long sel_key[kMaxOut];         // key (score, -index) of every selected centre
     float4 sel_box[kMaxOut];
-    int seg_n[kK3Warps];                         // entries in each warp's list segment
+    unsigned long long cand_key[kTop];           // the round's examined candidates ...
+    float4 cand_box[kTop];
+    float wpair[kTop][kTop];                     // ... their pairwise soft-NMS weights [q][i], i < q
+    uint32_t rowmask[kTop];                      // bit i of row q: wpair[q][i] != 1
+    double exp_tab[kExpTab];                     // exp(-k/64)
     int batch_n;                                 // centres selected in this round
     int malformed;
 };
 
-struct K3Const {                                  // kernel-lifetime constants of the slow path (lives in shared memory)
+struct K3State {                                  // kernel-lifetime constants (registers)
     const float4* corn; float* ucur; float* stl; uint8_t* npend;
-    float* pw; uint8_t* pj; int pstride;          // pending (weight, selection) lists, [S][pstride]
-    const unsigned long long* sel_key; const float4* sel_box;
-    float scale, thr; int is_soft;
+    float* pws; int S32, psm;                     // pending weights in shared memory: entry i of candidate s at pws[s*psm+i], i < psm (psm % 4 == 0)
+    float* pwg; int pstride;                      // spill rows in global memory: entry i >= psm at pwg[s*pstride+i]
+    uint32_t* member; int words;                  // membership rows of this image
+    float scale, thr; bool is_soft;
 };
+
+// list entry: candidate | centre-of-batch << 16 | first pair of its candidate << 20 | candidate queued << 21 | pairs of the candidate << 22
+BOD_DEVINL uint32_t ent_make(int s, int q, bool head, bool queued, int c) {
+    return (uint32_t)s | ((uint32_t)q << 16) | ((uint32_t)head << 20) | ((uint32_t)queued << 21) | ((uint32_t)c << 22);
+}
+BOD_DEVINL int ent_s(uint32_t e) { return (int)(e & 0xFFFFu); }
+BOD_DEVINL int ent_q(uint32_t e) { return (int)((e >> 16) & 15u); }
+BOD_DEVINL bool ent_head(uint32_t e) { return (e >> 20) & 1u; }
+BOD_DEVINL bool ent_queued(uint32_t e) { return (e >> 21) & 1u; }
+BOD_DEVINL int ent_pairs(uint32_t e) { return (int)((e >> 22) & 31u); }
 
 // exp(y) rounded to binary32 for the soft-NMS argument range: y = -k/64 + r, table of exp(-k/64) in
 // binary64 and a degree-6 Taylor polynomial in r (|r| <= 1/128, error < 2e-17): the binary64 value is
 // within ~1e-16 of exp(y), so its binary32 rounding equals the correctly rounded one except with
 // probability ~1e-8 per evaluation (same caveat as exp_cr).
-__constant__ double c_exp_tab[129];
-BOD_DEVINL float exp_neg_cr(float y) {
+__constant__ double c_exp_tab[kExpTab];
+BOD_DEVINL float exp_neg_cr(float y, const double* tab) {
     if (!(y <= 0.0f && y >= -2.0f)) return exp_cr(y);
     const double yd = (double)y;
     const int k = __double2int_rn(yd * -64.0);
@@ -224,221 +254,256 @@ BOD_DEVINL float exp_neg_cr(float y) {
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    return (float)(c_exp_tab[k] * p);
+    return (float)(tab[k] * p);
 }
-BOD_DEVINL float nms_weight_fast(float sim, float scale, bool is_soft, float thr) {
+BOD_DEVINL float nms_weight_fast(float sim, float scale, bool is_soft, float thr, const double* tab) {
     if (sim == 0.0f) return 1.0f;                                   // exp(+-0) = 1 exactly (0 <= thr: never hard-suppressed)
-    const float w = exp_neg_cr(scale * sim * sim);
+    const float w = exp_neg_cr(scale * sim * sim, tab);
     return (is_soft || sim <= thr) ? w : 0.0f;
 }
 
-// first round rr in [lo, hi] with sel_key[rr] < ks (keys strictly decrease; sel_key[hi] < ks is known)
-BOD_DEVINL int first_pop_round(const unsigned long long* sel_key, unsigned long long ks, int lo, int hi) {
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (ks > sel_key[mid]) hi = mid; else lo = mid + 1;
-    }
-    return lo;
+// bbox_iou_vuvu(survivor, centre) > threshold (strict), skipping the division when the boxes cannot
+// overlap even with the +1 pixel convention ((hi - lo) + 1 > 0 <=> hi - lo > -1 in binary32)
+BOD_DEVINL bool is_member(const float4 bs, const float4 bx, float thr) {
+    const float dx = fminf(bs.w, bx.w) - fmaxf(bs.y, bx.y);
+    const float dy = fminf(bs.z, bx.z) - fmaxf(bs.x, bx.x);
+    const bool wellformed = (bx.x <= bx.z) && (bx.y <= bx.w) && (bs.x <= bs.z) && (bs.y <= bs.w);
+    if (!wellformed || (dx > -1.0f && dy > -1.0f)) return repo_iou(bs, bx) > thr;
+    return false;
 }
 
-// The slow part of a round for one QUEUED candidate s whose box intersects the batch centres whose bits
-// are set in `mask` (centre k of the batch is selection r0 + k).
-__device__ __noinline__ void k3_process(const K3Const* C, const int r0, const uint32_t mask, const int s) {
-    const float4 bs = C->corn[s];
-    float u = C->ucur[s];
-    const float scale = C->scale, thr = C->thr;
-    const bool is_soft = C->is_soft != 0;
-    int n = C->npend[s];
-    float* wrow = C->pw + (size_t)s * C->pstride;
-    uint8_t* jrow = C->pj + (size_t)s * C->pstride;
-    // issue the loads of the newest pending weights first: their latency overlaps the IoU / exp arithmetic
-    const float4* wrow4 = reinterpret_cast<const float4*>(wrow);
-    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-    const int blk = (n - 1) >> 2;
-    float4 cur = (n > 0) ? wrow4[blk] : one4;
-    float4 nxt = (blk > 0) ? wrow4[blk - 1] : one4;
-    float st = C->stl[s];
-    bool changed = false, folded = false, first = true;
+// best two keys a thread has seen in a round
+struct Top2 {
+    unsigned long long a = 0ull, b = 0ull;
+    BOD_DEVINL void add(unsigned long long k) {
+        if (k > a) { b = a; a = k; } else if (k > b) { b = k; }
+    }
+};
 
+BOD_DEVINL void pend_put(const K3State& C, int s, int i, float w) {
+    if (i < C.psm) C.pws[s * C.psm + i] = w; else C.pwg[(size_t)s * C.pstride + i] = w;
+}
+// st * (pending weights, newest first).  The shared-memory part of the list is a row of the candidate
+// (psm is a multiple of 4): blocks of four weights per LDS.128, the next block in flight while the
+// current one is multiplied in.
+BOD_DEVINL float pend_product(const K3State& C, int s, int n, float st) {
+    float v = st;
+    int i = n - 1;
+    for (; i >= C.psm; --i) v = v * C.pwg[(size_t)s * C.pstride + i];        // spilled entries (rare)
+    if (i < 0) return v;
+    const float4* row = reinterpret_cast<const float4*>(C.pws + s * C.psm);
+    int blk = i >> 2;
+    float4 cur = row[blk];
+    const int top = i & 3;
+    {
+        const float4 nxt = row[blk > 0 ? blk - 1 : 0];
+        if (top >= 3) v = v * cur.w;
+        if (top >= 2) v = v * cur.z;
+        if (top >= 1) v = v * cur.y;
+        v = v * cur.x;
+        cur = nxt;
+    }
+    for (--blk; blk >= 0; --blk) {
+        const float4 nxt = row[blk > 0 ? blk - 1 : 0];
+        v = v * cur.w; v = v * cur.z; v = v * cur.y; v = v * cur.x;
+        cur = nxt;
+    }
+    return v;
+}
+
+// Epoch walk of one QUEUED candidate s over the round's batch (selections r0 .. r0+m-1).  weight_of(q)
+// returns the candidate's soft-NMS weight against centre q of the batch (1 for centres it does not
+// overlap).  Returns the candidate's new up-to-date score (-inf: removed by hard-NMS).
+template <typename WeightOf>
+BOD_DEVINL float k3_walk(const K3State& C, const K3Smem& sm, const int r0, const int m, const int s, WeightOf weight_of) {
+    float st = C.stl[s];
+    int n = C.npend[s];
+    const int n_in = n;
+    bool folded = false;
+    unsigned long long ks = make_key(st, s);
+    for (int q = 0; q < m; ++q) {
+        if (n > 0 && ks > sm.sel_key[r0 + q]) {            // TF pops s right before selection r0+q: fold, newest first
+            st = pend_product(C, s, n, st);
+            n = 0; folded = true;
+            ks = make_key(st, s);
+        }
+        const float w = weight_of(q);
+        if (w != 1.0f) {
+            if (!C.is_soft && w == 0.0f) { C.ucur[s] = -INFINITY; return -INFINITY; }   // hard-NMS: removed for good
+            pend_put(C, s, n, w);
+            ++n;
+        }
+    }
+    if (!folded && n == n_in) return C.ucur[s];            // every weight was exactly 1: untouched
+    const float u = pend_product(C, s, n, st);
+    C.ucur[s] = u;
+    C.npend[s] = (uint8_t)n;
+    if (folded) C.stl[s] = st;
+    return u;
+}
+
+// A whole candidate in place (only when a warp's list segment is full): membership bits and, if the
+// candidate is queued, its walk with the weights computed on the fly.
+__device__ __noinline__ float k3_process_inplace(const K3State* Cp, const K3Smem& sm, const int r0, const int m, const uint32_t mask,
+                                                 const int s, const bool queued) {
+    const K3State C = *Cp;                                  // a shared-memory copy: nothing of the caller's is forced to the stack
+    const float4 bs = C.corn[s];
     for (uint32_t rem = mask; rem; rem &= rem - 1) {
-        const int r = r0 + __ffs(rem) - 1;
-        const float sim = tf_iou(bs, C->sel_box[r]);
-        const float w = nms_weight_fast(sim, scale, is_soft, thr);
-        if (w == 1.0f) continue;                                                   // untouched by this centre
-        changed = true;
-        if (!is_soft && w == 0.0f) { u = -INFINITY; break; }                       // hard-NMS: removed for good
-        const unsigned long long kxr = C->sel_key[r];
-        if (n > 0 && make_key(st, s) > kxr) {
-            // rare: TF popped this candidate at least once since its list was last touched: replay
-            int i0 = 0;
-            while (i0 < n) {
-                const unsigned long long ks = make_key(st, s);
-                if (!(ks > kxr)) break;                                            // keys decrease: no further pop
-                const int rr = first_pop_round(C->sel_key, ks, (int)jrow[i0] + 1, r);
-                int i1 = i0;
-                while (i1 < n && (int)jrow[i1] < rr) ++i1;
-                float v = st;
-                for (int i = i1 - 1; i >= i0; --i) v = v * wrow[i];                // newest first
-                st = v; i0 = i1;
-            }
-            if (i0 > 0) {                                                          // drop the folded entries
-                for (int i = 0; i < n - i0; ++i) { wrow[i] = wrow[i0 + i]; jrow[i] = jrow[i0 + i]; }
-                n -= i0; folded = true;
-            }
-            first = false;
-        }
-        // u = stale * w(x_r) * (pending weights, newest first)
-        float v = st * w;
-        if (first) {                                                               // weights prefetched in blocks of 4
-            int b4 = blk;
-            while (b4 >= 0) {
-                const float4 nn = (b4 >= 2) ? wrow4[b4 - 2] : one4;
-                const int top = n - 1 - 4 * b4;                                    // highest valid lane of this block (0..3)
-                if (top >= 3) v = v * cur.w;
-                if (top >= 2) v = v * cur.z;
-                if (top >= 1) v = v * cur.y;
-                v = v * cur.x;
-                cur = nxt; nxt = nn; --b4;
-            }
-            first = false;
-        } else {
-            for (int i = n - 1; i >= 0; --i) v = v * wrow[i];
-        }
-        u = v;
-        wrow[n] = w; jrow[n] = (uint8_t)r;
-        ++n;
+        const int q = __ffs(rem) - 1;
+        if (is_member(bs, sm.sel_box[r0 + q], C.thr))
+            atomicOr(&C.member[(size_t)(r0 + q) * C.words + (s >> 5)], 1u << (s & 31));
     }
-    if (changed) {
-        C->ucur[s] = u;
-        C->npend[s] = (uint8_t)n;
-        if (folded) C->stl[s] = st;
-    }
+    if (!queued) return -INFINITY;
+    return k3_walk(C, sm, r0, m, s, [&](int q) {
+        if (!((mask >> q) & 1u)) return 1.0f;
+        return nms_weight_fast(tf_iou(bs, sm.sel_box[r0 + q]), C.scale, C.is_soft, C.thr, sm.exp_tab);
+    });
 }
 
-// insert key into the descending list t[0..kTop)
-BOD_DEVINL void top_insert(unsigned long long (&t)[kTop], unsigned long long key) {
-    if (key > t[kTop - 1]) {
-        t[kTop - 1] = key;
+// Warp-level merge of the lanes' Top2 pairs: every lane returns with the warp's best keys in out[]
+// (descending, 0 = none), cut after the first key whose lane has nothing tracked behind it; `bound`
+// is that key (0 when the list was not cut and the warp has no further keys).
+BOD_DEVINL void warp_top_merge2(Top2 t, unsigned long long (&out)[kTop1], unsigned long long& bound) {
+    unsigned long long cur = t.a, nxt = t.b;
+    bool spent = false;                                     // this lane's second key has been promoted already
+    bool cut = false;
+    bound = 0ull;
 #pragma unroll
-        for (int q = kTop - 1; q > 0; --q)
-            if (t[q] > t[q - 1]) { const unsigned long long x = t[q]; t[q] = t[q - 1]; t[q - 1] = x; }
+    for (int q = 0; q < kTop1; ++q) {
+        const unsigned long long mx = cut ? 0ull : warp_max_u64(cur);
+        out[q] = mx;
+        const bool mine = (mx != 0ull) && (cur == mx);      // keys are unique: exactly one lane pops
+        const bool exhausted = mine && spent;               // its third best is unknown
+        if (mine) { cur = nxt; nxt = 0ull; spent = true; }
+        if (!cut && __any_sync(0xffffffffu, exhausted)) { cut = true; bound = mx; }
     }
-}
-// pop the heads of the lanes' sorted lists kTop times: every lane ends with the warp's top-kTop, descending
-BOD_DEVINL void warp_top_merge(unsigned long long (&t)[kTop]) {
-    unsigned long long out[kTop];
-#pragma unroll
-    for (int q = 0; q < kTop; ++q) {
-        const unsigned long long m = warp_max_u64(t[0]);
-        out[q] = m;
-        if (m != 0ull && t[0] == m) {                  // keys are unique: exactly one lane pops
-#pragma unroll
-            for (int i = 0; i < kTop - 1; ++i) t[i] = t[i + 1];
-            t[kTop - 1] = 0ull;
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < kTop; ++q) t[q] = out[q];
+    if (!cut) bound = out[kTop1 - 1];                       // untracked keys are below the last one listed
 }
 
 __global__ void __launch_bounds__(kK3Threads, 1)
-k3_softnms_kernel(K3Args a, int smem_S) {
+k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ K3Smem sm;
-    __shared__ K3Const kc;
+    __shared__ K3State kc;
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = a.num_survivors[b];
     if (S > smem_S) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
 
-    float4* corn = reinterpret_cast<float4*>(dyn);                       // [smem_S] corners
-    float* ucur = reinterpret_cast<float*>(corn + smem_S);               // [smem_S] up-to-date score, -inf = not queued
-    float* stl = ucur + smem_S;                                          // [smem_S] score as of the last fold
-    uint32_t* list = reinterpret_cast<uint32_t*>(stl + smem_S);          // [kK3Warps][kSegCap] candidate | batch mask << 16
-    uint8_t* npend = reinterpret_cast<uint8_t*>(list + kK3Warps * kSegCap);   // [smem_S] pending entries per candidate
+    const int S32 = (S + 31) & ~31;
+    uint32_t* list = reinterpret_cast<uint32_t*>(dyn);                    // [kK3Warps][kSegCap] pair entries (ent_make)
+    float* wl = reinterpret_cast<float*>(list + kK3Warps * kSegCap);      // [kK3Warps][kSegCap] their soft-NMS weights
+    float4* corn = reinterpret_cast<float4*>(wl + kK3Warps * kSegCap);    // [S32] corners
+    float* ucur = reinterpret_cast<float*>(corn + S32);                   // [S32] up-to-date score, -inf = not queued
+    float* stl = ucur + S32;                                              // [S32] score as of the last fold
+    // pending weights per candidate held in shared memory: whatever fits behind the fixed arrays
+    int psm = S32 > 0 ? (pool_bytes - S32 * 25) / (S32 * 4) : 0;
+    psm = psm < 0 ? 0 : (psm > a.pstride ? a.pstride : psm);
+    if (a.psm_max >= 0 && psm > a.psm_max) psm = a.psm_max;              // diagnostics: force the global spill rows
+    psm &= ~3;                                                            // rows are read four weights at a time
+    float* pws = stl + S32;                                               // [S32][psm]
+    uint8_t* npend = reinterpret_cast<uint8_t*>(pws + (size_t)psm * S32); // [S32] pending entries per candidate
 
     const int Dmax = a.Dmax;
     const float4* corners = a.corners + (size_t)b * a.capacity;
     const float* score = a.score + (size_t)b * a.capacity;
-    const bool is_soft = a.soft_nms_sigma > 0.0f;
-    const float scale = is_soft ? -0.5f / a.soft_nms_sigma : 0.0f;
-    const float thr = a.iou_threshold;
-    const int S32 = (S + 31) & ~31;
+    K3State C;
+    C.corn = corn; C.ucur = ucur; C.stl = stl; C.npend = npend;
+    C.pws = pws; C.S32 = S32; C.psm = psm;
+    C.pwg = a.pw + (size_t)b * a.fastS * a.pstride; C.pstride = a.pstride;
+    C.member = a.member + (size_t)b * Dmax * a.words; C.words = a.words;
+    C.is_soft = a.soft_nms_sigma > 0.0f;
+    C.scale = C.is_soft ? -0.5f / a.soft_nms_sigma : 0.0f;
+    C.thr = a.iou_threshold;
 
-    if (tid == 0) {
-        kc.corn = corn; kc.ucur = ucur; kc.stl = stl; kc.npend = npend;
-        kc.pstride = a.pstride;
-        kc.pw = a.pw + (size_t)b * a.fastS * a.pstride; kc.pj = a.pj + (size_t)b * a.fastS * a.pstride;
-        kc.sel_key = sm.sel_key; kc.sel_box = sm.sel_box;
-        kc.scale = scale; kc.thr = thr; kc.is_soft = is_soft ? 1 : 0;
-        sm.malformed = 0;
+    if (tid == 0) { sm.malformed = 0; kc = C; }
+    for (int k = tid; k < kExpTab; k += kK3Threads) sm.exp_tab[k] = c_exp_tab[k];
+    // membership rows start out empty (only the words K4 / bod_fetch_members read)
+    {
+        const int nw = S32 >> 5;
+        for (int d = warp; d < Dmax; d += kK3Warps)
+            for (int w = lane; w < nw; w += 32) C.member[(size_t)d * a.words + w] = 0u;
     }
     __syncthreads();
 
-    // ---- load; membership rows start out empty ----
+    // ---- load; the first round's top keys come from the initial scores ----
+    Top2 t2k;
     for (int s = tid; s < S; s += kK3Threads) {
         const float4 c = corners[s];
         corn[s] = c;
         if (!((c.x <= c.z) && (c.y <= c.w))) sm.malformed = 1;          // needs the canonicalising IoU path every round
         const float sc = score[s];
-        ucur[s] = (sc > -INFINITY) ? sc : -INFINITY;                     // scores_data[i] > score_threshold (-inf); NaN stays out
+        const bool queued = sc > -INFINITY;                              // scores_data[i] > score_threshold (-inf); NaN stays out
+        ucur[s] = queued ? sc : -INFINITY;
         stl[s] = sc;
         npend[s] = 0;
+        if (queued) t2k.add(make_key(sc, s));
     }
-    __syncthreads();
-    const bool all_maybe = sm.malformed != 0;
 
-    long long tA = 0, tB = 0, tC = 0, tL = 0, t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    long long tA = 0, tB = 0, tC = 0, tL = 0, t0 = 0, t1 = 0, t2c = 0, t3 = 0;
     int r = 0, rounds = 0;
     while (r < Dmax) {
         if (a.dbg && tid == 0) t0 = clock64();
-        // ---- pass C: block-wide top-kTop of the up-to-date scores ----
-        unsigned long long top[kTop];
+        // ---- warp lists of this round's best keys ----
+        {
+            unsigned long long out[kTop1], bound;
+            warp_top_merge2(t2k, out, bound);
+            if (lane < kTop1) {
+                unsigned long long v = out[0];
 #pragma unroll
-        for (int q = 0; q < kTop; ++q) top[q] = 0ull;
-#pragma unroll 4
-        for (int s = tid; s < S; s += kK3Threads) {
-            const float u = ucur[s];
-            if (u > -INFINITY) top_insert(top, make_key(u, s));
-        }
-        warp_top_merge(top);
-        if (lane < kTop) {
-            unsigned long long v = top[0];
-#pragma unroll
-            for (int q = 1; q < kTop; ++q) v = (lane == q) ? top[q] : v;
-            sm.top_w[warp][lane] = v;
+                for (int q = 1; q < kTop1; ++q) v = (lane == q) ? out[q] : v;
+                sm.top_w[warp][lane] = v;
+            }
+            if (lane == 0) sm.bound_w[warp] = bound;
         }
         __syncthreads();
         if (warp == 0) {
-            // merge the kK3Warps x kTop warp results, then accept centres in key order (see header)
-            const unsigned long long* src = &sm.top_w[0][0];
+            // merge the kK3Warps sorted lists (lane l: four consecutive entries of one warp's list; a lane's head
+            // can only surface after the larger entries of the same list were popped), then accept centres in
+            // key order (see header)
+            static_assert(kK3Warps * kTop1 == 128 && kTop1 % 4 == 0, "four list entries of one warp per lane of warp 0");
+            unsigned long long h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = (&sm.top_w[0][0])[4 * lane + i];
+            unsigned long long G = (lane < kK3Warps) ? sm.bound_w[lane] : 0ull;
+            G = warp_max_u64(G);
             unsigned long long t2[kTop];
 #pragma unroll
-            for (int q = 0; q < kTop; ++q) t2[q] = 0ull;
-#pragma unroll
-            for (int i = 0; i < kK3Warps * kTop / 32; ++i) top_insert(t2, src[lane + 32 * i]);
-            warp_top_merge(t2);
-            // lane p < kTop holds candidate p
+            for (int q = 0; q < kTop; ++q) {
+                const unsigned long long mx = warp_max_u64(h[0]);
+                t2[q] = (mx >= G) ? mx : 0ull;                            // below G an untracked key might outrank it
+                if (mx != 0ull && h[0] == mx) { h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = 0ull; }
+            }
+            // lane p < kTop publishes candidate p
             unsigned long long myk = t2[0];
 #pragma unroll
             for (int q = 1; q < kTop; ++q) myk = (lane == q) ? t2[q] : myk;
             if (lane >= kTop) myk = 0ull;
-            // pairwise weights among the examined candidates: pair (q, i), i < q, on lane q*(q-1)/2 + i
-            float wp = 1.0f;
-            {
-                int q = 1, base = 0;
-                while (base + q <= lane) { base += q; ++q; }             // lane -> (q, i)
-                const int i = lane - base;
-                if (q < kTop) {
-                    unsigned long long kq = t2[0], ki = t2[0];
-#pragma unroll
-                    for (int z = 1; z < kTop; ++z) { kq = (q == z) ? t2[z] : kq; ki = (i == z) ? t2[z] : ki; }
-                    if (kq != 0ull && ki != 0ull)
-                        wp = nms_weight_fast(tf_iou(corn[key_index(kq)], corn[key_index(ki)]), scale, is_soft, thr);
-                }
+            if (lane < kTop) {
+                sm.cand_key[lane] = myk;
+                if (myk != 0ull) sm.cand_box[lane] = corn[key_index(myk)];
             }
-            static_assert(kTop * (kTop - 1) / 2 <= 32, "one lane per candidate pair");
-            const uint32_t nonunit = __ballot_sync(0xffffffffu, wp != 1.0f);
+            __syncwarp();
+            // pairwise weights among the examined candidates: lane 2q+h does candidate q against candidates
+            // [8h, 8h+8) below q
+            static_assert(kTop == 16, "two lanes per examined candidate");
+            {
+                const int q = lane >> 1, i0 = (lane & 1) * 8;
+                const unsigned long long kq = sm.cand_key[q];
+                uint32_t bits = 0u;
+                if (kq != 0ull) {
+                    const float4 bq = sm.cand_box[q];
+                    const int i1 = min(q, i0 + 8);
+                    for (int i = i0; i < i1; ++i) {
+                        const float w = nms_weight_fast(tf_iou(bq, sm.cand_box[i]), C.scale, C.is_soft, C.thr, sm.exp_tab);
+                        sm.wpair[q][i] = w;
+                        if (w != 1.0f) bits |= 1u << i;
+                    }
+                }
+                bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+                if ((lane & 1) == 0) sm.rowmask[q] = bits;
+            }
+            __syncwarp();
             int m = 0;
             uint32_t acc = 0u;                                           // accepted candidates (bit q)
             if (t2[0] != 0ull) {
@@ -448,14 +513,13 @@ k3_softnms_kernel(K3Args a, int smem_S) {
                 for (int q = 1; q < kTop; ++q) {
                     if (t2[q] == 0ull || r + m >= Dmax || m >= kBatch) break;
                     const float sq = key_score(t2[q]);
-                    const int base = q * (q - 1) / 2;
-                    const uint32_t hit = (nonunit >> base) & acc & ((1u << q) - 1u);   // accepted centres it overlaps
+                    const uint32_t hit = sm.rowmask[q] & acc;            // accepted centres it overlaps
                     if (hit == 0u) {
                         if (!(sq > ub_max)) break;                       // a skipped candidate might still outrank it
                         acc |= 1u << q; ++m;
                     } else {
-                        const float w = __shfl_sync(0xffffffffu, wp, base + __ffs(hit) - 1);
-                        ub_max = fmaxf(ub_max, sq * w * 1.00001f);
+                        const float w = sm.wpair[q][__ffs(hit) - 1];
+                        ub_max = fmaxf(ub_max, sq * w * 1.00005f);     // 2n+2 roundings apart, n <= 255
                     }
                 }
             }
@@ -463,7 +527,7 @@ k3_softnms_kernel(K3Args a, int smem_S) {
             if (lane < kTop && ((acc >> lane) & 1u)) {
                 const int pos = r + __popc(acc & ((1u << lane) - 1u));
                 const int x = key_index(myk);
-                sm.sel_box[pos] = corn[x];
+                sm.sel_box[pos] = sm.cand_box[lane];
                 sm.sel_key[pos] = myk;
                 ucur[x] = -INFINITY;                                     // leaves the queue
                 a.nms_idx[(size_t)b * Dmax + pos] = x;
@@ -476,100 +540,99 @@ k3_softnms_kernel(K3Args a, int smem_S) {
         const int m = sm.batch_n;
         if (m == 0) break;                                                     // queue empty
         if (a.dbg && tid == 0) t1 = clock64();
+        const bool all_maybe = sm.malformed != 0;
 
-        // ---- pass A: geometric overlap of every candidate with the batch centres ----
-        float4 bxs[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) bxs[q] = sm.sel_box[r + (q < m ? q : 0)];
+        // ---- pass A: geometric overlap of every survivor with the batch centres (queued or not: selected
+        // and removed survivors still belong to clusters) ----
+        t2k = Top2();
         int cnt = 0;                                                           // entries in this warp's segment
         uint32_t* seg = list + warp * kSegCap;
-#pragma unroll 2
+        const int seg_cap = (a.seg_cap >= 0 && a.seg_cap < kSegCap) ? a.seg_cap : kSegCap;   // tests shrink it
         for (int s = tid; s < S32; s += kK3Threads) {
             uint32_t mask = 0u;
-            if (s < S && ucur[s] > -INFINITY) {
+            bool queued = false;
+            if (s < S) {
+                const float u = ucur[s];
+                queued = u > -INFINITY;
                 const float4 bs = corn[s];
-                // TF's intersection area is max(dy,0)*max(dx,0): no positive intersection => IoU = 0 and the
-                // weight is exactly 1, the centre does nothing to this candidate
+                // no overlap even with the +1 pixel convention => not a member, and TF's intersection area
+                // max(dy,0)*max(dx,0) is 0 => IoU = 0, weight exactly 1: the centre does nothing to this survivor
+                for (int q = 0; q < m; ++q) {
+                    const float4 bx = sm.sel_box[r + q];
+                    const float dx = fminf(bs.w, bx.w) - fmaxf(bs.y, bx.y);
+                    const float dy = fminf(bs.z, bx.z) - fmaxf(bs.x, bx.x);
+                    if ((dx > -1.0f && dy > -1.0f) || all_maybe) mask |= 1u << q;
+                }
+                if (mask == 0u && queued) t2k.add(make_key(u, s));
+            }
+            const int c = __popc(mask);
+            int incl = c;
 #pragma unroll
-                for (int q = 0; q < kBatch; ++q) {
-                    if (q < m) {
-                        const float dx = fminf(bs.w, bxs[q].w) - fmaxf(bs.y, bxs[q].y);
-                        const float dy = fminf(bs.z, bxs[q].z) - fmaxf(bs.x, bxs[q].x);
-                        if ((dx > 0.0f && dy > 0.0f) || all_maybe) mask |= 1u << q;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total != 0) {
+                if (cnt + total <= seg_cap) {
+                    int pos = cnt + incl - c;
+                    bool head = true;
+                    for (uint32_t rem = mask; rem; rem &= rem - 1) {
+                        seg[pos++] = ent_make(s, __ffs(rem) - 1, head, queued, c);
+                        head = false;
                     }
+                    cnt += total;
+                } else if (mask) {                                             // segment full: handle in place
+                    const float u = k3_process_inplace(&kc, sm, r, m, mask, s, queued);
+                    if (u > -INFINITY) t2k.add(make_key(u, s));
                 }
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, mask != 0u);
-            if (mask) {
-                const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-                if (pos < kSegCap) seg[pos] = (uint32_t)s | (mask << 16);
-                else k3_process(&kc, r, mask, s);                              // segment overflow: handle in place
-            }
-            cnt += __popc(bal);
         }
-        if (lane == 0) sm.seg_n[warp] = min(cnt, kSegCap);
-        __syncthreads();
-        if (a.dbg && tid == 0) t2 = clock64();
+        __syncwarp();
+        if (a.dbg && tid == 0) t2c = clock64();
 
-        // ---- pass B: the compacted overlapping candidates (entry e -> segment, slot) ----
-        int total = 0;
-#pragma unroll
-        for (int w = 0; w < kK3Warps; ++w) total += sm.seg_n[w];
-        for (int base = 0; base < total; base += kK3Threads) {
-            int e = base + tid, sgw = -1, slot = 0;
-#pragma unroll
-            for (int w = 0; w < kK3Warps; ++w) {
-                const int c = sm.seg_n[w];
-                if (sgw < 0 && e >= 0 && e < c) { sgw = w; slot = e; }
-                e -= c;
-            }
-            if (sgw >= 0) { const uint32_t ent = list[sgw * kSegCap + slot]; k3_process(&kc, r, ent >> 16, (int)(ent & 0xFFFFu)); }
+        // Every survivor is scanned by the same thread in every round (s = tid + k * kK3Threads), so a warp's
+        // segment only ever lists survivors whose state this warp owns: passes B1 / B2 run per warp on the
+        // warp's own segment and need no block barrier.
+        // ---- pass B1: one listed pair per lane: soft-NMS weight + membership bit ----
+        float* wseg = wl + warp * kSegCap;
+        for (int e = lane; e < cnt; e += 32) {
+            const uint32_t ent = seg[e];
+            const int s = ent_s(ent), q = ent_q(ent);
+            const float4 bs = corn[s], bx = sm.sel_box[r + q];
+            wseg[e] = ent_queued(ent) ? nms_weight_fast(tf_iou(bs, bx), C.scale, C.is_soft, C.thr, sm.exp_tab) : 1.0f;
+            if (is_member(bs, bx, C.thr)) atomicOr(&C.member[(size_t)(r + q) * C.words + (s >> 5)], 1u << (s & 31));
         }
-        __syncthreads();
-        if (a.dbg && tid == 0) { t3 = clock64(); tC += t1 - t0; tA += t2 - t1; tB += t3 - t2; tL += total; }
+        __syncwarp();
+        // ---- pass B2: one listed candidate per lane (its first pair): the epoch walk ----
+        for (int e = lane; e < cnt; e += 32) {
+            const uint32_t ent = seg[e];
+            if (ent_head(ent) && ent_queued(ent)) {
+                const int s = ent_s(ent), c = ent_pairs(ent);
+                int j = 0, nextq = ent_q(ent);
+                const float u = k3_walk(C, sm, r, m, s, [&](int q) {
+                    if (q != nextq) return 1.0f;
+                    const float w = wseg[e + j];
+                    ++j;
+                    nextq = (j < c) ? ent_q(seg[e + j]) : -1;
+                    return w;
+                });
+                if (u > -INFINITY) t2k.add(make_key(u, s));
+            }
+        }
+        __syncwarp();
+        if (a.dbg && tid == 0) { t3 = clock64(); tC += t1 - t0; tA += t2c - t1; tB += t3 - t2c; tL += cnt; }
         r += m;
         ++rounds;
+        // no barrier here: the warp lists of the next round go to sm.top_w, which warp 0 finished reading
+        // before the batch barrier; seg_n / list / wl are next written after the top-of-round barrier
     }
     if (a.dbg && tid == 0) {
         a.dbg[b * 8 + 0] = tA; a.dbg[b * 8 + 1] = tB; a.dbg[b * 8 + 2] = tL; a.dbg[b * 8 + 3] = rounds; a.dbg[b * 8 + 4] = S;
-        a.dbg[b * 8 + 5] = tC; a.dbg[b * 8 + 6] = r;
+        a.dbg[b * 8 + 5] = tC; a.dbg[b * 8 + 6] = r; a.dbg[b * 8 + 7] = psm;
     }
     if (tid == 0) a.num_dets[b] = r;
     for (int d = r + tid; d < Dmax; d += kK3Threads) {       // padding rows
         a.nms_idx[(size_t)b * Dmax + d] = -1;
         a.centre_anchor[(size_t)b * Dmax + d] = -1;
         a.nms_score[(size_t)b * Dmax + d] = 0.0f;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// cluster membership (inference_utils.py:214-215 + :316): bit s of row d <=>
-// bbox_iou_vuvu(survivor s, centre d) > threshold, for the D centre columns only.
-// One CTA per (centre, image); fully parallel, off the sequential path.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k3_membership_kernel(K3Args a) {
-    const int d = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-    if (d >= a.num_dets[b]) return;
-    const int S = a.num_survivors[b];
-    const float4* corners = a.corners + (size_t)b * a.capacity;
-    uint32_t* row = a.member + ((size_t)b * a.Dmax + d) * a.words;
-    const float4 bx = corners[a.nms_idx[(size_t)b * a.Dmax + d]];
-    const bool bx_ok = (bx.x <= bx.z) && (bx.y <= bx.w);
-    const float thr = a.iou_threshold;
-    const int S32 = (S + 31) & ~31;
-    for (int s = tid; s < S32; s += 256) {
-        bool mem = false;
-        if (s < S) {
-            const float4 bs = corners[s];
-            // no overlap even with the +1 pixel convention ((hi - lo) + 1 > 0 <=> hi - lo > -1 in binary32)
-            // => intersection 0 => IoU <= 0 <= threshold
-            const float dx = fminf(bs.w, bx.w) - fmaxf(bs.y, bx.y);
-            const float dy = fminf(bs.z, bx.z) - fmaxf(bs.x, bx.x);
-            const bool wellformed = bx_ok && (bs.x <= bs.z) && (bs.y <= bs.w);
-            if (!wellformed || (dx > -1.0f && dy > -1.0f)) mem = repo_iou(bs, bx) > thr;   // strict >
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, mem);
-        if (lane == 0) row[s >> 5] = bal;
     }
 }
 
@@ -584,20 +647,23 @@ cudaError_t launch_k3(const K3Args& a, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !g_exp_tab_ready[dev]) {
-        double tab[129];
-        for (int k = 0; k <= 128; ++k) tab[k] = exp(-(double)k / 64.0);
+        double tab[kExpTab];
+        for (int k = 0; k < kExpTab; ++k) tab[k] = exp(-(double)k / 64.0);
         cudaError_t e0 = cudaMemcpyToSymbol(c_exp_tab, tab, sizeof tab);
         if (e0 != cudaSuccess) return e0;
         g_exp_tab_ready[dev] = true;
     }
     const int smem_S = a.fastS;
-    const size_t smem = (size_t)smem_S * (16 + 4 + 4 + 1) + (size_t)kK3Warps * kSegCap * 4;
+    // dynamic shared memory: pair lists + the per-candidate pool (corners, scores, pending weights);
+    // as much as one CTA can have next to the static part, so small images keep long pending lists on chip
+    const size_t lists = (size_t)kK3Warps * kSegCap * 8;
+    const size_t most = (227 * 1024 - sizeof(K3Smem) - 1024 - lists) & ~(size_t)15;
+    static_assert((size_t)kFastS * 25 <= 227 * 1024 - sizeof(K3Smem) - 1024 - (size_t)kK3Warps * kSegCap * 8 - 16,
+                  "kFastS candidates must fit the shared-memory pool");
+    const size_t smem = lists + most;
     cudaError_t e = cudaFuncSetAttribute(k3_softnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k3_softnms_kernel<<<a.B, kK3Threads, smem, st>>>(a, smem_S);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    k3_membership_kernel<<<dim3(a.Dmax, a.B), 256, 0, st>>>(a);
+    k3_softnms_kernel<<<a.B, kK3Threads, smem, st>>>(a, smem_S, (int)most);
     return cudaGetLastError();
 }
 

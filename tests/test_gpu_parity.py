@@ -83,6 +83,17 @@ def test_synthetic_batch_bit_exact(name):
         compare_image_with_oracle(eng, res, b, r, spec.K)
 
 
+@pytest.mark.parametrize("env", [dict(BOD_K3_SEGCAP="8"), dict(BOD_K3_SEGCAP="0"), dict(BOD_K3_PSM_MAX="0"),
+                                 dict(BOD_K3_PSM_MAX="2", BOD_K3_SEGCAP="40")])
+@pytest.mark.parametrize("name", ["bdd_covar_k8", "dense_cluster", "dense_cluster_sigma", "hard_nms"])
+def test_softnms_overflow_paths(name, env, monkeypatch):
+    """The soft-NMS kernel's rarely taken paths on small inputs: pair-list segments that overflow (candidates
+    handled in place) and pending weights that spill from shared memory to the global rows."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    test_synthetic_batch_bit_exact(name)
+
+
 def test_host_path_equals_device_path():
     spec = synthetic.SceneSpec(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=3)
     B = 9       # > 8 so that the host path splits the batch into chunks
