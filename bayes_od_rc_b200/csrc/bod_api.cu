@@ -47,6 +47,8 @@ struct bod_ctx {
     Lane lane[2];
     int nlanes = 1, cur = 0;          // cur: lane of the last issued run
     int32_t* status = nullptr;
+    unsigned long long* pf_key = nullptr;   // pre-NMS filter scratch [B,A] (only with score_threshold / pre_nms_top_k)
+    bool prefilter = false;
     uint32_t* ticket = nullptr;       // K1's dynamic tile scheduler: monotonically increasing ticket counter
     uint32_t ticket_next = 0;         // its value once every launch issued so far has finished
     float* probs = nullptr; float* sampled = nullptr;
@@ -128,7 +130,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     if (!(cfg->iou_threshold >= 0.0f)) return bad("iou_threshold must be >= 0");
     if (!(cfg->soft_nms_sigma >= 0.0f)) return bad("soft_nms_sigma must be >= 0");
     if (cfg->num_draws < 1 || cfg->num_draws > 4096) return bad("num_draws must be in [1,4096]");
-    if (cfg->pre_nms_top_k != 0 || cfg->score_threshold > -INFINITY) return bad("score_threshold / pre_nms_top_k extensions are not built yet");
+    if (cfg->pre_nms_top_k < 0) return bad("pre_nms_top_k must be >= 0");
     if (cfg->anchor_mode == BOD_ANCHORS_GENERATE && count_anchors(cfg->im_h, cfg->im_w) != cfg->A)
         return bad("anchor_mode=GENERATE: A does not match the FPN anchor count of (im_h, im_w)");
 
@@ -154,6 +156,8 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
 #define TAKE(ptr, bytes) pieces.push_back(Piece{reinterpret_cast<void**>(&ptr), take(bytes)})
     TAKE(c->status, 256);
     TAKE(c->ticket, 256);
+    c->prefilter = cfg->pre_nms_top_k > 0 || cfg->score_threshold > -INFINITY;
+    if (c->prefilter) TAKE(c->pf_key, (size_t)B * A * 8);
     if (cfg->emit_probs) { TAKE(c->probs, (size_t)B * A * K * 4); TAKE(c->sampled, (size_t)B * A * K * 4); }
     for (int l = 0; l < c->nlanes; ++l) {
         Lane& L = c->lane[l];
@@ -261,6 +265,17 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
     CU(c, launch_k1(k1, hs));
     if (record) CU(c, cudaEventRecord(c->ev[1], hs));
 
+    int launches = 3;
+    if (c->prefilter) {
+        PrefilterArgs pf{};
+        pf.slot_anchor = k1.slot_anchor; pf.slot_counts = k1.slot_counts; pf.tile_count = k1.tile_count;
+        pf.key = c->pf_key + b0 * A;
+        pf.B = nb; pf.A = g.A; pf.K = g.K; pf.tiles = c->tiles;
+        pf.dirichlet = g.dirichlet_prior == BOD_DIRICHLET_NON_INFORMATIVE;
+        pf.score_threshold = g.score_threshold; pf.top_k = g.pre_nms_top_k;
+        CU(c, launch_prefilter(pf, hs));
+        ++launches;
+    }
     ScanArgs sc{};
     sc.tile_count = k1.tile_count; sc.tile_off = L.tile_off + (size_t)b0 * (c->tiles + 1);
     sc.num_survivors = L.num_survivors + b0; sc.status = c->status;
@@ -293,7 +308,6 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
     k2.isotropic_variance = g.isotropic_variance; k2.scale_v = g.scale_v; k2.scale_u = g.scale_u;
     k2.anchor_mode = g.anchor_mode; k2.im_h = g.im_h; k2.im_w = g.im_w;
     CU(c, launch_k2(k2, k2s));
-    int launches = 3;
     if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, k2s)); ++launches; }
     if (record) CU(c, cudaEventRecord(c->ev[3], k2s));
     if (hs != ts && !k2_tail) {

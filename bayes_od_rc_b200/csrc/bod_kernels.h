@@ -37,6 +37,19 @@ struct ScanArgs {
 };
 cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st);
 
+// ---- K1c: pre-NMS filter on the slot lists (extension knobs score_threshold / pre_nms_top_k) --
+struct PrefilterArgs {
+    int32_t* slot_anchor;       // [B,A]   re-compacted in place, tile by tile
+    float* slot_counts;         // [B,A,K]
+    int32_t* tile_count;        // [B,tiles] updated
+    unsigned long long* key;    // [B,A] scratch
+    int B, A, K, tiles;
+    int dirichlet;              // counts + 1/K before normalising (non_informative prior)
+    float score_threshold;      // keep iff score > threshold (-inf: all)
+    int top_k;                  // 0 = off
+};
+cudaError_t launch_prefilter(const PrefilterArgs& a, cudaStream_t st);
+
 // ---- K2: per-survivor posterior -------------------------------------------
 struct K2Args {
     const float* box;           // [B,N,A,4]

@@ -68,6 +68,123 @@ cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
+// K1c: pre-NMS filter (EXTENSION, BASELINE.json config 5).  The
+// reference has no such knobs; the semantics are the oracle's orc_prefilter:
+//   (1) drop survivors whose count score max_k (c_k + alpha) / sum is <= score_threshold,
+//   (2) if more than top_k remain keep the top_k by (score desc, anchor index asc),
+//   (3) keep ascending anchor order.
+// The score depends on the counts only, so this runs between K1 and K2, on the
+// per-tile slot lists: one CTA per image computes a 64-bit key per slot, finds the
+// top_k-th largest key with an 8 x 8-bit radix select (keys are unique) and
+// re-compacts every tile in place; the tile scan then runs on the new counts.
+// ---------------------------------------------------------------------------
+constexpr int kPfThreads = 1024;
+
+BOD_DEVINL float count_score(const float* c, int K, bool dirichlet) {
+    const float alpha = 1.0f / (float)K;
+    float sum = 0.0f, best = 0.0f;
+    for (int k = 0; k < K; ++k) sum = sum + (dirichlet ? c[k] + alpha : c[k]);
+    for (int k = 0; k < K; ++k) {
+        const float p = (dirichlet ? c[k] + alpha : c[k]) / sum;
+        if (k == 0 || p > best) best = p;
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(kPfThreads) prefilter_kernel(PrefilterArgs a) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long sh_prefix;
+    __shared__ unsigned int sh_k, sh_total;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.K;
+    int32_t* tcount = a.tile_count + (size_t)b * a.tiles;
+    int32_t* sanchor = a.slot_anchor + (size_t)b * a.A;
+    float* scounts = a.slot_counts + (size_t)b * a.A * K;
+    unsigned long long* key = a.key + (size_t)b * a.A;
+
+    // ---- keys: (score, -anchor); 0 = dropped by the threshold ----
+    if (tid == 0) sh_total = 0u;
+    __syncthreads();
+    unsigned int mine = 0u;
+    for (int slot = tid; slot < a.tiles * kTileAnchors; slot += kPfThreads) {
+        const int t = slot / kTileAnchors, j = slot - t * kTileAnchors;
+        if (j >= tcount[t]) continue;
+        const float sc = count_score(scounts + (size_t)slot * K, K, a.dirichlet != 0);
+        unsigned long long k64 = 0ull;
+        if (sc > a.score_threshold) {
+            k64 = ((unsigned long long)float_key(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)sanchor[slot]);
+            ++mine;
+        }
+        key[slot] = k64;
+    }
+    if (mine) atomicAdd(&sh_total, mine);
+    __syncthreads();
+    const unsigned int n = sh_total;
+
+    // ---- threshold key: the top_k-th largest (keys are unique), or 1 = keep every non-dropped slot ----
+    unsigned long long thr_key = 1ull;
+    if (a.top_k > 0 && n > (unsigned int)a.top_k) {
+        if (tid == 0) { sh_prefix = 0ull; sh_k = (unsigned int)a.top_k; }
+        for (int pass = 7; pass >= 0; --pass) {
+            for (int i = tid; i < 256; i += kPfThreads) hist[i] = 0u;
+            __syncthreads();
+            const unsigned long long prefix = sh_prefix;
+            const int shift = pass * 8;
+            const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
+            for (int slot = tid; slot < a.tiles * kTileAnchors; slot += kPfThreads) {
+                const int t = slot / kTileAnchors, j = slot - t * kTileAnchors;
+                if (j >= tcount[t]) continue;
+                const unsigned long long k64 = key[slot];
+                if (k64 != 0ull && (k64 & himask) == prefix) atomicAdd(&hist[(unsigned int)(k64 >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned int need = sh_k, acc = 0u;
+                int d = 255;
+                for (; d > 0; --d) { if (acc + hist[d] >= need) break; acc += hist[d]; }
+                sh_prefix = prefix | ((unsigned long long)d << shift);
+                sh_k = need - acc;                          // rank of the wanted key inside digit d
+            }
+            __syncthreads();
+        }
+        thr_key = sh_prefix;
+    }
+
+    // ---- stable re-compaction of every tile, one warp per tile ----
+    for (int t = warp; t < a.tiles; t += kPfThreads / 32) {
+        const int cnt = tcount[t];
+        int kept = 0;
+        for (int c0 = 0; c0 < cnt; c0 += 32) {
+            const int j = c0 + lane;
+            const int slot = t * kTileAnchors + j;
+            const bool valid = j < cnt;
+            const bool keep = valid && key[slot] >= thr_key;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const int dst = t * kTileAnchors + kept + __popc(bal & ((1u << lane) - 1u));     // dst <= slot
+            // element by element: every lane reads before any lane writes, so a row that is somebody's
+            // destination is never overwritten ahead of its own owner's read
+            const int32_t an = keep ? sanchor[slot] : 0;
+            __syncwarp();
+            if (keep) sanchor[dst] = an;
+            for (int k = 0; k < K; ++k) {
+                const float v = keep ? scounts[(size_t)slot * K + k] : 0.0f;
+                __syncwarp();
+                if (keep) scounts[(size_t)dst * K + k] = v;
+            }
+            kept += __popc(bal);
+            __syncwarp();
+        }
+        __syncwarp();
+        if (lane == 0) tcount[t] = kept;
+    }
+}
+
+cudaError_t launch_prefilter(const PrefilterArgs& a, cudaStream_t st) {
+    prefilter_kernel<<<a.B, kPfThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // anchors: fpn_anchor_generator.py:21-59, levels 3..7 concatenated P3 -> P7
 // ---------------------------------------------------------------------------
 struct AnchorLevels {

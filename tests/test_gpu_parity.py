@@ -94,6 +94,60 @@ def test_softnms_overflow_paths(name, env, monkeypatch):
     test_synthetic_batch_bit_exact(name)
 
 
+PREFILTER = {
+    # name: (SceneSpec kwargs, OracleConfig kwargs)
+    "top_k": (dict(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=51), dict(pre_nms_top_k=200)),
+    "top_k_k11": (dict(im_h=192, im_w=320, N=6, K=11, g_min=6, g_max=10, box_hi=150., fg_logit=1.0, bg_logit_for_fg=0.0,
+                       stray_frac=0.02, config_id=52), dict(pre_nms_top_k=300)),
+    "threshold": (dict(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., fg_logit=1.0, bg_logit_for_fg=0.0,
+                       config_id=53), dict(score_threshold=0.6)),
+    "both": (dict(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., fg_logit=1.0, bg_logit_for_fg=0.0,
+                  config_id=54), dict(score_threshold=0.3, pre_nms_top_k=100)),
+    "top_k_inactive": (dict(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=55),
+                       dict(pre_nms_top_k=100000, score_threshold=0.01)),
+    "drops_everything": (dict(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=56),
+                         dict(score_threshold=2.0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PREFILTER))
+def test_prefilter_extension_bit_exact(name):
+    """score_threshold / pre_nms_top_k (BASELINE config 5 knobs; semantics = the oracle's orc_prefilter):
+    the kept anchors and everything downstream are bit-exact."""
+    spec_kw, oc_kw = PREFILTER[name]
+    spec = synthetic.SceneSpec(**spec_kw)
+    B = 3
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, B))
+    oc = oracle.OracleConfig(**oc_kw)
+    plain = oracle.OracleConfig()
+    eng, res = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"])
+    cut = 0
+    for b in range(B):
+        r = oracle.run_image(oc, batch["cls"][b], batch["box"][b], batch["cov"][b], batch["anchors"], batch["counts"][b])
+        r0 = oracle.category_filter(batch["counts"][b])
+        cut += len(r0) - len(r.keep)
+        compare_image_with_oracle(eng, res, b, r, spec.K)
+    if name in ("top_k", "top_k_k11", "threshold", "both"):
+        assert cut > 0, "the knob did not bite: the case tests nothing"
+    if name == "drops_everything":
+        assert res.num_survivors.sum() == 0 and res.num_dets.sum() == 0
+    del plain
+
+
+def test_prefilter_top_k_above_the_fast_softnms_capacity():
+    """Stress shape (config 5): tens of thousands of survivors capped to 10 000 by pre_nms_top_k, which is
+    more than the shared-memory soft-NMS kernel holds (falls through to the global-memory kernel)."""
+    spec = synthetic.SceneSpec(N=4, K=11, g_min=80, g_max=120, fg_iou=0.2, fg_logit=1.0, bg_logit_for_fg=0.0,
+                               stray_frac=0.02, config_id=5)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, 1))
+    oc = oracle.OracleConfig(pre_nms_top_k=10000, score_threshold=0.01)
+    eng, res = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"], emit_probs=False)
+    r = oracle.run_image(oc, batch["cls"][0], batch["box"][0], batch["cov"][0], batch["anchors"], batch["counts"][0],
+                         with_probs=False)
+    assert len(oracle.category_filter(batch["counts"][0])) > 10000 and len(r.keep) == 10000
+    compare_image_with_oracle(eng, res, 0, r, 11, check_probs=False)
+
+
 def test_host_path_equals_device_path():
     spec = synthetic.SceneSpec(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=3)
     B = 9       # > 8 so that the host path splits the batch into chunks
