@@ -47,12 +47,15 @@ struct bod_ctx {
     Lane lane[2];
     int nlanes = 1, cur = 0;          // cur: lane of the last issued run
     int32_t* status = nullptr;
-    unsigned long long* pf_key = nullptr;   // pre-NMS filter scratch [B,A] (only with score_threshold / pre_nms_top_k)
+    // pre-NMS filter (only with score_threshold / pre_nms_top_k): key scratch [B,A], threshold keys [B], and the
+    // filtered slot lists K2 reads instead of K1's (the head stream serialises their use across lanes)
+    unsigned long long* pf_key = nullptr; unsigned long long* pf_thr = nullptr;
+    int32_t* pf_anchor = nullptr; float* pf_counts = nullptr; int32_t* pf_tile_count = nullptr;
     bool prefilter = false;
     uint32_t* ticket = nullptr;       // K1's dynamic tile scheduler: monotonically increasing ticket counter
     uint32_t ticket_next = 0;         // its value once every launch issued so far has finished
     float* probs = nullptr; float* sampled = nullptr;
-    int fastS = 0, pstride = 0;
+    int fastS = 0, pstride = 0, pw_rows = 0, k3_smem_S = 0, k3_rows = 0;
     // device staging of host inputs (bod_run_host), allocated on first use
     float* in_cls = nullptr; float* in_box = nullptr; float* in_cov = nullptr; float* in_anchors = nullptr; float* in_counts = nullptr;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
@@ -72,7 +75,6 @@ struct bod_ctx {
     bool host_copy_all = false;       // BOD_HOST_COPY_ALL: never read box/cov in place from pinned host memory
     int k1_debug = 0;                 // BOD_K1_DEBUG (diagnostics)
     long long* k3_dbg = nullptr;      // BOD_K3_DEBUG (diagnostics): [B][8] cycle counters
-    bool k2_on_tail = false;          // pipelined mode: issue K2 with the tail (BOD_K2_TAIL=1, experiment)
     int k3_seg_cap = -1, k3_psm_max = -1;   // BOD_K3_SEGCAP / BOD_K3_PSM_MAX (tests: reach the overflow paths on small inputs)
 };
 
@@ -149,6 +151,13 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     c->nlanes = (cfg->pipeline_depth >= 2) ? 2 : 1;
     c->fastS = k3_fast_capacity(c->capacity);
     c->pstride = (c->Dmax + 3) & ~3;
+    c->pw_rows = c->capacity < 65535 ? c->capacity : 65535;
+    int k3_smem_S = c->fastS, k3_rows = c->pw_rows;       // BOD_K3_MODE (tests): force the soft-NMS variants
+    if (const char* md = getenv("BOD_K3_MODE")) {
+        if (!strcmp(md, "big")) k3_smem_S = 0;                              // per-candidate state in global memory
+        else if (!strcmp(md, "generic")) { k3_smem_S = 0; k3_rows = 0; }    // the literal round-per-selection kernel
+    }
+    c->k3_smem_S = k3_smem_S; c->k3_rows = k3_rows;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     struct Piece { void** p; size_t o; };
@@ -157,7 +166,11 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     TAKE(c->status, 256);
     TAKE(c->ticket, 256);
     c->prefilter = cfg->pre_nms_top_k > 0 || cfg->score_threshold > -INFINITY;
-    if (c->prefilter) TAKE(c->pf_key, (size_t)B * A * 8);
+    if (c->prefilter) {
+        TAKE(c->pf_key, (size_t)B * A * 8); TAKE(c->pf_thr, (size_t)B * 8);
+        TAKE(c->pf_anchor, (size_t)B * A * 4); TAKE(c->pf_counts, (size_t)B * A * K * 4);
+        TAKE(c->pf_tile_count, (size_t)B * c->tiles * 4);
+    }
     if (cfg->emit_probs) { TAKE(c->probs, (size_t)B * A * K * 4); TAKE(c->sampled, (size_t)B * A * K * 4); }
     for (int l = 0; l < c->nlanes; ++l) {
         Lane& L = c->lane[l];
@@ -177,7 +190,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
         TAKE(L.cur, B * cap * 4);
         TAKE(L.begin, B * cap * 4);
         TAKE(L.pend, B * cap * kPendStride * 4);
-        TAKE(L.pw, (size_t)B * c->fastS * c->pstride * 4);
+        TAKE(L.pw, (size_t)B * c->pw_rows * c->pstride * 4);
         TAKE(L.nms_idx, B * D * 4);
         TAKE(L.nms_score, B * D * 4);
         TAKE(L.centre_anchor, B * D * 4);
@@ -202,9 +215,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     {
         int lo = 0, hi = 0;                                  // the tail is latency-bound and short: let its CTAs go first
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        const char* pr = getenv("BOD_TAIL_PRIORITY");
-        const int tail_prio = (pr && atoi(pr) == 0) ? lo : hi;
-        cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, tail_prio);
+        cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, hi);
     }
     cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
     for (int l = 0; l < c->nlanes; ++l) {
@@ -216,7 +227,6 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
     if (const char* d = getenv("BOD_K1_DEBUG")) c->k1_debug = atoi(d);
     c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
-    if (const char* d = getenv("BOD_K2_TAIL")) c->k2_on_tail = atoi(d) != 0;
     if (const char* d = getenv("BOD_K3_SEGCAP")) { int v = atoi(d); if (v >= 0) c->k3_seg_cap = v; }
     if (const char* d = getenv("BOD_K3_PSM_MAX")) c->k3_psm_max = atoi(d);
     if (getenv("BOD_K3_DEBUG")) { cudaMalloc(&c->k3_dbg, (size_t)B * 8 * sizeof(long long)); cudaMemset(c->k3_dbg, 0, (size_t)B * 8 * sizeof(long long)); }
@@ -266,35 +276,41 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
     if (record) CU(c, cudaEventRecord(c->ev[1], hs));
 
     int launches = 3;
-    if (c->prefilter) {
-        PrefilterArgs pf{};
-        pf.slot_anchor = k1.slot_anchor; pf.slot_counts = k1.slot_counts; pf.tile_count = k1.tile_count;
-        pf.key = c->pf_key + b0 * A;
-        pf.B = nb; pf.A = g.A; pf.K = g.K; pf.tiles = c->tiles;
-        pf.dirichlet = g.dirichlet_prior == BOD_DIRICHLET_NON_INFORMATIVE;
-        pf.score_threshold = g.score_threshold; pf.top_k = g.pre_nms_top_k;
-        CU(c, launch_prefilter(pf, hs));
-        ++launches;
-    }
+    const int32_t* slot_anchor = k1.slot_anchor;      // the slot lists K2 reads: K1's, or the filtered ones
+    const float* slot_counts = k1.slot_counts;
     ScanArgs sc{};
     sc.tile_count = k1.tile_count; sc.tile_off = L.tile_off + (size_t)b0 * (c->tiles + 1);
     sc.num_survivors = L.num_survivors + b0; sc.status = c->status;
     sc.B = nb; sc.tiles = c->tiles; sc.capacity = c->capacity;
+    if (c->prefilter) {
+        // scan (dense indexing of the slots) -> filter -> scan again on the new counts; the capacity check
+        // belongs to the second scan only
+        ScanArgs s0 = sc;
+        s0.capacity = 0x7fffffff;
+        CU(c, launch_scan(s0, hs));
+        PrefilterArgs pf{};
+        pf.slot_anchor = k1.slot_anchor; pf.slot_counts = k1.slot_counts; pf.tile_count = k1.tile_count;
+        pf.tile_off = sc.tile_off;
+        pf.out_anchor = c->pf_anchor + b0 * A; pf.out_counts = c->pf_counts + b0 * A * K;
+        pf.out_tile_count = c->pf_tile_count + (size_t)b0 * c->tiles;
+        pf.key = c->pf_key + b0 * A; pf.thr_key = c->pf_thr + b0;
+        pf.B = nb; pf.A = g.A; pf.K = g.K; pf.tiles = c->tiles;
+        pf.dirichlet = g.dirichlet_prior == BOD_DIRICHLET_NON_INFORMATIVE;
+        pf.score_threshold = g.score_threshold; pf.top_k = g.pre_nms_top_k;
+        CU(c, launch_prefilter(pf, hs));
+        sc.tile_count = pf.out_tile_count;
+        slot_anchor = pf.out_anchor; slot_counts = pf.out_counts;
+        launches += 4;
+    }
     CU(c, launch_scan(sc, hs));
     if (record) CU(c, cudaEventRecord(c->ev[2], hs));
 
     // K2 overwrites what the previous tail on this lane (two runs ago) reads
-    const bool k2_tail = (hs != ts) && c->k2_on_tail;
-    cudaStream_t k2s = k2_tail ? ts : hs;
-    if (k2_tail) {
-        CU(c, cudaEventRecord(L.head_done, hs));
-        CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));     // same-stream order already covers the lane's previous tail
-    } else if (hs != ts && L.tail_pending) {
-        CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
-    }
+    // (K2 stays on the head stream: with it on the tail, the tail becomes the longer leg -- measured)
+    if (hs != ts && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
     K2Args k2{};
     k2.box = box; k2.cov = cw ? cov : nullptr; k2.anchors = anchors;
-    k2.slot_anchor = k1.slot_anchor; k2.slot_counts = k1.slot_counts; k2.tile_off = sc.tile_off;
+    k2.slot_anchor = slot_anchor; k2.slot_counts = slot_counts; k2.tile_off = sc.tile_off;
     k2.num_survivors = sc.num_survivors;
     k2.surv_anchor = L.surv_anchor + b0 * cap; k2.cnt_post = L.cnt_post + b0 * cap * K;
     k2.mu_post = L.mu_post + b0 * cap * 4; k2.sig_post = L.sig_post + b0 * cap * 16;
@@ -307,10 +323,10 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
                          g.dirichlet_prior != BOD_PRIOR_NONE) ? 1 : 0;
     k2.isotropic_variance = g.isotropic_variance; k2.scale_v = g.scale_v; k2.scale_u = g.scale_u;
     k2.anchor_mode = g.anchor_mode; k2.im_h = g.im_h; k2.im_w = g.im_w;
-    CU(c, launch_k2(k2, k2s));
-    if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, k2s)); ++launches; }
-    if (record) CU(c, cudaEventRecord(c->ev[3], k2s));
-    if (hs != ts && !k2_tail) {
+    CU(c, launch_k2(k2, hs));
+    if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, hs)); ++launches; }
+    if (record) CU(c, cudaEventRecord(c->ev[3], hs));
+    if (hs != ts) {
         CU(c, cudaEventRecord(L.head_done, hs));
         CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));
     }
@@ -320,8 +336,8 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
     k3.corners = k2.corners; k3.score = k2.score; k3.num_survivors = sc.num_survivors; k3.surv_anchor = k2.surv_anchor;
     k3.stale = L.stale + b0 * cap; k3.cur = L.cur + b0 * cap; k3.begin = L.begin + b0 * cap;
     k3.pend = L.pend + b0 * cap * kPendStride;
-    k3.pw = L.pw + (size_t)b0 * c->fastS * c->pstride;
-    k3.fastS = c->fastS; k3.pstride = c->pstride;
+    k3.pw = L.pw + (size_t)b0 * c->pw_rows * c->pstride; k3.pw_rows = c->pw_rows; k3.max_rows = c->k3_rows;
+    k3.fastS = c->k3_smem_S; k3.pstride = c->pstride;
     k3.nms_idx = L.nms_idx + b0 * D; k3.nms_score = L.nms_score + b0 * D; k3.centre_anchor = L.centre_anchor + b0 * D;
     k3.num_dets = L.num_dets + b0; k3.member = L.member + b0 * D * c->words;
     k3.B = nb; k3.capacity = c->capacity; k3.Dmax = c->Dmax; k3.words = c->words;

@@ -39,10 +39,15 @@ cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st);
 
 // ---- K1c: pre-NMS filter on the slot lists (extension knobs score_threshold / pre_nms_top_k) --
 struct PrefilterArgs {
-    int32_t* slot_anchor;       // [B,A]   re-compacted in place, tile by tile
-    float* slot_counts;         // [B,A,K]
-    int32_t* tile_count;        // [B,tiles] updated
+    const int32_t* slot_anchor; // [B,A]   K1's slot lists ...
+    const float* slot_counts;   // [B,A,K]
+    const int32_t* tile_count;  // [B,tiles]
+    const int32_t* tile_off;    // [B,tiles+1] exclusive scan of tile_count
+    int32_t* out_anchor;        // [B,A]   ... and the filtered ones (same layout)
+    float* out_counts;          // [B,A,K]
+    int32_t* out_tile_count;    // [B,tiles]
     unsigned long long* key;    // [B,A] scratch
+    unsigned long long* thr_key;  // [B] scratch
     int B, A, K, tiles;
     int dirichlet;              // counts + 1/K before normalising (non_informative prior)
     float score_threshold;      // keep iff score > threshold (-inf: all)
@@ -87,7 +92,9 @@ struct K3Args {
     float* cur;       // up-to-date score
     int32_t* begin;   // suppress_begin_index
     uint32_t* pend;   // [B,cap,kPendStride] pending-selection bitmask (generic kernel)
-    float* pw;        // [B,fastS,pstride] spill rows of the pending soft-NMS weights (fast kernel)
+    float* pw;        // [B,pw_rows,pstride] spill rows of the pending soft-NMS weights (fast kernel)
+    int pw_rows;      // rows per image in pw: min(capacity, 65535)
+    int max_rows;     // survivors the fast kernel takes (<= pw_rows: its list entries hold 16-bit indices); more: literal kernel
     int fastS, pstride;
     // outputs
     int32_t* nms_idx;           // [B,Dmax]

@@ -74,11 +74,14 @@ cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st) {
 //   (2) if more than top_k remain keep the top_k by (score desc, anchor index asc),
 //   (3) keep ascending anchor order.
 // The score depends on the counts only, so this runs between K1 and K2, on the
-// per-tile slot lists: one CTA per image computes a 64-bit key per slot, finds the
-// top_k-th largest key with an 8 x 8-bit radix select (keys are unique) and
-// re-compacts every tile in place; the tile scan then runs on the new counts.
+// per-tile slot lists: (a) a 64-bit key per slot, one warp per tile; (b) one CTA per
+// image finds the top_k-th largest key with an 8 x 8-bit radix select (keys are
+// unique); (c) every tile is re-compacted, one warp per tile, into a second set of
+// slot lists.  The tile scan runs before (dense key indexing) and again after (the
+// new counts).
 // ---------------------------------------------------------------------------
 constexpr int kPfThreads = 1024;
+constexpr int kPfTileWarps = 8;           // tiles per CTA in the key / compaction kernels
 
 BOD_DEVINL float count_score(const float* c, int K, bool dirichlet) {
     const float alpha = 1.0f / (float)K;
@@ -91,37 +94,46 @@ BOD_DEVINL float count_score(const float* c, int K, bool dirichlet) {
     return best;
 }
 
-__global__ void __launch_bounds__(kPfThreads) prefilter_kernel(PrefilterArgs a) {
+// (a) keys: (score, -anchor), 0 = dropped by the threshold; dense entry tile_off[t] + j for slot (t, j).
+// One warp per tile, grid (tiles / kPfTileWarps, B).
+__global__ void __launch_bounds__(kPfTileWarps * 32) prefilter_keys_kernel(PrefilterArgs a) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kPfTileWarps + (threadIdx.x >> 5);
+    if (t >= a.tiles) return;
+    const int K = a.K;
+    const int cnt = a.tile_count[(size_t)b * a.tiles + t];
+    const int off = a.tile_off[(size_t)b * (a.tiles + 1) + t];
+    const int32_t* sanchor = a.slot_anchor + (size_t)b * a.A;
+    const float* scounts = a.slot_counts + (size_t)b * a.A * K;
+    unsigned long long* key = a.key + (size_t)b * a.A;
+    for (int j = lane; j < cnt; j += 32) {
+        const int slot = t * kTileAnchors + j;
+        const float sc = count_score(scounts + (size_t)slot * K, K, a.dirichlet != 0);
+        unsigned long long k64 = 0ull;
+        if (sc > a.score_threshold)
+            k64 = ((unsigned long long)float_key(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)sanchor[slot]);
+        key[off + j] = k64;
+    }
+}
+
+// (b) threshold key per image: the top_k-th largest key (keys are unique), or 1 = keep every
+// non-dropped slot.  One CTA per image, 8 x 8-bit radix select over the dense keys.
+__global__ void __launch_bounds__(kPfThreads) prefilter_select_kernel(PrefilterArgs a) {
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long sh_prefix;
     __shared__ unsigned int sh_k, sh_total;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = a.K;
-    int32_t* tcount = a.tile_count + (size_t)b * a.tiles;
-    int32_t* sanchor = a.slot_anchor + (size_t)b * a.A;
-    float* scounts = a.slot_counts + (size_t)b * a.A * K;
-    unsigned long long* key = a.key + (size_t)b * a.A;
-
-    // ---- keys: (score, -anchor); 0 = dropped by the threshold ----
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const unsigned long long* key = a.key + (size_t)b * a.A;
+    const int S0 = a.tile_off[(size_t)b * (a.tiles + 1) + a.tiles];
     if (tid == 0) sh_total = 0u;
     __syncthreads();
     unsigned int mine = 0u;
-    for (int slot = tid; slot < a.tiles * kTileAnchors; slot += kPfThreads) {
-        const int t = slot / kTileAnchors, j = slot - t * kTileAnchors;
-        if (j >= tcount[t]) continue;
-        const float sc = count_score(scounts + (size_t)slot * K, K, a.dirichlet != 0);
-        unsigned long long k64 = 0ull;
-        if (sc > a.score_threshold) {
-            k64 = ((unsigned long long)float_key(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)sanchor[slot]);
-            ++mine;
-        }
-        key[slot] = k64;
-    }
-    if (mine) atomicAdd(&sh_total, mine);
+    for (int i = tid; i < S0; i += kPfThreads) mine += key[i] != 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0 && mine) atomicAdd(&sh_total, mine);
     __syncthreads();
     const unsigned int n = sh_total;
-
-    // ---- threshold key: the top_k-th largest (keys are unique), or 1 = keep every non-dropped slot ----
     unsigned long long thr_key = 1ull;
     if (a.top_k > 0 && n > (unsigned int)a.top_k) {
         if (tid == 0) { sh_prefix = 0ull; sh_k = (unsigned int)a.top_k; }
@@ -131,11 +143,15 @@ __global__ void __launch_bounds__(kPfThreads) prefilter_kernel(PrefilterArgs a) 
             const unsigned long long prefix = sh_prefix;
             const int shift = pass * 8;
             const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-            for (int slot = tid; slot < a.tiles * kTileAnchors; slot += kPfThreads) {
-                const int t = slot / kTileAnchors, j = slot - t * kTileAnchors;
-                if (j >= tcount[t]) continue;
-                const unsigned long long k64 = key[slot];
-                if (k64 != 0ull && (k64 & himask) == prefix) atomicAdd(&hist[(unsigned int)(k64 >> shift) & 255u], 1u);
+            for (int i0 = 0; i0 < S0; i0 += kPfThreads) {                 // warp-uniform trip count
+                const int i = i0 + tid;
+                const unsigned long long k64 = (i < S0) ? key[i] : 0ull;
+                const bool in = k64 != 0ull && (k64 & himask) == prefix;
+                // scores take few distinct values, so most keys share their digit: one atomic per distinct
+                // digit and warp instead of one per key
+                const unsigned int digit = in ? ((unsigned int)(k64 >> shift) & 255u) : 256u;
+                const unsigned int peers = __match_any_sync(0xffffffffu, digit);
+                if (in && (int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
             }
             __syncthreads();
             if (tid == 0) {
@@ -149,38 +165,47 @@ __global__ void __launch_bounds__(kPfThreads) prefilter_kernel(PrefilterArgs a) 
         }
         thr_key = sh_prefix;
     }
+    if (tid == 0) a.thr_key[b] = thr_key;
+}
 
-    // ---- stable re-compaction of every tile, one warp per tile ----
-    for (int t = warp; t < a.tiles; t += kPfThreads / 32) {
-        const int cnt = tcount[t];
-        int kept = 0;
-        for (int c0 = 0; c0 < cnt; c0 += 32) {
-            const int j = c0 + lane;
-            const int slot = t * kTileAnchors + j;
-            const bool valid = j < cnt;
-            const bool keep = valid && key[slot] >= thr_key;
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            const int dst = t * kTileAnchors + kept + __popc(bal & ((1u << lane) - 1u));     // dst <= slot
-            // element by element: every lane reads before any lane writes, so a row that is somebody's
-            // destination is never overwritten ahead of its own owner's read
-            const int32_t an = keep ? sanchor[slot] : 0;
-            __syncwarp();
-            if (keep) sanchor[dst] = an;
-            for (int k = 0; k < K; ++k) {
-                const float v = keep ? scounts[(size_t)slot * K + k] : 0.0f;
-                __syncwarp();
-                if (keep) scounts[(size_t)dst * K + k] = v;
-            }
-            kept += __popc(bal);
-            __syncwarp();
+// (c) stable compaction of every tile into the second set of slot lists (out of place: rows are copied
+// with independent loads), new tile counts.  One warp per tile, grid (tiles / kPfTileWarps, B).
+__global__ void __launch_bounds__(kPfTileWarps * 32) prefilter_compact_kernel(PrefilterArgs a) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kPfTileWarps + (threadIdx.x >> 5);
+    if (t >= a.tiles) return;
+    const int K = a.K;
+    const int cnt = a.tile_count[(size_t)b * a.tiles + t];
+    const int off = a.tile_off[(size_t)b * (a.tiles + 1) + t];
+    const unsigned long long thr_key = a.thr_key[b];
+    const int32_t* sanchor = a.slot_anchor + (size_t)b * a.A;
+    const float* scounts = a.slot_counts + (size_t)b * a.A * K;
+    int32_t* oanchor = a.out_anchor + (size_t)b * a.A;
+    float* ocounts = a.out_counts + (size_t)b * a.A * K;
+    const unsigned long long* key = a.key + (size_t)b * a.A;
+    int kept = 0;
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+        const int j = c0 + lane;
+        const int slot = t * kTileAnchors + j;
+        const bool keep = (j < cnt) && key[off + j] >= thr_key;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int dst = t * kTileAnchors + kept + __popc(bal & ((1u << lane) - 1u));
+            oanchor[dst] = sanchor[slot];
+            const float* src = scounts + (size_t)slot * K;
+            float* d = ocounts + (size_t)dst * K;
+            for (int k = 0; k < K; ++k) d[k] = src[k];
         }
-        __syncwarp();
-        if (lane == 0) tcount[t] = kept;
+        kept += __popc(bal);
     }
+    if (lane == 0) a.out_tile_count[(size_t)b * a.tiles + t] = kept;
 }
 
 cudaError_t launch_prefilter(const PrefilterArgs& a, cudaStream_t st) {
-    prefilter_kernel<<<a.B, kPfThreads, 0, st>>>(a);
+    dim3 grid((a.tiles + kPfTileWarps - 1) / kPfTileWarps, a.B);
+    prefilter_keys_kernel<<<grid, kPfTileWarps * 32, 0, st>>>(a);
+    prefilter_select_kernel<<<a.B, kPfThreads, 0, st>>>(a);
+    prefilter_compact_kernel<<<grid, kPfTileWarps * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -388,7 +388,10 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = a.num_survivors[b];
-    if (S > smem_S) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
+    // more survivors than the shared-memory pool holds: same algorithm with the per-candidate state in
+    // global memory (L2-resident scratch rows of the workspace); beyond 16-bit list entries: the literal kernel
+    const bool big = S > smem_S;
+    if (big && S > a.max_rows) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
 
     const int S32 = (S + 31) & ~31;
     uint32_t* list = reinterpret_cast<uint32_t*>(dyn);                    // [kK3Warps][kSegCap] pair entries (ent_make)
@@ -403,6 +406,13 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
     psm &= ~3;                                                            // rows are read four weights at a time
     float* pws = stl + S32;                                               // [S32][psm]
     uint8_t* npend = reinterpret_cast<uint8_t*>(pws + (size_t)psm * S32); // [S32] pending entries per candidate
+    if (big) {
+        corn = const_cast<float4*>(a.corners + (size_t)b * a.capacity);   // read in place, never written
+        ucur = a.cur + (size_t)b * a.capacity;
+        stl = a.stale + (size_t)b * a.capacity;
+        npend = reinterpret_cast<uint8_t*>(a.begin + (size_t)b * a.capacity);
+        psm = 0; pws = nullptr;
+    }
 
     const int Dmax = a.Dmax;
     const float4* corners = a.corners + (size_t)b * a.capacity;
@@ -410,7 +420,7 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
     K3State C;
     C.corn = corn; C.ucur = ucur; C.stl = stl; C.npend = npend;
     C.pws = pws; C.S32 = S32; C.psm = psm;
-    C.pwg = a.pw + (size_t)b * a.fastS * a.pstride; C.pstride = a.pstride;
+    C.pwg = a.pw + (size_t)b * a.pw_rows * a.pstride; C.pstride = a.pstride;
     C.member = a.member + (size_t)b * Dmax * a.words; C.words = a.words;
     C.is_soft = a.soft_nms_sigma > 0.0f;
     C.scale = C.is_soft ? -0.5f / a.soft_nms_sigma : 0.0f;
@@ -430,7 +440,7 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
     Top2 t2k;
     for (int s = tid; s < S; s += kK3Threads) {
         const float4 c = corners[s];
-        corn[s] = c;
+        if (!big) corn[s] = c;
         if (!((c.x <= c.z) && (c.y <= c.w))) sm.malformed = 1;          // needs the canonicalising IoU path every round
         const float sc = score[s];
         const bool queued = sc > -INFINITY;                              // scores_data[i] > score_threshold (-inf); NaN stays out

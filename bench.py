@@ -42,6 +42,10 @@ WORKLOADS = {
     "bdd_kendall_b8_k8": dict(im_h=720, im_w=1280, N=10, K=8, B=8, use_full_covar=False, config_id=2),
     "kitti_covar_b64_n20_k4": dict(im_h=512, im_w=1696, N=20, K=4, B=64, use_full_covar=True, config_id=4,
                                    scale_v=375 / 512, scale_u=1242 / 1696),
+    # BASELINE.json config 5 (clustering stress): threshold 0.01, top-k 10k per image, N=40; 128 images over 8 GPUs
+    "stress_b16_n40_k11": dict(im_h=720, im_w=1280, N=40, K=11, B=16, use_full_covar=True, config_id=5,
+                               spec=dict(g_min=80, g_max=120, fg_iou=0.2, fg_logit=1.0, bg_logit_for_fg=0.0, stray_frac=0.02),
+                               score_threshold=0.01, pre_nms_top_k=10000),
     "tiny": dict(im_h=192, im_w=320, N=10, K=8, B=4, use_full_covar=True, config_id=9),
 }
 DEFAULT_WORKLOAD = "bdd_covar_b32_k11"
@@ -171,7 +175,7 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     B = args.batch or wl["B"]
     N, K = wl["N"], wl["K"]
-    spec = synthetic.SceneSpec(im_h=wl["im_h"], im_w=wl["im_w"], N=N, K=K, config_id=wl["config_id"])
+    spec = synthetic.SceneSpec(im_h=wl["im_h"], im_w=wl["im_w"], N=N, K=K, config_id=wl["config_id"], **wl.get("spec", {}))
     first_image = rank * B                      # global image ids: shard-invariant RNG + data
 
     # ---- synthetic head outputs, generated on the device, then resident in HBM ----
@@ -184,7 +188,8 @@ def main():
 
     cfg = BayesODConfig(use_full_covar=wl["use_full_covar"], cov_layout=_cabi.COV_FULL16, seed=1234,
                         image_id_base=first_image, scale_v=wl.get("scale_v", 1.0), scale_u=wl.get("scale_u", 1.0),
-                        max_survivors=min(A, 32768), pipeline_depth=args.pipeline)
+                        max_survivors=min(A, 32768), pipeline_depth=args.pipeline,
+                        score_threshold=wl.get("score_threshold", float("-inf")), pre_nms_top_k=wl.get("pre_nms_top_k", 0))
     eng = BayesODEngine(B, N, A, K, cfg, device=local_rank)
     stream = torch.cuda.Stream(device=dev)
 
@@ -332,7 +337,9 @@ def main():
 def _oracle_cfg(wl, image_id_base):
     import oracle
     return oracle.OracleConfig(use_full_covar=wl["use_full_covar"], cov_layout=1, seed=1234, image_id_base=image_id_base,
-                               scale_v=wl.get("scale_v", 1.0), scale_u=wl.get("scale_u", 1.0))
+                               scale_v=wl.get("scale_v", 1.0), scale_u=wl.get("scale_u", 1.0),
+                               score_threshold=wl.get("score_threshold", float("-inf")),
+                               pre_nms_top_k=wl.get("pre_nms_top_k", 0))
 
 
 def cpu_baseline(cls, box, cov, anchors, wl, sample, first_image):
@@ -370,7 +377,7 @@ def reference_arm(args, rank):
     cores = os.cpu_count() or 1
     n = args.cpu_sample or min(wl["B"], max(4, min(cores, 32)))
     threads = min(cores, n)
-    spec = synthetic.SceneSpec(im_h=wl["im_h"], im_w=wl["im_w"], N=N, K=K, config_id=wl["config_id"])
+    spec = synthetic.SceneSpec(im_h=wl["im_h"], im_w=wl["im_w"], N=N, K=K, config_id=wl["config_id"], **wl.get("spec", {}))
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     batch = synthetic.to_numpy(synthetic.make_batch(spec, n, device=dev, with_counts=False))
     oc = _oracle_cfg(wl, 0)

@@ -148,6 +148,15 @@ def test_prefilter_top_k_above_the_fast_softnms_capacity():
     compare_image_with_oracle(eng, res, 0, r, 11, check_probs=False)
 
 
+@pytest.mark.parametrize("mode", ["big", "generic"])
+@pytest.mark.parametrize("name", ["bdd_covar_k8", "dense_cluster_sigma", "hard_nms", "kitti_k4_n20"])
+def test_softnms_large_survivor_variants(name, mode, monkeypatch):
+    """The soft-NMS variants for survivor counts beyond the shared-memory pool (state in global memory) and
+    beyond 16-bit list entries (the literal round-per-selection kernel), forced on small inputs."""
+    monkeypatch.setenv("BOD_K3_MODE", mode)
+    test_synthetic_batch_bit_exact(name)
+
+
 def test_host_path_equals_device_path():
     spec = synthetic.SceneSpec(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=3)
     B = 9       # > 8 so that the host path splits the batch into chunks
