@@ -37,6 +37,14 @@ class BodConfig(C.Structure):
     ]
 
 
+class BodValScaling(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("shift", C.c_float * 4), ("norm_h", C.c_float), ("norm_w", C.c_float),
+                ("scale_h", C.c_float), ("scale_w", C.c_float)]
+
+
+VAL_SCALE_NONE, VAL_SCALE_KITTI, VAL_SCALE_COCO = 0, 1, 2
+
+
 class BodHostResults(C.Structure):
     _fields_ = [
         ("num_dets", C.c_void_p), ("num_survivors", C.c_void_p), ("means", C.c_void_p), ("covs", C.c_void_p),
@@ -66,6 +74,7 @@ SYMBOLS = {
     "bod_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "bod_run": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
     "bod_wait_results": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bod_validate_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BodValScaling), C.c_void_p]),
     "bod_run_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(BodHostResults)]),
     "bod_last_host_traffic": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bod_cluster_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

@@ -25,6 +25,7 @@ UNITS = {
     "k2_posterior.cu": ["-fmad=false"],
     "k3_softnms.cu": ["-fmad=false"],
     "k4_fusion.cu": ["-fmad=false"],
+    "kv_validation.cu": ["-fmad=false"],
     "bod_api.cu": ["-fmad=false"],
 }
 HEADERS = ["bod_common.cuh", "bod_kernels.h", os.path.join("..", "..", "include", "bayesod.h")]

@@ -124,7 +124,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     c->device = device;
     auto bad = [&](const char* msg) { snprintf(create_err, sizeof create_err, "%s", msg); delete c; return BOD_ERR_INVALID; };
     if (cfg->B < 1 || cfg->B > 128) return bad("B must be in [1,128]");
-    if (cfg->N < 2) return bad("N (mc_dropout_samples) must be >= 2: the sample covariance divides by N-1");
+    if (cfg->N < 1) return bad("N (mc_dropout_samples) must be >= 1");
     if (cfg->A < 1) return bad("A must be positive");
     if (!k1_supports(cfg->K)) return bad("unsupported K (classes + background)");
     if (cfg->max_output_size < 1 || cfg->max_output_size > 255) return bad("max_output_size must be in [1,255]");
@@ -373,6 +373,7 @@ extern "C" int bod_run(bod_ctx* c, const float* cls, const float* box, const flo
                        const float* counts, void* cuda_stream) {
     int rc = check_inputs(c, cls, box, cov, anchors);
     if (rc) return rc;
+    if (c->cfg.N < 2) return fail(c, BOD_ERR_INVALID, "bod_run needs N (mc_dropout_samples) >= 2: the sample covariance divides by N-1");
     if ((reinterpret_cast<uintptr_t>(box) & 15u) || (cov && (reinterpret_cast<uintptr_t>(cov) & 15u)) ||
         (anchors && (reinterpret_cast<uintptr_t>(anchors) & 15u)))
         return fail(c, BOD_ERR_INVALID, "box / cov / anchors must be 16-byte aligned");
@@ -401,6 +402,57 @@ extern "C" int bod_run(bod_ctx* c, const float* cls, const float* box, const flo
     if (c->timing) ++c->runs_recorded;
     c->last_timed = c->timing;
     c->ran = true; c->used_sampler = (counts == nullptr);
+    return BOD_OK;
+}
+
+// validation_utils.post_process_predictions (validation_utils.py:10-77) for the batch
+extern "C" int bod_validate_run(bod_ctx* c, const float* cls, const float* box, const float* anchors,
+                                const bod_val_scaling* scaling, void* cuda_stream) {
+    if (!c) return BOD_ERR_INVALID;
+    if (!cls || !box || !anchors) return fail(c, BOD_ERR_INVALID, "cls, box and anchors must not be NULL");
+    if ((reinterpret_cast<uintptr_t>(box) & 15u) || (reinterpret_cast<uintptr_t>(anchors) & 15u))
+        return fail(c, BOD_ERR_INVALID, "box / anchors must be 16-byte aligned");
+    if (scaling && (scaling->mode < 0 || scaling->mode > 2)) return fail(c, BOD_ERR_INVALID, "bad scaling mode");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (c->nlanes > 1) CU(c, cudaStreamSynchronize(c->tail_stream));    // drain pipelined runs first
+    c->cur = 0;
+    Lane& L = c->lane[0];
+    const bod_config& g = c->cfg;
+    c->launches = 0;
+    ValArgs v{};
+    v.cls = cls; v.box = box; v.anchors = anchors;
+    v.slot_anchor = L.slot_anchor; v.slot_counts = L.slot_counts; v.tile_count = L.tile_count;
+    v.tile_off = L.tile_off; v.num_survivors = L.num_survivors;
+    v.surv_anchor = L.surv_anchor; v.cnt_post = L.cnt_post; v.mu_post = L.mu_post; v.score = L.score; v.corners = L.corners;
+    v.nms_idx = L.nms_idx; v.num_dets = L.num_dets;
+    v.out_means = L.out_means; v.out_covs = L.out_covs; v.out_param = L.out_param; v.out_count = L.out_count;
+    v.B = g.B; v.A = g.A; v.K = g.K; v.tiles = c->tiles; v.capacity = c->capacity; v.Dmax = c->Dmax;
+    v.scale_mode = scaling ? scaling->mode : BOD_VAL_SCALE_NONE;
+    for (int i = 0; i < 4; ++i) v.shift[i] = scaling ? scaling->shift[i] : 0.0f;
+    v.norm_h = scaling ? scaling->norm_h : 1.0f; v.norm_w = scaling ? scaling->norm_w : 1.0f;
+    v.scale_h = scaling ? scaling->scale_h : 1.0f; v.scale_w = scaling ? scaling->scale_w : 1.0f;
+    CU(c, launch_val_filter(v, st));
+    ScanArgs sc{};
+    sc.tile_count = L.tile_count; sc.tile_off = L.tile_off; sc.num_survivors = L.num_survivors; sc.status = c->status;
+    sc.B = g.B; sc.tiles = c->tiles; sc.capacity = c->capacity;
+    CU(c, launch_scan(sc, st));
+    CU(c, launch_val_survivors(v, st));
+    K3Args k3{};
+    k3.corners = L.corners; k3.score = L.score; k3.num_survivors = L.num_survivors; k3.surv_anchor = L.surv_anchor;
+    k3.stale = L.stale; k3.cur = L.cur; k3.begin = L.begin; k3.pend = L.pend;
+    k3.pw = L.pw; k3.pw_rows = c->pw_rows; k3.max_rows = c->k3_rows;
+    k3.fastS = c->k3_smem_S; k3.pstride = c->pstride;
+    k3.nms_idx = L.nms_idx; k3.nms_score = L.nms_score; k3.centre_anchor = L.centre_anchor;
+    k3.num_dets = L.num_dets; k3.member = L.member;
+    k3.B = g.B; k3.capacity = c->capacity; k3.Dmax = c->Dmax; k3.words = c->words;
+    k3.iou_threshold = g.iou_threshold; k3.soft_nms_sigma = g.soft_nms_sigma;
+    k3.dbg = nullptr; k3.seg_cap = c->k3_seg_cap; k3.psm_max = c->k3_psm_max;
+    CU(c, launch_k3(k3, st));
+    CU(c, launch_val_gather(v, st));
+    c->launches = 5;
+    c->last_timed = false;
+    c->last_stream = st; c->ran = true; c->used_sampler = false;
     return BOD_OK;
 }
 

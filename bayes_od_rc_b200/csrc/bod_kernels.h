@@ -129,6 +129,24 @@ struct K4Args {
 };
 cudaError_t launch_k4(const K4Args& a, cudaStream_t st);
 
+// ---- validation post-process (validation_utils.py:10-77): V1 filter, V2 survivors, V3 gather ----
+struct ValArgs {
+    const float* cls;        // [B,A,K] logits (one sample)
+    const float* box;        // [B,A,4] deltas
+    const float* anchors;    // [A,4]
+    int32_t* slot_anchor; float* slot_counts; int32_t* tile_count;      // V1 out (slot_counts holds the probabilities)
+    const int32_t* tile_off; const int32_t* num_survivors;              // scan out
+    int32_t* surv_anchor; float* cnt_post; float* mu_post; float* score; float4* corners;   // V2 out
+    const int32_t* nms_idx; const int32_t* num_dets;                    // K3 out
+    float* out_means; float* out_covs; float* out_param; float* out_count;                  // V3 out
+    int B, A, K, tiles, capacity, Dmax;
+    int scale_mode;          // 0 none, 1 kitti, 2 coco (validation_utils.py:54-66)
+    float shift[4]; float norm_h, norm_w, scale_h, scale_w;
+};
+cudaError_t launch_val_filter(const ValArgs& a, cudaStream_t st);
+cudaError_t launch_val_survivors(const ValArgs& a, cudaStream_t st);
+cudaError_t launch_val_gather(const ValArgs& a, cudaStream_t st);
+
 // ---- anchors ----------------------------------------------------------------
 cudaError_t launch_generate_anchors(int im_h, int im_w, float* anchors, cudaStream_t st);
 int count_anchors(int im_h, int im_w);

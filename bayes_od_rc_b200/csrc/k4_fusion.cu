@@ -45,7 +45,7 @@ BOD_DEVINL float kl_div_norm(const float (&p)[K], const float (&qk_raw)[K]) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(kK4Warps * 32, 5)
+__global__ void __launch_bounds__(kK4Warps * 32, 6)
 k4_fusion_kernel(K4Args a) {
     __shared__ float stage[kK4Warps][32][21];     // per lane: 16 precision entries + 4 weighted-mean entries (+pad)
     __shared__ uint32_t mlist[kK4Warps][kK4List]; // ascending member indices of the segment being processed

@@ -244,6 +244,23 @@ class BayesODEngine:
         self._keep = (cls, box, cov, anchors, counts, keep)          # keep the buffers alive until fetch
         self._check(self.lib.bod_run(self._ctx, p_cls, p_box, p_cov, p_anc, p_cnt, C.c_void_p(int(stream) or None)))
 
+    def validate(self, cls, box, anchors, scaling=None, stream=0):
+        """validation_utils.post_process_predictions for the batch (bod_validate_run): device arrays
+        cls [B,A,K], box [B,A,4], anchors [A,4]; ``scaling`` = None | (mode, shift[4], (norm_h, norm_w),
+        (scale_h, scale_w)).  Fetch with ``fetch()``: classes in ``cat_param``, corners (vuvu) in ``means``."""
+        B, A, K = self.B, self.A, self.K
+        keep = []
+        p_cls = device_ptr(cls, B * A * K, keep)
+        p_box = device_ptr(box, B * A * 4, keep)
+        p_anc = device_ptr(anchors, A * 4, keep)
+        sc = None
+        if scaling is not None:
+            mode, shift, norm_hw, scale_hw = scaling
+            sc = C.byref(_cabi.BodValScaling(int(mode), (C.c_float * 4)(*[float(x) for x in shift]), float(norm_hw[0]),
+                                             float(norm_hw[1]), float(scale_hw[0]), float(scale_hw[1])))
+        self._keep = (cls, box, anchors, keep)
+        self._check(self.lib.bod_validate_run(self._ctx, p_cls, p_box, p_anc, sc, C.c_void_p(int(stream) or None)))
+
     def wait_results(self, stream=0):
         """Make ``stream`` wait for the results of the last run (pipeline_depth = 2 only; bod_wait_results)."""
         self._check(self.lib.bod_wait_results(self._ctx, C.c_void_p(int(stream) or None)))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BOD_ABI_VERSION 4
+#define BOD_ABI_VERSION 5
 
 typedef enum bod_status {
     BOD_OK            = 0,
@@ -59,7 +59,8 @@ typedef enum bod_status {
  * struct, plus the shapes and the extension knobs of SURVEY.md §8(d). */
 typedef struct bod_config {
     int32_t  B;                  /* images per call (the reference is B=1: run_inference.py:68) */
-    int32_t  N;                  /* mc_dropout_samples (retinanet_bdd.yaml:68)            */
+    int32_t  N;                  /* mc_dropout_samples (retinanet_bdd.yaml:68); >= 2 for
+                                    bod_run (sample covariance), ignored by bod_validate_run */
     int32_t  A;                  /* anchors per image                                      */
     int32_t  K;                  /* logits per anchor = classes + background (last)        */
     int32_t  cov_layout;         /* BOD_COV_*                                              */
@@ -173,6 +174,35 @@ int bod_run(bod_ctx* ctx, const float* cls, const float* box, const float* cov,
  * by consumers that read bod_device_results_of on their own stream; a no-op
  * otherwise (the run is already ordered on the caller's stream). */
 int bod_wait_results(bod_ctx* ctx, void* cuda_stream);
+
+/*
+ * The validation post-process: validation_utils.post_process_predictions
+ * (src/retina_net/experiments/validation_utils.py:10-77, called at
+ * run_validation.py:143-144) for B images, one deterministic sample each, no
+ * MC-dropout moments, no fusion: softmax -> arg-max filter -> decode -> the same
+ * soft-NMS (ctx's max_output_size / iou_threshold / soft_nms_sigma;
+ * validation_utils.py:47-52 hard-codes 100 / 0.5 / 0.5) -> gather.
+ *   cls [B,A,K] logits, box [B,A,4] deltas, anchors [A,4] (v,u,h,w), device memory
+ *   scaling: NULL (bdd) or how :54-66 rescales the selected corners
+ * Results come back through bod_fetch / bod_device_results_of:
+ *   cat_param [B,Dmax,K] = predicted_boxes_classes_out   (softmax rows of the selected boxes)
+ *   means     [B,Dmax,4] = predicted_boxes_corners_out   (v_min,u_min,v_max,u_max, rescaled)
+ *   num_dets, nms_indices, centre_anchor_idx, centre_scores, num_survivors as for bod_run;
+ *   covs and cat_count are zero.  bod_fetch_survivors gives the per-survivor softmax rows
+ *   (counts), unscaled corners and scores.  Uses the context's single-run buffers
+ *   (not pipelined); N of the context is ignored.
+ */
+#define BOD_VAL_SCALE_NONE  0 /* bdd: corners as decoded (validation_utils.py:65-66)              */
+#define BOD_VAL_SCALE_KITTI 1 /* (corners / [h,w,h,w]) * [H0,W0,H0,W0]            (:54-59)        */
+#define BOD_VAL_SCALE_COCO  2 /* ((corners - padding) / [h',w',h',w']) * [H0,W0,H0,W0]  (:60-64)  */
+typedef struct bod_val_scaling {
+    int32_t mode;             /* BOD_VAL_SCALE_*                                                   */
+    float   shift[4];         /* coco: sample_dict[IMAGE_PADDING_KEY][0]                           */
+    float   norm_h, norm_w;   /* normalize_2d_bounding_boxes divisor (box_utils.py:195-205)        */
+    float   scale_h, scale_w; /* expand_2d_bounding_boxes factor     (box_utils.py:208-220)        */
+} bod_val_scaling;
+int bod_validate_run(bod_ctx* ctx, const float* cls, const float* box, const float* anchors,
+                     const bod_val_scaling* scaling, void* cuda_stream);
 
 /* Same call with HOST buffers (what a caller holding numpy arrays makes):
  * stages `cls` host->device in image chunks overlapped with compute, runs the

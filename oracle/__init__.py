@@ -287,6 +287,44 @@ def run_image(cfg: OracleConfig, cls, box, cov, anchors, counts=None, image_id=0
     return r
 
 
+class _ValScaling(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("shift", C.c_float * 4), ("norm_h", C.c_float), ("norm_w", C.c_float),
+                ("scale_h", C.c_float), ("scale_w", C.c_float)]
+
+
+@dataclass
+class ValResult:
+    keep: np.ndarray = None        # [S] kept anchor indices
+    probs: np.ndarray = None       # [S,K] softmax probabilities
+    corners: np.ndarray = None     # [S,4] unscaled corners (what NMS sees)
+    scores: np.ndarray = None      # [S]
+    nms_indices: np.ndarray = None  # [D]
+    nms_scores: np.ndarray = None
+    classes_out: np.ndarray = None  # [D,K]
+    corners_out: np.ndarray = None  # [D,4]
+
+
+def val_postprocess(cls, box, anchors, max_output_size=100, iou_threshold=0.5, soft_nms_sigma=0.5,
+                    scale_mode=0, shift=(0, 0, 0, 0), norm_hw=(1, 1), scale_hw=(1, 1)) -> ValResult:
+    """validation_utils.post_process_predictions (validation_utils.py:10-77) for one image.
+    cls [A,K] logits, box [A,4] deltas, anchors [A,4].  scale_mode 0 none / 1 kitti / 2 coco."""
+    cls = _f(cls); A, K = cls.shape
+    box = _f(box).reshape(A, 4); anchors = _f(anchors).reshape(A, 4)
+    sc = _ValScaling(int(scale_mode), (C.c_float * 4)(*[float(x) for x in shift]), float(norm_hw[0]), float(norm_hw[1]),
+                     float(scale_hw[0]), float(scale_hw[1]))
+    D = int(max_output_size)
+    keep = np.empty(A, np.int32); probs = np.empty((A, K), np.float32); corners = np.empty((A, 4), np.float32)
+    scores = np.empty(A, np.float32); sel = np.empty(max(D, 1), np.int32); ss = np.empty(max(D, 1), np.float32)
+    oc = np.zeros((max(D, 1), K), np.float32); ob = np.zeros((max(D, 1), 4), np.float32)
+    nd = C.c_int32(0)
+    S = lib().orc_val_postprocess(_p(cls), _p(box), _p(anchors), A, K, D, C.c_float(iou_threshold),
+                                  C.c_float(soft_nms_sigma), C.byref(sc), _p(keep), _p(probs), _p(corners), _p(scores),
+                                  _p(sel), _p(ss), _p(oc), _p(ob), C.byref(nd))
+    d = nd.value
+    return ValResult(keep[:S].copy(), probs[:S].copy(), corners[:S].copy(), scores[:S].copy(), sel[:d].copy(),
+                     ss[:d].copy(), oc[:d].copy(), ob[:d].copy())
+
+
 def run_batch(cfg: OracleConfig, cls, box, cov, anchors, counts=None, nthreads=1):
     """Whole path for [B,...] inputs, padded outputs (CPU baseline arm)."""
     cls = _f(cls); B, N, A, K = cls.shape

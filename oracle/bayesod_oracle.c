@@ -733,6 +733,79 @@ int ORC(clustering)(const R* cnt, const R* mu, const R* sig, int S, int K,
 /* ------------------------------------------------------------------------- */
 /* EXTENSIONS: score threshold + pre-NMS top-k on the keep list */
 /* ------------------------------------------------------------------------- */
+/* Validation post-process: validation_utils.post_process_predictions          */
+/* (src/retina_net/experiments/validation_utils.py:10-77), one image, N = 1.   */
+/*   :22-26   box_from_anchor_and_target (box_utils.py:149-168) for EVERY anchor */
+/*   :28      vuhw_to_vuvu (box_utils.py:5-23)                                   */
+/*   :29-30   softmax over the K logits                                          */
+/*   :34-43   argmax != K-1 (first maximum) + boolean_mask (ascending order)     */
+/*   :45      top score = max probability                                        */
+/*   :47-52   the same NonMaxSuppressionV5 call (100, 0.5, sigma 0.5)            */
+/*   :54-66   kitti: (corners / [h,w,h,w]) * [H0,W0,H0,W0]; coco: shift first    */
+/*   :68-73   gather classes and (scaled) corners of the selected boxes          */
+/* scale_mode: 0 none (bdd), 1 kitti, 2 coco.  Outputs: keep [S] anchor indices, */
+/* probs [S,K], corners [S,4] (unscaled, what NMS sees), scores [S], then        */
+/* sel [D], sel_scores [D], out_classes [D,K], out_corners [D,4].  Returns S;    */
+/* *D_out receives D.  Buffers are sized for A survivors / max_output_size rows. */
+/* ------------------------------------------------------------------------- */
+typedef struct orc_val_scaling {
+    int32_t mode;            /* 0 none, 1 kitti, 2 coco */
+    float shift[4];          /* coco: IMAGE_PADDING_KEY[0], subtracted from the corners */
+    float norm_h, norm_w;    /* normalize_2d_bounding_boxes (box_utils.py:195-205) */
+    float scale_h, scale_w;  /* expand_2d_bounding_boxes (box_utils.py:208-220)    */
+} orc_val_scaling;
+
+int orc_val_postprocess(const float* cls, const float* box, const float* anchors, int A, int K,
+                        int max_output_size, float iou_threshold, float soft_nms_sigma,
+                        const orc_val_scaling* sc,
+                        int32_t* keep, float* probs, float* corners, float* scores,
+                        int32_t* sel, float* sel_scores, float* out_classes, float* out_corners, int32_t* D_out) {
+    int S = 0;
+    float* e = (float*)malloc(sizeof(float) * (size_t)K);
+    for (int a = 0; a < A; ++a) {
+        const float* x = cls + (size_t)a * K;
+        float m = x[0];
+        for (int k = 1; k < K; ++k) m = r_max(m, x[k]);
+        float sum = 0.0f;
+        for (int k = 0; k < K; ++k) { e[k] = r_exp(x[k] - m); sum = sum + e[k]; }
+        int am = 0;
+        float best = e[0] / sum;
+        for (int k = 0; k < K; ++k) { e[k] = e[k] / sum; if (e[k] > best) { best = e[k]; am = k; } }
+        if (am == K - 1) continue;
+        keep[S] = a;
+        for (int k = 0; k < K; ++k) probs[(size_t)S * K + k] = e[k];
+        scores[S] = best;
+        const float* an = anchors + (size_t)a * 4;
+        const float* t = box + (size_t)a * 4;
+        const float v = an[2] * t[0] / 10.0f + an[0];
+        const float u = an[3] * t[1] / 10.0f + an[1];
+        const float h = an[2] * r_min(r_max(r_exp(t[2] / 5.0f), 1e-4f), 1e4f);
+        const float w = an[3] * r_min(r_max(r_exp(t[3] / 5.0f), 1e-4f), 1e4f);
+        float* c = corners + (size_t)S * 4;
+        c[0] = v - h / 2.0f; c[1] = u - w / 2.0f; c[2] = v + h / 2.0f; c[3] = u + w / 2.0f;
+        ++S;
+    }
+    free(e);
+    for (int d = 0; d < max_output_size; ++d) sel[d] = -1;
+    const int D = orc32_nms_v5(corners, scores, S, max_output_size, iou_threshold, -INFINITY, soft_nms_sigma, sel, sel_scores, NULL);
+    for (int d = 0; d < D; ++d) {
+        const int s = sel[d];
+        for (int k = 0; k < K; ++k) out_classes[(size_t)d * K + k] = probs[(size_t)s * K + k];
+        for (int i = 0; i < 4; ++i) {
+            float c = corners[(size_t)s * 4 + i];
+            if (sc && sc->mode == 2) c = c - sc->shift[i];
+            if (sc && sc->mode != 0) {
+                c = c / ((i & 1) ? sc->norm_w : sc->norm_h);
+                c = c * ((i & 1) ? sc->scale_w : sc->scale_h);
+            }
+            out_corners[(size_t)d * 4 + i] = c;
+        }
+    }
+    *D_out = D;
+    return S;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Ranking score from counts alone ('score' ranking): max_k (c_k+alpha)/sum. */
 static float count_score(const float* c, int K, int dirichlet) {
     const float alpha = 1.0f / (float)K;

@@ -125,10 +125,51 @@ def run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical):
     print(f"{name:16s} A={len(anchors)} S={S} D={D} members(min/max)={min(members, default=0)}/{max(members, default=0)}")
 
 
+VAL_CASES = {
+    # validation_utils.post_process_predictions (validation_utils.py:10-77): name -> (SceneSpec kwargs, overrides)
+    "val_bdd_k8":   (dict(im_h=96, im_w=160, N=2, K=8, g_min=4, g_max=6, box_hi=90., config_id=21), {}),
+    "val_kitti_k4": (dict(im_h=64, im_w=128, N=2, K=4, g_min=3, g_max=5, box_hi=60., config_id=22),
+                     dict(dataset_name='kitti', orig_size=(47, 94))),
+    "val_none_k8":  (dict(im_h=64, im_w=96, N=2, K=8, g_min=3, g_max=4, box_hi=60., config_id=23), dict(all_background=True)),
+}
+
+
+def run_val_case(name, spec_kw, ov, vu, ag, cs):
+    spec = synthetic.SceneSpec(**spec_kw)
+    gen = ag.FpnAnchorGenerator(dict(aspect_ratios=[[1.0, 1.0], [1.0, 2.0], [2.0, 1.0]], scales=[1.0, 1.26, 1.59]))
+    image_norm = np.zeros((spec.im_h, spec.im_w, 3), np.float32)
+    anchors = np.concatenate([np.asarray(gen.generate_anchors(shim._t(np.asarray(image_norm.shape, np.int32)), l))
+                              for l in [3, 4, 5, 6, 7]], axis=0).astype(np.float32)
+    img = synthetic.make_image(spec, 0, torch.from_numpy(anchors), "cpu", with_counts=False)
+    cls16, box16 = f16_exact(img["cls"][0]), f16_exact(img["box"][0])          # one sample: validation runs without dropout
+    if ov.get("all_background"):
+        cls16 = cls16.copy(); cls16[:, -1] = np.float16(20.0)
+    cls, box = cls16.astype(np.float32), box16.astype(np.float32)
+    dataset_name = ov.get("dataset_name", "bdd")
+    orig = ov.get("orig_size", (spec.im_h, spec.im_w))
+    pred = {cs.ANCHORS_CLASS_PREDICTIONS_KEY: shim._t(cls[None]), cs.ANCHORS_BOX_PREDICTIONS_KEY: shim._t(box[None])}
+    sample_dict = {cs.IMAGE_NORMALIZED_KEY: shim._t(image_norm[None]), cs.ANCHORS_KEY: shim._t(anchors[None]),
+                   cs.ORIGINAL_IM_SIZE_KEY: shim._t(np.asarray([[orig[0], orig[1], 3]], np.int32))}
+    classes_out, corners_out = vu.post_process_predictions(sample_dict, pred, dataset_name=dataset_name)
+    classes_out, corners_out = np.asarray(classes_out, np.float32), np.asarray(corners_out, np.float32)
+    meta = dict(case=name, spec=spec_kw, dataset_name=dataset_name, orig_size=list(orig), image_shape=[spec.im_h, spec.im_w],
+                numpy=np.__version__, generator="tests/golden/make_golden.py over tf_numpy_shim; "
+                "validation_utils.post_process_predictions executed verbatim")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), anchors=anchors, cls=cls16, box=box16,
+                        classes_out=classes_out.reshape(-1, spec.K), corners_out=corners_out.reshape(-1, 4))
+    print(f"{name:16s} A={len(anchors)} D={len(classes_out)}")
+
+
 def main():
     iu, bu, ag, cs, Categorical = shim.load_reference()
-    for name, (spec_kw, ov) in CASES.items():
-        run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical)
+    only_val = "--val-only" in sys.argv
+    if not only_val:
+        for name, (spec_kw, ov) in CASES.items():
+            run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical)
+    import importlib
+    vu = importlib.import_module("src.retina_net.experiments.validation_utils")
+    for name, (spec_kw, ov) in VAL_CASES.items():
+        run_val_case(name, spec_kw, ov, vu, ag, cs)
 
 
 if __name__ == "__main__":

@@ -14,8 +14,25 @@ GOLDEN_DIR = os.path.join(HERE, "golden")
 RTOL, ATOL = 1e-4, 1e-5
 
 
-def golden_cases():
+def _all_cases():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_cases():
+    """Fixtures of bayes_od_inference / bayes_od_clustering (inference_utils.py)."""
+    return [c for c in _all_cases() if not c.startswith("val_")]
+
+
+def val_golden_cases():
+    """Fixtures of validation_utils.post_process_predictions."""
+    return [c for c in _all_cases() if c.startswith("val_")]
+
+
+def val_scaling_of(meta):
+    """(scale_mode, norm_hw, scale_hw) as validation_utils.py:54-66 derives them."""
+    if meta["dataset_name"] == "kitti":
+        return 1, tuple(float(x) for x in meta["image_shape"]), tuple(float(x) for x in meta["orig_size"])
+    return 0, (1.0, 1.0), (1.0, 1.0)
 
 
 def load_golden(name):
@@ -24,8 +41,9 @@ def load_golden(name):
     g["meta"] = json.loads(str(g["meta"]))
     g["cls"] = g["cls"].astype(np.float32)
     g["box"] = g["box"].astype(np.float32)
-    g["cov"] = g["cov"].astype(np.float32)
-    g["counts"] = g["counts"].astype(np.float32)
+    for k in ("cov", "counts"):
+        if k in g:
+            g[k] = g[k].astype(np.float32)
     return g
 
 

@@ -9,7 +9,7 @@ from bayes_od_rc_b200 import anchors as anchors_mod
 from bayes_od_rc_b200 import synthetic
 from gpu_common import assert_bit_equal, compare_image_with_oracle, run_gpu_batch
 from helpers import (adjudicated_close, check_categorical_merge, golden_cases, load_golden, oracle_config_of,
-                     within_tol)
+                     val_golden_cases, val_scaling_of, within_tol)
 
 pytestmark = pytest.mark.gpu
 
@@ -377,3 +377,91 @@ def test_dropin_inference_utils(name):
             fast.bayes_od_clustering(counts, means, covs, nms_indices, iou_mat, affinity_threshold=0.7)
     else:
         assert nms_indices.size == 0
+
+
+# --------------------------------------------------------------------------
+# validation post-process (validation_utils.post_process_predictions)
+# --------------------------------------------------------------------------
+def _run_validate(cls, box, anchors, scaling=None, **cfg_kw):
+    """cls [B,A,K], box [B,A,4] numpy -> (engine, results)."""
+    import torch
+    from bayes_od_rc_b200.engine import BayesODConfig, BayesODEngine
+    B, A, K = cls.shape
+    eng = BayesODEngine(B, 1, A, K, BayesODConfig(**cfg_kw))
+    t = [torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda() for x in (cls, box, anchors)]
+    torch.cuda.synchronize()
+    eng.validate(*t, scaling=scaling, stream=torch.cuda.current_stream().cuda_stream)
+    return eng, eng.fetch()
+
+
+def _compare_validate(eng, res, b, r, K):
+    S, D = len(r.keep), len(r.nms_indices)
+    assert int(res.num_survivors[b]) == S and int(res.num_dets[b]) == D
+    sv = eng.survivors(b)
+    assert_bit_equal(sv["anchor_idx"], r.keep, "kept anchors")
+    assert_bit_equal(sv["counts"], r.probs, "softmax rows")
+    assert_bit_equal(sv["corners"], r.corners, "corners")
+    assert_bit_equal(sv["scores"], r.scores, "top scores")
+    assert_bit_equal(res.nms_indices[b, :D], r.nms_indices, "nms_indices")
+    assert_bit_equal(res.centre_scores[b, :D], r.nms_scores, "scores at selection")
+    assert_bit_equal(res.cat_param[b, :D], r.classes_out, "classes_out")
+    assert_bit_equal(res.means[b, :D], r.corners_out, "corners_out")
+    assert not res.cat_param[b, D:].any() and not res.means[b, D:].any() and not res.covs[b].any()
+
+
+@pytest.mark.parametrize("name", val_golden_cases())
+def test_validation_golden(name):
+    g = load_golden(name)
+    mode, norm_hw, scale_hw = val_scaling_of(g["meta"])
+    eng, res = _run_validate(g["cls"][None], g["box"][None], g["anchors"],
+                             scaling=None if mode == 0 else (mode, (0, 0, 0, 0), norm_hw, scale_hw))
+    r = oracle.val_postprocess(g["cls"], g["box"], g["anchors"], scale_mode=mode, norm_hw=norm_hw, scale_hw=scale_hw)
+    _compare_validate(eng, res, 0, r, g["cls"].shape[1])
+    D = len(g["classes_out"])                      # and against the reference's own function
+    assert int(res.num_dets[0]) == D
+    if D:
+        assert within_tol(res.cat_param[0, :D], g["classes_out"]).all()
+        assert within_tol(res.means[0, :D], g["corners_out"], rtol=1e-5, atol=1e-4).all()
+
+
+@pytest.mark.parametrize("case", ["bdd_k8", "kitti_k4", "coco_k11", "hard_nms"])
+def test_validation_batch_bit_exact(case):
+    kw = dict(bdd_k8=dict(im_h=192, im_w=320, N=2, K=8, g_min=6, g_max=10, box_hi=150., config_id=71),
+              kitti_k4=dict(im_h=128, im_w=424, N=2, K=4, g_min=5, g_max=9, box_hi=120., config_id=72),
+              coco_k11=dict(im_h=160, im_w=160, N=2, K=11, g_min=5, g_max=9, box_hi=120., config_id=73),
+              hard_nms=dict(im_h=96, im_w=160, N=2, K=8, g_min=4, g_max=6, box_hi=90., config_id=74))[case]
+    spec = synthetic.SceneSpec(**kw)
+    B = 3
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, B, with_counts=False))
+    cls, box = batch["cls"][:, 0], batch["box"][:, 0]
+    scaling, okw, ckw = None, {}, {}
+    if case == "kitti_k4":
+        scaling = (1, (0, 0, 0, 0), (128., 424.), (94., 311.)); okw = dict(scale_mode=1, norm_hw=(128., 424.), scale_hw=(94., 311.))
+    if case == "coco_k11":
+        scaling = (2, (8., 0., 8., 0.), (144., 160.), (480., 533.))
+        okw = dict(scale_mode=2, shift=(8., 0., 8., 0.), norm_hw=(144., 160.), scale_hw=(480., 533.))
+    if case == "hard_nms":
+        ckw = dict(soft_nms_sigma=0.0, max_output_size=50); okw = dict(soft_nms_sigma=0.0, max_output_size=50)
+    eng, res = _run_validate(cls, box, batch["anchors"], scaling=scaling, **ckw)
+    for b in range(B):
+        r = oracle.val_postprocess(cls[b], box[b], batch["anchors"], **okw)
+        assert len(r.keep) > 10
+        _compare_validate(eng, res, b, r, spec.K)
+
+
+def test_validation_dropin():
+    """bayes_od_rc_b200.validation_utils.post_process_predictions driven the way run_validation.py:143-147 does."""
+    import torch
+    from bayes_od_rc_b200 import validation_utils as fast
+    g = load_golden("val_kitti_k4")
+    meta = g["meta"]
+    pred = {fast.ANCHORS_CLASS_PREDICTIONS_KEY: torch.from_numpy(g["cls"][None]).cuda(),
+            fast.ANCHORS_BOX_PREDICTIONS_KEY: torch.from_numpy(g["box"][None]).cuda()}
+    h, w = meta["image_shape"]
+    sample_dict = {fast.IMAGE_NORMALIZED_KEY: np.zeros((1, h, w, 3), np.float32), fast.ANCHORS_KEY: g["anchors"][None],
+                   fast.ORIGINAL_IM_SIZE_KEY: np.asarray([[meta["orig_size"][0], meta["orig_size"][1], 3]], np.int32)}
+    output_classes, output_boxes = fast.post_process_predictions(sample_dict, pred, dataset_name=meta["dataset_name"])
+    output_boxes = output_boxes.numpy(); output_classes = output_classes.numpy()       # run_validation.py:146-147
+    assert output_classes.shape == g["classes_out"].shape and output_boxes.shape == g["corners_out"].shape
+    assert within_tol(output_classes, g["classes_out"]).all()
+    assert within_tol(output_boxes, g["corners_out"], rtol=1e-5, atol=1e-4).all()

@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 from helpers import (adjudicated_close, check_categorical_merge, golden_cases, load_golden, oracle_config_of,
-                     within_tol)
+                     val_golden_cases, val_scaling_of, within_tol)
 
 CASES = golden_cases()
 
@@ -101,3 +101,26 @@ def test_stage_isolated_nms_and_clustering(name):
     fs64, fm64, fc64, *_ = oracle.clustering(g["cnt_post"], mu, g["sig_post"], sel, mask, 70.0, real="f64")
     ok, frac = adjudicated_close(fc, g["final_covs"], fc64)
     assert ok.all() and frac > 0.99
+
+
+@pytest.mark.parametrize("name", val_golden_cases())
+def test_validation_postprocess(name):
+    """validation_utils.post_process_predictions (validation_utils.py:10-77), executed verbatim over the shim,
+    against the oracle restatement: same boxes selected in the same order, values within tolerance."""
+    g = load_golden(name)
+    mode, norm_hw, scale_hw = val_scaling_of(g["meta"])
+    r = oracle.val_postprocess(g["cls"], g["box"], g["anchors"], scale_mode=mode, norm_hw=norm_hw, scale_hw=scale_hw)
+    D = len(g["classes_out"])
+    assert len(r.nms_indices) == D
+    if D == 0:
+        assert len(r.keep) == 0
+        return
+    assert within_tol(r.classes_out, g["classes_out"]).all()
+    assert within_tol(r.corners_out, g["corners_out"], rtol=1e-5, atol=1e-4).all()
+    # kept anchors = softmax arg-max is not the background column (float-independent here: margins are large)
+    keep = np.flatnonzero(np.argmax(g["cls"], axis=1) != g["cls"].shape[1] - 1)
+    assert np.array_equal(r.keep, keep)
+
+
+def test_validation_fixtures_present():
+    assert len(val_golden_cases()) >= 3
