@@ -33,6 +33,7 @@ struct Lane {
     // K4 outputs
     float* out_means = nullptr; float* out_covs = nullptr; float* out_param = nullptr; float* out_count = nullptr;
     cudaEvent_t head_done = nullptr, tail_done = nullptr;
+    cudaStream_t tail_stream = nullptr;   // the lane's own tail stream: tails of different lanes run concurrently
     bool tail_pending = false;        // a tail has been issued on this lane (tail_done is meaningful)
 };
 
@@ -44,7 +45,8 @@ struct bod_ctx {
     // one slab of device memory, carved up below
     unsigned char* slab = nullptr;
     size_t slab_bytes = 0;
-    Lane lane[2];
+    static constexpr int kMaxLanes = 8;
+    Lane lane[kMaxLanes];
     int nlanes = 1, cur = 0;          // cur: lane of the last issued run
     int32_t* status = nullptr;
     // pre-NMS filter (only with score_threshold / pre_nms_top_k): key scratch [B,A], threshold keys [B], and the
@@ -58,7 +60,7 @@ struct bod_ctx {
     int fastS = 0, pstride = 0, pw_rows = 0, k3_smem_S = 0, k3_rows = 0;
     // device staging of host inputs (bod_run_host), allocated on first use
     float* in_cls = nullptr; float* in_box = nullptr; float* in_cov = nullptr; float* in_anchors = nullptr; float* in_counts = nullptr;
-    cudaStream_t own_stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     cudaStream_t last_stream = nullptr;
     cudaEvent_t ev_in = nullptr;
     // stage-timing events: a ring of the last kEvRing runs, 7 events each
@@ -148,7 +150,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     const size_t cap = (size_t)c->capacity, D = (size_t)c->Dmax;
 
     // carve the slab
-    c->nlanes = (cfg->pipeline_depth >= 2) ? 2 : 1;
+    c->nlanes = cfg->pipeline_depth < 1 ? 1 : (cfg->pipeline_depth > bod_ctx::kMaxLanes ? bod_ctx::kMaxLanes : cfg->pipeline_depth);
     c->fastS = k3_fast_capacity(c->capacity);
     c->pstride = (c->Dmax + 3) & ~3;
     c->pw_rows = c->capacity < 65535 ? c->capacity : 65535;
@@ -215,7 +217,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     {
         int lo = 0, hi = 0;                                  // the tail is latency-bound and short: let its CTAs go first
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, hi);
+        for (int l = 0; l < c->nlanes; ++l) cudaStreamCreateWithPriority(&c->lane[l].tail_stream, cudaStreamNonBlocking, hi);
     }
     cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
     for (int l = 0; l < c->nlanes; ++l) {
@@ -244,7 +246,7 @@ extern "C" void bod_destroy(bod_ctx* c) {
     for (float* p : {c->in_cls, c->in_box, c->in_cov, c->in_anchors, c->in_counts}) if (p) cudaFree(p);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
+    for (auto& L : c->lane) if (L.tail_stream) cudaStreamDestroy(L.tail_stream);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     for (auto& L : c->lane) { if (L.head_done) cudaEventDestroy(L.head_done); if (L.tail_done) cudaEventDestroy(L.tail_done); }
     for (auto& set : c->evring) for (auto& ev : set) if (ev) cudaEventDestroy(ev);
@@ -361,6 +363,13 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
     return BOD_OK;
 }
 
+// wait for every tail in flight (pipelined contexts) before a synchronous entry reuses lane 0
+static int drain_tails(bod_ctx* c) {
+    if (c->nlanes > 1)
+        for (int l = 0; l < c->nlanes; ++l) CU(c, cudaStreamSynchronize(c->lane[l].tail_stream));
+    return BOD_OK;
+}
+
 static int check_inputs(bod_ctx* c, const float* cls, const float* box, const float* cov, const float* anchors) {
     if (!c) return BOD_ERR_INVALID;
     if (!cls || !box) return fail(c, BOD_ERR_INVALID, "cls and box must not be NULL");
@@ -390,14 +399,14 @@ extern "C" int bod_run(bod_ctx* c, const float* cls, const float* box, const flo
         // pipelined: the head runs on the context's own stream once the caller's stream has reached this
         // point; the tail floats on a second stream.  The caller's stream only waits for the head (the
         // last reader of the inputs); results are complete at bod_fetch / bod_wait_results.
-        c->cur ^= 1;
+        c->cur = (c->cur + 1) % c->nlanes;
         Lane& L = c->lane[c->cur];
         CU(c, cudaEventRecord(c->ev_in, st));
         CU(c, cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
-        rc = run_range(c, L, 0, c->cfg.B, cls, box, cov, anchors, counts, c->own_stream, c->tail_stream, c->timing);
+        rc = run_range(c, L, 0, c->cfg.B, cls, box, cov, anchors, counts, c->own_stream, L.tail_stream, c->timing);
         if (rc) return rc;
         CU(c, cudaStreamWaitEvent(st, L.head_done, 0));
-        c->last_stream = c->tail_stream;
+        c->last_stream = L.tail_stream;
     }
     if (c->timing) ++c->runs_recorded;
     c->last_timed = c->timing;
@@ -415,7 +424,7 @@ extern "C" int bod_validate_run(bod_ctx* c, const float* cls, const float* box, 
     if (scaling && (scaling->mode < 0 || scaling->mode > 2)) return fail(c, BOD_ERR_INVALID, "bad scaling mode");
     CU(c, cudaSetDevice(c->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-    if (c->nlanes > 1) CU(c, cudaStreamSynchronize(c->tail_stream));    // drain pipelined runs first
+    { int rc0 = drain_tails(c); if (rc0) return rc0; }                  // drain pipelined runs first
     c->cur = 0;
     Lane& L = c->lane[0];
     const bod_config& g = c->cfg;
@@ -613,6 +622,7 @@ extern "C" int bod_stage_ms_accum(bod_ctx* c, float sum_ms[6], int32_t* runs) {
     if (c->runs_recorded == c->runs_reported) return BOD_OK;
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->last_stream));
+    { int rc0 = drain_tails(c); if (rc0) return rc0; }      // earlier runs' tails live on other streams
     long long first = c->runs_reported;
     if (c->runs_recorded - first > bod_ctx::kEvRing) first = c->runs_recorded - bod_ctx::kEvRing;
     for (long long r = first; r < c->runs_recorded; ++r) {
@@ -666,7 +676,7 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
     if (!box_m && !c->in_box) CU(c, cudaMalloc(&c->in_box, B * N * A * 16));
     if (cw && !cov_m && !c->in_cov) CU(c, cudaMalloc(&c->in_cov, B * N * A * cw * 4));
     cudaStream_t cs = c->copy_stream, st = c->own_stream;
-    if (c->nlanes > 1) CU(c, cudaStreamSynchronize(c->tail_stream));    // drain pipelined runs; this entry is synchronous
+    { int rc0 = drain_tails(c); if (rc0) return rc0; }                  // drain pipelined runs; this entry is synchronous
     c->cur = 0;
     Lane& L = c->lane[0];
     c->launches = 0;
@@ -749,7 +759,7 @@ extern "C" int bod_cluster_host(bod_ctx* c, int32_t S, const float* counts, cons
         if (centres[d] < 0 || centres[d] >= S) return fail(c, BOD_ERR_INVALID, "bod_cluster_host: centre index out of range");
     CU(c, cudaSetDevice(c->device));
     cudaStream_t st = c->own_stream;
-    if (c->nlanes > 1) CU(c, cudaStreamSynchronize(c->tail_stream));
+    { int rc0 = drain_tails(c); if (rc0) return rc0; }
     c->cur = 0;
     Lane& L = c->lane[0];
     const size_t K = c->cfg.K, Dm = c->Dmax;

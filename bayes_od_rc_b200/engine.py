@@ -241,7 +241,10 @@ class BayesODEngine:
         p_cov = device_ptr(cov, B * N * A * self.cov_width, keep) if self.cov_width else None
         p_anc = device_ptr(anchors, A * 4, keep) if self.config.anchor_mode == _cabi.ANCHORS_TENSOR else None
         p_cnt = device_ptr(counts, B * A * K, keep) if counts is not None else None
-        self._keep = (cls, box, cov, anchors, counts, keep)          # keep the buffers alive until fetch
+        # keep the buffers alive while any run that reads them may be in flight (one per lane)
+        self._keeps = getattr(self, "_keeps", [])
+        self._keeps.append((cls, box, cov, anchors, counts, keep))
+        del self._keeps[:-max(1, int(self.config.pipeline_depth))]
         self._check(self.lib.bod_run(self._ctx, p_cls, p_box, p_cov, p_anc, p_cnt, C.c_void_p(int(stream) or None)))
 
     def validate(self, cls, box, anchors, scaling=None, stream=0):

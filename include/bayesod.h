@@ -88,12 +88,14 @@ typedef struct bod_config {
     int32_t  max_survivors;      /* per-image survivor capacity; 0 => A                    */
     int32_t  emit_probs;         /* keep the [B,A,K] mean class probabilities (parity)     */
     int32_t  pipeline_depth;     /* 0/1: every bod_run is issued whole, in order, on the
-                                    caller's stream.  2: two sets of buffers; run i+1 streams
-                                    its logits (K1, scan, K2) while run i is still selecting
-                                    centres and fusing (soft-NMS, K4) on a second internal
-                                    stream.  The caller's stream then only waits for the
-                                    part that reads the inputs; results are complete at
-                                    bod_fetch or after bod_wait_results                      */
+                                    caller's stream.  L = 2..8: L sets of buffers (lanes);
+                                    run i+1 streams its logits (K1, scan, K2) on the context's
+                                    own stream while runs i, i-1, .. are still selecting centres
+                                    and fusing (soft-NMS, K4), each on its lane's own stream.
+                                    2 is enough once a batch fills the GPU (soft-NMS holds one
+                                    SM per image); small batches want more lanes.  The caller's
+                                    stream then only waits for the part that reads the inputs;
+                                    results are complete at bod_fetch or after bod_wait_results */
 } bod_config;
 
 typedef struct bod_ctx bod_ctx;
@@ -116,7 +118,7 @@ typedef struct bod_host_results {
 } bod_host_results;
 
 /* The same blocks as device pointers (valid until the next bod_run on ctx; with
- * pipeline_depth = 2 until the run after the next),
+ * pipeline_depth = L for the next L-1 runs),
  * for consumers that stay on the GPU (e.g. an NCCL all-gather of detections). */
 typedef struct bod_device_results {
     const int32_t* num_dets;
@@ -170,7 +172,7 @@ int bod_run(bod_ctx* ctx, const float* cls, const float* box, const float* cov,
             const float* anchors, const float* counts, void* cuda_stream);
 
 /* Make `cuda_stream` wait (on the device, without blocking the host) until the
- * results of the last bod_run are complete.  Only needed with pipeline_depth = 2
+ * results of the last bod_run are complete.  Only needed with pipeline_depth >= 2
  * by consumers that read bod_device_results_of on their own stream; a no-op
  * otherwise (the run is already ordered on the caller's stream). */
 int bod_wait_results(bod_ctx* ctx, void* cuda_stream);

@@ -209,20 +209,21 @@ def test_batch_composition_independence():
             assert_bit_equal(getattr(res1, k)[0], getattr(res4, k)[b], k)
 
 
-def test_pipelined_runs_equal_serial_runs():
-    """pipeline_depth = 2: run i+1's head overlaps run i's tail on a second set of buffers.  A stream of
+@pytest.mark.parametrize("depth", [2, 3, 8])
+def test_pipelined_runs_equal_serial_runs(depth):
+    """pipeline_depth >= 2: run i+1's head overlaps run i's tail on a second set of buffers.  A stream of
     different batches through one pipelined context gives the same bits as serial contexts, the last
     result is the one fetched, and device results of run i survive the issue of run i+1."""
     import torch
     from gpu_common import engine_config_from_oracle
     from bayes_od_rc_b200.engine import BayesODEngine
     spec = synthetic.SceneSpec(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=45)
-    B, rounds = 3, 5
+    B, rounds = 3, 11
     oc = oracle.OracleConfig()
     batches = [synthetic.to_numpy(synthetic.make_batch(spec, B, first_image_id=100 * i)) for i in range(rounds)]
     serial = [run_gpu_batch(oc, b["cls"], b["box"], b["cov"], b["anchors"], b["counts"], emit_probs=False)[1] for b in batches]
     N, A, K = batches[0]["cls"].shape[1:]
-    eng = BayesODEngine(B, N, A, K, engine_config_from_oracle(oc, pipeline_depth=2))
+    eng = BayesODEngine(B, N, A, K, engine_config_from_oracle(oc, pipeline_depth=depth))
     dev = [{k: torch.from_numpy(b[k]).cuda() for k in ("cls", "box", "cov", "anchors", "counts")} for b in batches]
     torch.cuda.synchronize()
     st = torch.cuda.Stream()
