@@ -212,6 +212,7 @@ struct K3Smem {
     float4 sel_box[kMaxOut];
     unsigned long long cand_key[kTop];           // the round's examined candidates ...
     float4 cand_box[kTop];
+    float4 batch_ebox[kBatch];                   // the round's centres grown by 2 px: pass A's lean overlap test
     float wpair[kTop][kTop];                     // ... their pairwise soft-NMS weights [q][i], i < q
     uint32_t rowmask[kTop];                      // bit i of row q: wpair[q][i] != 1
     double exp_tab[kExpTab];                     // exp(-k/64)
@@ -311,36 +312,48 @@ BOD_DEVINL float pend_product(const K3State& C, int s, int n, float st) {
     return v;
 }
 
-// Epoch walk of one QUEUED candidate s over the round's batch (selections r0 .. r0+m-1).  weight_of(q)
-// returns the candidate's soft-NMS weight against centre q of the batch (1 for centres it does not
-// overlap).  Returns the candidate's new up-to-date score (-inf: removed by hard-NMS).
-template <typename WeightOf>
-BOD_DEVINL float k3_walk(const K3State& C, const K3Smem& sm, const int r0, const int m, const int s, WeightOf weight_of) {
-    float st = C.stl[s];
-    int n = C.npend[s];
-    const int n_in = n;
-    bool folded = false;
-    unsigned long long ks = make_key(st, s);
-    for (int q = 0; q < m; ++q) {
-        if (n > 0 && ks > sm.sel_key[r0 + q]) {            // TF pops s right before selection r0+q: fold, newest first
-            st = pend_product(C, s, n, st);
-            n = 0; folded = true;
-            ks = make_key(st, s);
-        }
-        const float w = weight_of(q);
+// Epoch walk of one QUEUED candidate s over the round's batch (selections r0 .. r0+m-1), driven by the
+// candidate's listed pairs in ascending centre order: step(q, w) for every batch centre q it overlaps
+// (w = its soft-NMS weight against that centre), then finish().  TF pops s right before selection j iff
+// it has pending weights and key(stale) > key(selection j); between two of its pairs the pending list
+// does not change and the selection keys decrease, so such a pop exists in (q_prev, q] iff
+// key(stale) > key(selection q), and wherever it happens it folds the same list.
+struct K3Walk {
+    float st;
+    int n, n_in, last_q;
+    bool folded, dead;
+    unsigned long long ks;
+    BOD_DEVINL void begin(const K3State& C, int s) {
+        st = C.stl[s]; n = C.npend[s]; n_in = n; last_q = -1; folded = false; dead = false;
+        ks = make_key(st, s);
+    }
+    BOD_DEVINL void fold(const K3State& C, int s) {        // newest first
+        st = pend_product(C, s, n, st);
+        n = 0; folded = true;
+        ks = make_key(st, s);
+    }
+    BOD_DEVINL void step(const K3State& C, const K3Smem& sm, int r0, int s, int q, float w) {
+        if (dead) return;
+        if (n > 0 && ks > sm.sel_key[r0 + q]) fold(C, s);
+        last_q = q;
         if (w != 1.0f) {
-            if (!C.is_soft && w == 0.0f) { C.ucur[s] = -INFINITY; return -INFINITY; }   // hard-NMS: removed for good
+            if (!C.is_soft && w == 0.0f) { dead = true; return; }           // hard-NMS: removed for good
             pend_put(C, s, n, w);
             ++n;
         }
     }
-    if (!folded && n == n_in) return C.ucur[s];            // every weight was exactly 1: untouched
-    const float u = pend_product(C, s, n, st);
-    C.ucur[s] = u;
-    C.npend[s] = (uint8_t)n;
-    if (folded) C.stl[s] = st;
-    return u;
-}
+    // returns the candidate's new up-to-date score (-inf: removed by hard-NMS)
+    BOD_DEVINL float finish(const K3State& C, const K3Smem& sm, int r0, int m, int s) {
+        if (dead) { C.ucur[s] = -INFINITY; return -INFINITY; }
+        if (last_q < m - 1 && n > 0 && ks > sm.sel_key[r0 + m - 1]) fold(C, s);   // popped before a later selection of the batch
+        if (!folded && n == n_in) return C.ucur[s];        // every weight was exactly 1: untouched
+        const float u = pend_product(C, s, n, st);
+        C.ucur[s] = u;
+        C.npend[s] = (uint8_t)n;
+        if (folded) C.stl[s] = st;
+        return u;
+    }
+};
 
 // A whole candidate in place (only when a warp's list segment is full): membership bits and, if the
 // candidate is queued, its walk with the weights computed on the fly.
@@ -354,10 +367,13 @@ __device__ __noinline__ float k3_process_inplace(const K3State* Cp, const K3Smem
             atomicOr(&C.member[(size_t)(r0 + q) * C.words + (s >> 5)], 1u << (s & 31));
     }
     if (!queued) return -INFINITY;
-    return k3_walk(C, sm, r0, m, s, [&](int q) {
-        if (!((mask >> q) & 1u)) return 1.0f;
-        return nms_weight_fast(tf_iou(bs, sm.sel_box[r0 + q]), C.scale, C.is_soft, C.thr, sm.exp_tab);
-    });
+    K3Walk wk;
+    wk.begin(C, s);
+    for (uint32_t rem = mask; rem; rem &= rem - 1) {
+        const int q = __ffs(rem) - 1;
+        wk.step(C, sm, r0, s, q, nms_weight_fast(tf_iou(bs, sm.sel_box[r0 + q]), C.scale, C.is_soft, C.thr, sm.exp_tab));
+    }
+    return wk.finish(C, sm, r0, m, s);
 }
 
 // Warp-level merge of the lanes' Top2 pairs: every lane returns with the warp's best keys in out[]
@@ -441,7 +457,10 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
     for (int s = tid; s < S; s += kK3Threads) {
         const float4 c = corners[s];
         if (!big) corn[s] = c;
-        if (!((c.x <= c.z) && (c.y <= c.w))) sm.malformed = 1;          // needs the canonicalising IoU path every round
+        // corners out of order need the canonicalising IoU path for every pair; so do coordinates so large
+        // that the 2 px margin of pass A's lean test is not safely above their rounding
+        if (!((c.x <= c.z) && (c.y <= c.w)) || !(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))) < 1.0e5f))
+            sm.malformed = 1;
         const float sc = score[s];
         const bool queued = sc > -INFINITY;                              // scores_data[i] > score_threshold (-inf); NaN stays out
         ucur[s] = queued ? sc : -INFINITY;
@@ -500,11 +519,25 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
             {
                 const int q = lane >> 1, i0 = (lane & 1) * 8;
                 const unsigned long long kq = sm.cand_key[q];
-                uint32_t bits = 0u;
+                uint32_t bits = 0u, hot = 0u;
+                float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (kq != 0ull) {
-                    const float4 bq = sm.cand_box[q];
+                    bq = sm.cand_box[q];
                     const int i1 = min(q, i0 + 8);
+                    // most pairs do not intersect at all (weight exactly 1): find the few that do with the lean
+                    // test first, so that the division + exp below runs once per intersecting pair, not per pair
                     for (int i = i0; i < i1; ++i) {
+                        const float4 bi = sm.cand_box[i];
+                        const float dx = fminf(bq.w, bi.w) - fmaxf(bq.y, bi.y);
+                        const float dy = fminf(bq.z, bi.z) - fmaxf(bq.x, bi.x);
+                        if ((dx > 0.0f && dy > 0.0f) || sm.malformed != 0) hot |= 1u << i;
+                        else sm.wpair[q][i] = 1.0f;
+                    }
+                }
+                while (__any_sync(0xffffffffu, hot != 0u)) {
+                    if (hot) {
+                        const int i = __ffs(hot) - 1;
+                        hot &= hot - 1;
                         const float w = nms_weight_fast(tf_iou(bq, sm.cand_box[i]), C.scale, C.is_soft, C.thr, sm.exp_tab);
                         sm.wpair[q][i] = w;
                         if (w != 1.0f) bits |= 1u << i;
@@ -537,7 +570,9 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
             if (lane < kTop && ((acc >> lane) & 1u)) {
                 const int pos = r + __popc(acc & ((1u << lane) - 1u));
                 const int x = key_index(myk);
-                sm.sel_box[pos] = sm.cand_box[lane];
+                const float4 cb = sm.cand_box[lane];
+                sm.sel_box[pos] = cb;
+                sm.batch_ebox[pos - r] = make_float4(cb.x - 2.0f, cb.y - 2.0f, cb.z + 2.0f, cb.w + 2.0f);
                 sm.sel_key[pos] = myk;
                 ucur[x] = -INFINITY;                                     // leaves the queue
                 a.nms_idx[(size_t)b * Dmax + pos] = x;
@@ -565,13 +600,13 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
                 const float u = ucur[s];
                 queued = u > -INFINITY;
                 const float4 bs = corn[s];
-                // no overlap even with the +1 pixel convention => not a member, and TF's intersection area
-                // max(dy,0)*max(dx,0) is 0 => IoU = 0, weight exactly 1: the centre does nothing to this survivor
+                // No overlap even with the +1 pixel convention => not a member, and TF's intersection area
+                // max(dy,0)*max(dx,0) is 0 => IoU = 0, weight exactly 1: the centre does nothing to this survivor.
+                // The test here only has to be a superset of "(hi - lo) > -1 in both dimensions" (passes B1 / B2
+                // decide exactly), so it compares against the centre grown by 2 px: four compares per pair.
                 for (int q = 0; q < m; ++q) {
-                    const float4 bx = sm.sel_box[r + q];
-                    const float dx = fminf(bs.w, bx.w) - fmaxf(bs.y, bx.y);
-                    const float dy = fminf(bs.z, bx.z) - fmaxf(bs.x, bx.x);
-                    if ((dx > -1.0f && dy > -1.0f) || all_maybe) mask |= 1u << q;
+                    const float4 e = sm.batch_ebox[q];
+                    if ((bs.z > e.x && bs.x < e.z && bs.w > e.y && bs.y < e.w) || all_maybe) mask |= 1u << q;
                 }
                 if (mask == 0u && queued) t2k.add(make_key(u, s));
             }
@@ -616,14 +651,10 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
             const uint32_t ent = seg[e];
             if (ent_head(ent) && ent_queued(ent)) {
                 const int s = ent_s(ent), c = ent_pairs(ent);
-                int j = 0, nextq = ent_q(ent);
-                const float u = k3_walk(C, sm, r, m, s, [&](int q) {
-                    if (q != nextq) return 1.0f;
-                    const float w = wseg[e + j];
-                    ++j;
-                    nextq = (j < c) ? ent_q(seg[e + j]) : -1;
-                    return w;
-                });
+                K3Walk wk;
+                wk.begin(C, s);
+                for (int j = 0; j < c; ++j) wk.step(C, sm, r, s, ent_q(seg[e + j]), wseg[e + j]);
+                const float u = wk.finish(C, sm, r, m, s);
                 if (u > -INFINITY) t2k.add(make_key(u, s));
             }
         }
