@@ -247,13 +247,13 @@ k4_fusion_kernel(K4Args a) {
                 ps = ps + c[k] / su; ns = ns + c[k]; ++used;
             }
         } else {
-            for (int w = 0; w < nwords; ++w)
-                for (uint32_t rem = row[w]; rem; rem &= rem - 1) {
-                    const float* c = cnt + (size_t)((w << 5) + __ffs(rem) - 1) * K;
-                    float su = 0.0f;
-                    for (int kk = 0; kk < K; ++kk) su = su + c[kk];
-                    ps = ps + c[k] / su; ns = ns + c[k]; ++used;
-                }
+            // m <= 3: all members; they are still in the index list (a cluster this small is one segment)
+            for (int q = 0; q < m; ++q) {
+                const float* c = cnt + (size_t)ml[q] * K;
+                float su = 0.0f;
+                for (int kk = 0; kk < K; ++kk) su = su + c[kk];
+                ps = ps + c[k] / su; ns = ns + c[k]; ++used;
+            }
         }
         op[k] = ps / (float)used;
         on[k] = ns;
