@@ -342,6 +342,59 @@ def test_full_size_bdd_image_bit_exact():
         compare_image_with_oracle(eng, res, b, r, 8, check_probs=False)
 
 
+def test_full_size_batch_properties():
+    """The bench workload at full size (8 BDD-shape images, N = 10, K = 11, Philox sampler) through
+    size-independent properties: survivors ascending, centres unique and in selection-score order, every
+    centre a member of its own cluster, Dirichlet count invariants (rows sum to
+    31 m for m <= 3 members, 93 otherwise), symmetric positive fused covariances, identical bits from a
+    second run, from a pipelined context and from a different sharding of the same global images."""
+    import torch
+    from bayes_od_rc_b200.engine import BayesODConfig, BayesODEngine
+    B, K = 8, 11
+    spec = synthetic.SceneSpec(N=10, K=K, config_id=3)
+    batch = synthetic.make_batch(spec, B, device="cuda", with_counts=False, first_image_id=16)
+    A = batch["anchors"].shape[0]
+    assert A == 172980
+
+    def run(b0, nb, depth=1, repeat=1):
+        cfg = BayesODConfig(use_full_covar=True, seed=1234, image_id_base=16 + b0, max_survivors=32768, pipeline_depth=depth)
+        eng = BayesODEngine(nb, 10, A, K, cfg)
+        for _ in range(repeat):
+            eng.run(batch["cls"][b0:b0 + nb], batch["box"][b0:b0 + nb], batch["cov"][b0:b0 + nb], batch["anchors"], None)
+        return eng, eng.fetch()
+
+    eng, res = run(0, B)
+    keys = ("num_dets", "num_survivors", "means", "covs", "cat_param", "cat_count", "nms_indices", "centre_anchor_idx",
+            "centre_scores")
+    for b in range(B):
+        S, D = int(res.num_survivors[b]), int(res.num_dets[b])
+        assert 1000 < S < 10000 and D == 100
+        sv = eng.survivors(b)
+        assert (np.diff(sv["anchor_idx"]) > 0).all()
+        assert np.allclose(sv["counts"].sum(1), 31.0, atol=1e-3)
+        idx = res.nms_indices[b, :D]
+        assert len(np.unique(idx)) == D and idx.min() >= 0 and idx.max() < S
+        assert (np.diff(res.centre_scores[b, :D]) <= 0).all()
+        assert_bit_equal(res.centre_anchor_idx[b, :D], sv["anchor_idx"][idx], "centre anchors")
+        mem = oracle.mask_to_bool(eng.members(b, S, D), S)               # [D,S]
+        assert mem[np.arange(D), idx].all()
+        m = mem.sum(1)
+        tot = res.cat_count[b, :D].sum(1)
+        assert np.allclose(tot, np.where(m > 3, 93.0, 31.0 * m), atol=1e-2)
+        assert np.allclose(res.cat_param[b, :D].sum(1), 1.0, atol=1e-4)
+        cov = res.covs[b, :D].astype(np.float64)
+        assert np.allclose(cov, cov.transpose(0, 2, 1), rtol=1e-3, atol=1e-3)
+        assert (np.linalg.eigvalsh((cov + cov.transpose(0, 2, 1)) / 2) > 0).all()
+    _, again = run(0, B, repeat=3)
+    _, piped = run(0, B, depth=3, repeat=4)
+    for k in keys:
+        assert_bit_equal(getattr(again, k), getattr(res, k), f"second run: {k}")
+        assert_bit_equal(getattr(piped, k), getattr(res, k), f"pipelined: {k}")
+    _, shard = run(5, 3)                                  # images 5..7 as their own shard
+    for k in keys:
+        assert_bit_equal(getattr(shard, k), getattr(res, k)[5:8], f"resharded: {k}")
+
+
 @pytest.mark.parametrize("name", ["bdd_covar_k8", "kitti_k4_n8", "no_survivor"])
 def test_dropin_inference_utils(name):
     """The reference-facing pair (same names / arguments / return structure as
