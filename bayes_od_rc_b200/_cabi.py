@@ -34,6 +34,7 @@ class BodConfig(C.Structure):
         ("score_threshold", C.c_float), ("pre_nms_top_k", C.c_int32),
         ("anchor_mode", C.c_int32), ("im_h", C.c_int32), ("im_w", C.c_int32),
         ("max_survivors", C.c_int32), ("emit_probs", C.c_int32), ("pipeline_depth", C.c_int32),
+        ("n_levels", C.c_int32), ("level_anchors", C.c_int32 * 8),
     ]
 
 
@@ -73,6 +74,7 @@ SYMBOLS = {
     "bod_last_error": (C.c_char_p, [C.c_void_p]),
     "bod_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "bod_run": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "bod_run_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bod_wait_results": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bod_validate_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BodValScaling), C.c_void_p]),
     "bod_run_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(BodHostResults)]),

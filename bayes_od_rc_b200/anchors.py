@@ -57,3 +57,8 @@ def generate_anchors(im_h: int, im_w: int, levels=LEVELS) -> np.ndarray:
 
 def num_anchors(im_h: int, im_w: int, levels=LEVELS) -> int:
     return sum(9 * nv * nu for nv, nu in (level_grid(im_h, im_w, l) for l in levels))
+
+
+def level_anchor_counts(im_h: int, im_w: int, levels=LEVELS) -> list:
+    """Anchors per pyramid level, P3->P7 (the ``level_anchors`` of ``bod_config`` for ``bod_run_levels``)."""
+    return [9 * nv * nu for nv, nu in (level_grid(im_h, im_w, l) for l in levels)]

@@ -41,6 +41,7 @@ struct bod_ctx {
     bod_config cfg;
     int device = 0;
     int tiles = 0, capacity = 0, words = 0, Dmax = 0;
+    LevelTable levels{};              // level structure (anchors, tiles); the pointers are filled per run
     char err[512] = {0};
     // one slab of device memory, carved up below
     unsigned char* slab = nullptr;
@@ -135,6 +136,15 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     if (!(cfg->soft_nms_sigma >= 0.0f)) return bad("soft_nms_sigma must be >= 0");
     if (cfg->num_draws < 1 || cfg->num_draws > 4096) return bad("num_draws must be in [1,4096]");
     if (cfg->pre_nms_top_k < 0) return bad("pre_nms_top_k must be >= 0");
+    if (cfg->n_levels < 0 || cfg->n_levels > kMaxLevels) return bad("n_levels must be in [0,8]");
+    if (cfg->n_levels > 1) {
+        long long sum = 0;
+        for (int l = 0; l < cfg->n_levels; ++l) {
+            if (cfg->level_anchors[l] < 1) return bad("level_anchors must be positive");
+            sum += cfg->level_anchors[l];
+        }
+        if (sum != cfg->A) return bad("level_anchors do not sum to A");
+    }
     if (cfg->anchor_mode == BOD_ANCHORS_GENERATE && count_anchors(cfg->im_h, cfg->im_w) != cfg->A)
         return bad("anchor_mode=GENERATE: A does not match the FPN anchor count of (im_h, im_w)");
 
@@ -142,7 +152,22 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     if (e != cudaSuccess) { snprintf(create_err, sizeof create_err, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); delete c; return BOD_ERR_CUDA; }
 
     const int B = cfg->B, A = cfg->A, K = cfg->K;
-    c->tiles = (A + kTileAnchors - 1) / kTileAnchors;
+    {
+        LevelTable& lv = c->levels;
+        lv.n = cfg->n_levels < 1 ? 1 : cfg->n_levels;
+        int an = 0, tl = 0;
+        for (int l = 0; l < lv.n; ++l) {
+            const int A_l = (cfg->n_levels < 1 || cfg->n_levels == 1) ? A : cfg->level_anchors[l];
+            lv.first_anchor[l] = an; lv.first_tile[l] = tl; lv.count[l] = A_l;
+            an += A_l; tl += (A_l + kTileAnchors - 1) / kTileAnchors;
+        }
+        lv.first_anchor[lv.n] = an; lv.first_tile[lv.n] = tl;
+        // the kernels find a tile's / an anchor's level by counting first_* entries <= it over entries 1..7:
+        // entry n (the total) and everything past it must never count
+        const int total_anchors = an, total_tiles = tl;
+        for (int l = lv.n; l <= kMaxLevels; ++l) { lv.first_anchor[l] = 0x7fffffff; lv.first_tile[l] = 0x7fffffff; }
+        c->tiles = total_tiles; (void)total_anchors;
+    }
     c->capacity = (cfg->max_survivors > 0 && cfg->max_survivors < A) ? cfg->max_survivors : A;
     c->capacity = (c->capacity + 31) & ~31;
     c->words = c->capacity / 32;
@@ -169,15 +194,16 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     TAKE(c->ticket, 256);
     c->prefilter = cfg->pre_nms_top_k > 0 || cfg->score_threshold > -INFINITY;
     if (c->prefilter) {
-        TAKE(c->pf_key, (size_t)B * A * 8); TAKE(c->pf_thr, (size_t)B * 8);
-        TAKE(c->pf_anchor, (size_t)B * A * 4); TAKE(c->pf_counts, (size_t)B * A * K * 4);
+        const size_t slots = (size_t)c->tiles * kTileAnchors;
+        TAKE(c->pf_key, B * slots * 8); TAKE(c->pf_thr, (size_t)B * 8);
+        TAKE(c->pf_anchor, B * slots * 4); TAKE(c->pf_counts, B * slots * K * 4);
         TAKE(c->pf_tile_count, (size_t)B * c->tiles * 4);
     }
     if (cfg->emit_probs) { TAKE(c->probs, (size_t)B * A * K * 4); TAKE(c->sampled, (size_t)B * A * K * 4); }
     for (int l = 0; l < c->nlanes; ++l) {
         Lane& L = c->lane[l];
-        TAKE(L.slot_anchor, (size_t)B * A * 4);
-        TAKE(L.slot_counts, (size_t)B * A * K * 4);
+        TAKE(L.slot_anchor, (size_t)B * c->tiles * kTileAnchors * 4);
+        TAKE(L.slot_counts, (size_t)B * c->tiles * kTileAnchors * K * 4);
         TAKE(L.tile_count, (size_t)B * c->tiles * 4);
         TAKE(L.tile_off, (size_t)B * (c->tiles + 1) * 4);
         TAKE(L.num_survivors, (size_t)B * 4);
@@ -256,18 +282,38 @@ extern "C" void bod_destroy(bod_ctx* c) {
 
 // Launch the stage kernels for images [b0, b0+nb) of the context's batch on lane L.  The head (K1, scan,
 // K2) goes to stream `hs`, the tail (soft-NMS, membership, K4) to `ts`; hs == ts runs them back to back.
-static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, const float* box, const float* cov,
+// one tensor per kind (already offset to the first image of the range), seen through the context's level structure
+static LevelTable levels_concat(const bod_ctx* c, const float* cls, const float* box, const float* cov) {
+    LevelTable lv = c->levels;
+    for (int l = 0; l < lv.n; ++l) {
+        lv.rows[l] = c->cfg.A; lv.row0[l] = lv.first_anchor[l];
+        lv.cls[l] = cls; lv.box[l] = box; lv.cov[l] = cov;
+    }
+    return lv;
+}
+// one tensor per kind and FPN level
+static LevelTable levels_split(const bod_ctx* c, const float* const* cls, const float* const* box, const float* const* cov) {
+    LevelTable lv = c->levels;
+    for (int l = 0; l < lv.n; ++l) {
+        lv.rows[l] = lv.count[l]; lv.row0[l] = 0;
+        lv.cls[l] = cls[l]; lv.box[l] = box[l]; lv.cov[l] = cov ? cov[l] : nullptr;
+    }
+    return lv;
+}
+
+static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
                      const float* anchors, const float* counts, cudaStream_t hs, cudaStream_t ts, bool record) {
     const bod_config& g = c->cfg;
     const size_t A = g.A, K = g.K, cap = c->capacity, D = c->Dmax;
+    const size_t slots = (size_t)c->tiles * kTileAnchors;
     const int cw = cov_width(g.cov_layout);
 
     if (record) CU(c, cudaEventRecord(c->ev[0], hs));
     K1Args k1{};
-    k1.cls = cls; k1.counts_in = counts;
+    k1.lv = lv; k1.counts_in = counts;
     k1.probs_out = c->probs ? c->probs + b0 * A * K : nullptr;
     k1.sampled_out = (c->sampled && !counts) ? c->sampled + b0 * A * K : nullptr;
-    k1.slot_anchor = L.slot_anchor + b0 * A; k1.slot_counts = L.slot_counts + b0 * A * K;
+    k1.slot_anchor = L.slot_anchor + b0 * slots; k1.slot_counts = L.slot_counts + b0 * slots * K;
     k1.tile_count = L.tile_count + (size_t)b0 * c->tiles;
     k1.B = nb; k1.N = g.N; k1.A = g.A; k1.K = g.K; k1.tiles = c->tiles;
     k1.num_draws = g.num_draws; k1.seed = g.seed; k1.image_id_base = g.image_id_base + (uint32_t)b0;
@@ -293,10 +339,10 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
         PrefilterArgs pf{};
         pf.slot_anchor = k1.slot_anchor; pf.slot_counts = k1.slot_counts; pf.tile_count = k1.tile_count;
         pf.tile_off = sc.tile_off;
-        pf.out_anchor = c->pf_anchor + b0 * A; pf.out_counts = c->pf_counts + b0 * A * K;
+        pf.out_anchor = c->pf_anchor + b0 * slots; pf.out_counts = c->pf_counts + b0 * slots * K;
         pf.out_tile_count = c->pf_tile_count + (size_t)b0 * c->tiles;
-        pf.key = c->pf_key + b0 * A; pf.thr_key = c->pf_thr + b0;
-        pf.B = nb; pf.A = g.A; pf.K = g.K; pf.tiles = c->tiles;
+        pf.key = c->pf_key + b0 * slots; pf.thr_key = c->pf_thr + b0;
+        pf.B = nb; pf.A = g.A; pf.K = g.K; pf.tiles = c->tiles; pf.slot_stride = (int)slots;
         pf.dirichlet = g.dirichlet_prior == BOD_DIRICHLET_NON_INFORMATIVE;
         pf.score_threshold = g.score_threshold; pf.top_k = g.pre_nms_top_k;
         CU(c, launch_prefilter(pf, hs));
@@ -311,7 +357,8 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const float* cls, cons
     // (K2 stays on the head stream: with it on the tail, the tail becomes the longer leg -- measured)
     if (hs != ts && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
     K2Args k2{};
-    k2.box = box; k2.cov = cw ? cov : nullptr; k2.anchors = anchors;
+    k2.lv = lv; k2.anchors = anchors;
+    if (!cw) for (int l = 0; l < k2.lv.n; ++l) k2.lv.cov[l] = nullptr;
     k2.slot_anchor = slot_anchor; k2.slot_counts = slot_counts; k2.tile_off = sc.tile_off;
     k2.num_survivors = sc.num_survivors;
     k2.surv_anchor = L.surv_anchor + b0 * cap; k2.cnt_post = L.cnt_post + b0 * cap * K;
@@ -378,32 +425,28 @@ static int check_inputs(bod_ctx* c, const float* cls, const float* box, const fl
     return BOD_OK;
 }
 
-extern "C" int bod_run(bod_ctx* c, const float* cls, const float* box, const float* cov, const float* anchors,
-                       const float* counts, void* cuda_stream) {
-    int rc = check_inputs(c, cls, box, cov, anchors);
-    if (rc) return rc;
+// issue one whole run (serial on the caller's stream, or head / tail on the context's streams)
+static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, const float* counts, void* cuda_stream) {
     if (c->cfg.N < 2) return fail(c, BOD_ERR_INVALID, "bod_run needs N (mc_dropout_samples) >= 2: the sample covariance divides by N-1");
-    if ((reinterpret_cast<uintptr_t>(box) & 15u) || (cov && (reinterpret_cast<uintptr_t>(cov) & 15u)) ||
-        (anchors && (reinterpret_cast<uintptr_t>(anchors) & 15u)))
-        return fail(c, BOD_ERR_INVALID, "box / cov / anchors must be 16-byte aligned");
     CU(c, cudaSetDevice(c->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    int rc;
     c->launches = 0;
     c->ev = c->evring[c->runs_recorded % bod_ctx::kEvRing];
     if (c->nlanes == 1) {
         c->cur = 0;
-        rc = run_range(c, c->lane[0], 0, c->cfg.B, cls, box, cov, anchors, counts, st, st, c->timing);
+        rc = run_range(c, c->lane[0], 0, c->cfg.B, lv, anchors, counts, st, st, c->timing);
         if (rc) return rc;
         c->last_stream = st;
     } else {
         // pipelined: the head runs on the context's own stream once the caller's stream has reached this
-        // point; the tail floats on a second stream.  The caller's stream only waits for the head (the
+        // point; the tail floats on the lane's own stream.  The caller's stream only waits for the head (the
         // last reader of the inputs); results are complete at bod_fetch / bod_wait_results.
         c->cur = (c->cur + 1) % c->nlanes;
         Lane& L = c->lane[c->cur];
         CU(c, cudaEventRecord(c->ev_in, st));
         CU(c, cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
-        rc = run_range(c, L, 0, c->cfg.B, cls, box, cov, anchors, counts, c->own_stream, L.tail_stream, c->timing);
+        rc = run_range(c, L, 0, c->cfg.B, lv, anchors, counts, c->own_stream, L.tail_stream, c->timing);
         if (rc) return rc;
         CU(c, cudaStreamWaitEvent(st, L.head_done, 0));
         c->last_stream = L.tail_stream;
@@ -411,6 +454,42 @@ extern "C" int bod_run(bod_ctx* c, const float* cls, const float* box, const flo
     if (c->timing) ++c->runs_recorded;
     c->last_timed = c->timing;
     c->ran = true; c->used_sampler = (counts == nullptr);
+    return BOD_OK;
+}
+
+extern "C" int bod_run(bod_ctx* c, const float* cls, const float* box, const float* cov, const float* anchors,
+                       const float* counts, void* cuda_stream) {
+    int rc = check_inputs(c, cls, box, cov, anchors);
+    if (rc) return rc;
+    if ((reinterpret_cast<uintptr_t>(box) & 15u) || (cov && (reinterpret_cast<uintptr_t>(cov) & 15u)) ||
+        (anchors && (reinterpret_cast<uintptr_t>(anchors) & 15u)))
+        return fail(c, BOD_ERR_INVALID, "box / cov / anchors must be 16-byte aligned");
+    return issue_run(c, levels_concat(c, cls, box, cov), anchors, counts, cuda_stream);
+}
+
+extern "C" int bod_run_levels(bod_ctx* c, const float* const* cls, const float* const* box, const float* const* cov,
+                              const float* anchors, const float* counts, void* cuda_stream) {
+    if (!c) return BOD_ERR_INVALID;
+    if (c->cfg.n_levels < 2) return fail(c, BOD_ERR_STATE, "the context was created without n_levels / level_anchors");
+    if (!cls || !box) return fail(c, BOD_ERR_INVALID, "cls and box must not be NULL");
+    if (c->cfg.cov_layout != BOD_COV_NONE && !cov) return fail(c, BOD_ERR_INVALID, "cov is NULL but cov_layout != NONE");
+    if (c->cfg.anchor_mode == BOD_ANCHORS_TENSOR && !anchors) return fail(c, BOD_ERR_INVALID, "anchors is NULL but anchor_mode = TENSOR");
+    if (anchors && (reinterpret_cast<uintptr_t>(anchors) & 15u)) return fail(c, BOD_ERR_INVALID, "anchors must be 16-byte aligned");
+    for (int l = 0; l < c->cfg.n_levels; ++l) {
+        if (!cls[l] || !box[l] || (c->cfg.cov_layout != BOD_COV_NONE && !cov[l]))
+            return fail(c, BOD_ERR_INVALID, "level %d: NULL tensor", l);
+        if ((reinterpret_cast<uintptr_t>(box[l]) & 15u) || (c->cfg.cov_layout != BOD_COV_NONE && (reinterpret_cast<uintptr_t>(cov[l]) & 15u)))
+            return fail(c, BOD_ERR_INVALID, "level %d: box / cov must be 16-byte aligned", l);
+    }
+    return issue_run(c, levels_split(c, cls, box, c->cfg.cov_layout != BOD_COV_NONE ? cov : nullptr), anchors, counts, cuda_stream);
+}
+
+extern "C" int bod_wait_results(bod_ctx* c, void* cuda_stream) {
+    if (!c) return BOD_ERR_INVALID;
+    if (!c->ran) return fail(c, BOD_ERR_STATE, "no bod_run has been issued on this context");
+    CU(c, cudaSetDevice(c->device));
+    Lane& L = c->lane[c->cur];
+    if (c->nlanes > 1 && L.tail_pending) CU(c, cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(cuda_stream), L.tail_done, 0));
     return BOD_OK;
 }
 
@@ -462,15 +541,6 @@ extern "C" int bod_validate_run(bod_ctx* c, const float* cls, const float* box, 
     c->launches = 5;
     c->last_timed = false;
     c->last_stream = st; c->ran = true; c->used_sampler = false;
-    return BOD_OK;
-}
-
-extern "C" int bod_wait_results(bod_ctx* c, void* cuda_stream) {
-    if (!c) return BOD_ERR_INVALID;
-    if (!c->ran) return fail(c, BOD_ERR_STATE, "no bod_run has been issued on this context");
-    CU(c, cudaSetDevice(c->device));
-    Lane& L = c->lane[c->cur];
-    if (c->nlanes > 1 && L.tail_pending) CU(c, cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(cuda_stream), L.tail_done, 0));
     return BOD_OK;
 }
 
@@ -705,9 +775,10 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
         cudaEvent_t ev = c->ev_copy[nev++ & 3];
         CU(c, cudaEventRecord(ev, cs));
         CU(c, cudaStreamWaitEvent(st, ev, 0));
-        rc = run_range(c, L, (int)b0, (int)nb, c->in_cls + b0 * N * A * K,
-                       box_m ? box_m + b0 * N * A * 4 : c->in_box + b0 * N * A * 4,
-                       cw ? (cov_m ? cov_m + b0 * N * A * cw : c->in_cov + b0 * N * A * cw) : nullptr,
+        rc = run_range(c, L, (int)b0, (int)nb,
+                       levels_concat(c, c->in_cls + b0 * N * A * K,
+                                     box_m ? box_m + b0 * N * A * 4 : c->in_box + b0 * N * A * 4,
+                                     cw ? (cov_m ? cov_m + b0 * N * A * cw : c->in_cov + b0 * N * A * cw) : nullptr),
                        anchors ? c->in_anchors : nullptr, counts ? c->in_counts + b0 * A * K : nullptr, st, st, false);
         if (rc) return rc;
     }

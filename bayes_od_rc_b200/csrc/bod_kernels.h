@@ -5,16 +5,34 @@
 
 namespace bod {
 
+// Head outputs either as one tensor per kind ([B,N,A,*], n = 1) or as one tensor per FPN level
+// ([B,N,A_l,*], concatenated P3 -> P7 along the anchor axis by the reference, retinanet_model.py:82-112):
+// level l covers the global anchors [first_anchor[l], first_anchor[l+1]) and the tiles
+// [first_tile[l], first_tile[l+1]) of the per-image tile grid (tiles never straddle levels).
+constexpr int kMaxLevels = 8;
+struct LevelTable {
+    int n;
+    int first_anchor[kMaxLevels + 1];   // entries >= n: INT_MAX (a level is found by counting entries <= the index)
+    int first_tile[kMaxLevels + 1];
+    int count[kMaxLevels];              // anchors of level l
+    // where level l lives: tensors of `rows[l]` anchors per sample, the level's first anchor at row `row0[l]`
+    // (separate tensors: rows = A_l, row0 = 0; one concatenated tensor viewed per level: rows = A, row0 = first_anchor)
+    int rows[kMaxLevels], row0[kMaxLevels];
+    const float* cls[kMaxLevels];    // [B,N,rows,K]
+    const float* box[kMaxLevels];    // [B,N,rows,4]
+    const float* cov[kMaxLevels];    // [B,N,rows,16|10] or nullptr
+};
+
 // ---- K1: moments + counts + filter + per-tile compaction ------------------
 struct K1Args {
-    const float* cls;        // [B,N,A,K]
+    LevelTable lv;           // cls per level
     const float* counts_in;  // [B,A,K] or nullptr (Philox)
     float* probs_out;        // [B,A,K] or nullptr
     float* sampled_out;      // [B,A,K] or nullptr (Philox counts, parity)
-    int32_t* slot_anchor;    // [B,A]    survivors of tile t at [t*TILE, t*TILE+count)
-    float* slot_counts;      // [B,A,K]
+    int32_t* slot_anchor;    // [B,tiles*TILE]    survivors of tile t at [t*TILE, t*TILE+count)
+    float* slot_counts;      // [B,tiles*TILE,K]
     int32_t* tile_count;     // [B,tiles]
-    int B, N, A, K, tiles;
+    int B, N, A, K, tiles;   // tiles per image; the slot lists have tiles*TILE rows per image
     int num_draws;
     uint64_t seed;
     uint32_t image_id_base;
@@ -48,7 +66,7 @@ struct PrefilterArgs {
     int32_t* out_tile_count;    // [B,tiles]
     unsigned long long* key;    // [B,A] scratch
     unsigned long long* thr_key;  // [B] scratch
-    int B, A, K, tiles;
+    int B, A, K, tiles, slot_stride;   // slot_stride = tiles*TILE rows per image in the slot lists / key
     int dirichlet;              // counts + 1/K before normalising (non_informative prior)
     float score_threshold;      // keep iff score > threshold (-inf: all)
     int top_k;                  // 0 = off
@@ -57,11 +75,10 @@ cudaError_t launch_prefilter(const PrefilterArgs& a, cudaStream_t st);
 
 // ---- K2: per-survivor posterior -------------------------------------------
 struct K2Args {
-    const float* box;           // [B,N,A,4]
-    const float* cov;           // [B,N,A,16|10] or nullptr
+    LevelTable lv;              // box / cov per level (cov entries nullptr when cov_layout = none)
     const float* anchors;       // [A,4] or nullptr (generate)
-    const int32_t* slot_anchor; // [B,A]
-    const float* slot_counts;   // [B,A,K]
+    const int32_t* slot_anchor; // [B,tiles*TILE]
+    const float* slot_counts;   // [B,tiles*TILE,K]
     const int32_t* tile_off;    // [B,tiles+1]
     const int32_t* num_survivors;  // [B]
     // outputs, [B,cap,*]
@@ -134,7 +151,7 @@ struct ValArgs {
     const float* cls;        // [B,A,K] logits (one sample)
     const float* box;        // [B,A,4] deltas
     const float* anchors;    // [A,4]
-    int32_t* slot_anchor; float* slot_counts; int32_t* tile_count;      // V1 out (slot_counts holds the probabilities)
+    int32_t* slot_anchor; float* slot_counts; int32_t* tile_count;      // V1 out (slot_counts holds the probabilities); tiles*TILE rows per image
     const int32_t* tile_off; const int32_t* num_survivors;              // scan out
     int32_t* surv_anchor; float* cnt_post; float* mu_post; float* score; float4* corners;   // V2 out
     const int32_t* nms_idx; const int32_t* num_dets;                    // K3 out

@@ -161,6 +161,22 @@ BOD_DEVINL bool philox_counts(const float (&p)[K], uint32_t anchor, uint32_t ima
     return true;
 }
 
+// tile of the per-image grid -> level, first local anchor of the tile, anchors of the level
+struct TileRef { int level, a0, A_l, anchor0, rows, row; };   // rows: anchors per sample of the level's tensor; row: the tile's first row in it
+BOD_DEVINL TileRef tile_ref(const LevelTable& lv, int tile) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i) l += (tile >= lv.first_tile[i]) ? 1 : 0;     // entries past n hold INT_MAX
+    TileRef r;
+    r.level = l;
+    r.a0 = (tile - lv.first_tile[l]) * kTileAnchors;
+    r.A_l = lv.count[l];
+    r.anchor0 = lv.first_anchor[l] + r.a0;
+    r.rows = lv.rows[l];
+    r.row = lv.row0[l] + r.a0;
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------
@@ -178,14 +194,15 @@ k1_moments_kernel(K1Args a, int NC) {
     __shared__ int warp_count[kTileAnchors / 32];
 
     const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    const int a0 = tile * kTileAnchors;
-    const int rows = min(kTileAnchors, a.A - a0);            // anchors in this tile
+    const TileRef tr = tile_ref(a.lv, tile);
+    const int a0 = tile * kTileAnchors;                      // first slot of the tile
+    const int rows = min(kTileAnchors, tr.A_l - tr.a0);      // anchors in this tile
     const int N = a.N;
     const int nchunks = (N + NC - 1) / NC;
     constexpr size_t slab_stride = (size_t)kTileAnchors * K;  // floats per smem slab
     const size_t stage_stride = slab_stride * NC;
     float* ring = reinterpret_cast<float*>(smem_raw);
-    const float* src0 = a.cls + ((size_t)b * N * a.A + a0) * K;   // sample 0 of this tile
+    const float* src0 = a.lv.cls[tr.level] + ((size_t)b * N * tr.rows + tr.row) * K;   // sample 0 of this tile
     const uint32_t slab_bytes = (uint32_t)rows * K * 4u;
 
     auto issue = [&](int c) {   // one thread: bulk-copy chunk c into stage c&1
@@ -193,7 +210,7 @@ k1_moments_kernel(K1Args a, int NC) {
         uint64_t* br = &bar[c & 1];
         mbar_expect_tx(br, slab_bytes * (uint32_t)(n1 - n0));
         for (int n = n0; n < n1; ++n)
-            bulk_g2s(ring + (c & 1) * stage_stride + (size_t)(n - n0) * slab_stride, src0 + (size_t)n * a.A * K,
+            bulk_g2s(ring + (c & 1) * stage_stride + (size_t)(n - n0) * slab_stride, src0 + (size_t)n * tr.rows * K,
                      slab_bytes, br);
     };
 
@@ -205,7 +222,7 @@ k1_moments_kernel(K1Args a, int NC) {
     }
 
     // counts to inject (parity mode) are fetched while the slabs are in flight
-    const int anchor = a0 + tid;
+    const int anchor = tr.anchor0 + tid;
     const bool valid = tid < rows;
     float cnt[K];
 #pragma unroll
@@ -229,7 +246,7 @@ k1_moments_kernel(K1Args a, int NC) {
             __syncthreads();
             const int nflt = rows * K;
             for (int n = n0; n < n1; ++n) {
-                const float* src = src0 + (size_t)n * a.A * K;
+                const float* src = src0 + (size_t)n * tr.rows * K;
                 float* dst = ring + (size_t)(n - n0) * slab_stride;
                 for (int e = tid; e < nflt; e += kTileAnchors) dst[e] = __ldg(src + e);
             }
@@ -304,8 +321,8 @@ k1_moments_kernel(K1Args a, int NC) {
     }
     if (keep) {
         const int slot = a0 + base + __popc(ballot & ((1u << lane) - 1u));   // per-tile slot region
-        a.slot_anchor[(size_t)b * a.A + slot] = anchor;
-        float* o = a.slot_counts + ((size_t)b * a.A + slot) * K;
+        a.slot_anchor[(size_t)b * a.tiles * kTileAnchors + slot] = anchor;
+        float* o = a.slot_counts + ((size_t)b * a.tiles * kTileAnchors + slot) * K;
 #pragma unroll
         for (int k = 0; k < K; ++k) o[k] = cnt[k];
     }
@@ -356,14 +373,14 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
                 }
                 stage_tile[stage] = (int)t;
                 const int b = (int)t / tiles, tile = (int)t - b * tiles;
-                const int a0 = tile * kTileAnchors;
-                const int rows = min(kTileAnchors, a.A - a0);
+                const TileRef tr = tile_ref(a.lv, tile);
+                const int rows = min(kTileAnchors, tr.A_l - tr.a0);
                 const uint32_t bytes = (uint32_t)rows * K * 4u;
-                const float* src = a.cls + ((size_t)b * N * a.A + a0) * K;
+                const float* src = a.lv.cls[tr.level] + ((size_t)b * N * tr.rows + tr.row) * K;
                 for (int n = 0; n < N; ++n) {
                     if (n > 0 && round > 0) mbar_wait(&empty_bar[stage], (uint32_t)((round - 1) & 1));
                     mbar_expect_tx(&full_bar[stage], bytes);
-                    bulk_g2s(ring + stage * slab_stride, src + (size_t)n * a.A * K, bytes, &full_bar[stage]);
+                    bulk_g2s(ring + stage * slab_stride, src + (size_t)n * tr.rows * K, bytes, &full_bar[stage]);
                     if (++stage == NS) { stage = 0; ++round; }
                 }
             }
@@ -378,9 +395,10 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
         const int t = stage_tile[stage];
         if (t < 0) break;
         const int b = t / tiles, tile = t - b * tiles;
-        const int a0 = tile * kTileAnchors;
-        const int rows = min(kTileAnchors, a.A - a0);
-        const int anchor = a0 + tid;
+        const TileRef tr = tile_ref(a.lv, tile);
+        const int a0 = tile * kTileAnchors;                  // first slot of the tile
+        const int rows = min(kTileAnchors, tr.A_l - tr.a0);
+        const int anchor = tr.anchor0 + tid;
         const bool valid = tid < rows;
 
         float cnt[K];
@@ -469,8 +487,8 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
         }
         if (keep) {
             const int slot = a0 + base + __popc(ballot & ((1u << lane) - 1u));   // per-tile slot region
-            a.slot_anchor[(size_t)b * a.A + slot] = anchor;
-            float* o = a.slot_counts + ((size_t)b * a.A + slot) * K;
+            a.slot_anchor[(size_t)b * tiles * kTileAnchors + slot] = anchor;
+            float* o = a.slot_counts + ((size_t)b * tiles * kTileAnchors + slot) * K;
 #pragma unroll
             for (int k = 0; k < K; ++k) o[k] = cnt[k];
         }
@@ -479,8 +497,13 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
 }
 
 static bool k1_aligned(const K1Args& a) {
-    return ((reinterpret_cast<uintptr_t>(a.cls) & 15u) == 0) && (((size_t)a.A * a.K) % 4 == 0) &&
-           ((kTileAnchors * a.K) % 4 == 0);
+    // bulk copies need 16-byte aligned sources and sizes for every (level, image, sample, tile)
+    if ((kTileAnchors * a.K) % 4 != 0) return false;
+    for (int l = 0; l < a.lv.n; ++l)
+        if ((reinterpret_cast<uintptr_t>(a.lv.cls[l]) & 15u) != 0 || ((size_t)a.lv.rows[l] * a.K) % 4 != 0 ||
+            ((size_t)a.lv.row0[l] * a.K) % 4 != 0)
+            return false;
+    return true;
 }
 static int k1_ctas_per_sm() {
     static int v = 0;

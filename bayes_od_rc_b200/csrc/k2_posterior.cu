@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(kPfTileWarps * 32) prefilter_keys_kernel(Prefi
     const int K = a.K;
     const int cnt = a.tile_count[(size_t)b * a.tiles + t];
     const int off = a.tile_off[(size_t)b * (a.tiles + 1) + t];
-    const int32_t* sanchor = a.slot_anchor + (size_t)b * a.A;
-    const float* scounts = a.slot_counts + (size_t)b * a.A * K;
-    unsigned long long* key = a.key + (size_t)b * a.A;
+    const int32_t* sanchor = a.slot_anchor + (size_t)b * a.slot_stride;
+    const float* scounts = a.slot_counts + (size_t)b * a.slot_stride * K;
+    unsigned long long* key = a.key + (size_t)b * a.slot_stride;
     for (int j = lane; j < cnt; j += 32) {
         const int slot = t * kTileAnchors + j;
         const float sc = count_score(scounts + (size_t)slot * K, K, a.dirichlet != 0);
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kPfThreads) prefilter_select_kernel(PrefilterA
     __shared__ unsigned long long sh_prefix;
     __shared__ unsigned int sh_k, sh_total;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const unsigned long long* key = a.key + (size_t)b * a.A;
+    const unsigned long long* key = a.key + (size_t)b * a.slot_stride;
     const int S0 = a.tile_off[(size_t)b * (a.tiles + 1) + a.tiles];
     if (tid == 0) sh_total = 0u;
     __syncthreads();
@@ -178,11 +178,11 @@ __global__ void __launch_bounds__(kPfTileWarps * 32) prefilter_compact_kernel(Pr
     const int cnt = a.tile_count[(size_t)b * a.tiles + t];
     const int off = a.tile_off[(size_t)b * (a.tiles + 1) + t];
     const unsigned long long thr_key = a.thr_key[b];
-    const int32_t* sanchor = a.slot_anchor + (size_t)b * a.A;
-    const float* scounts = a.slot_counts + (size_t)b * a.A * K;
-    int32_t* oanchor = a.out_anchor + (size_t)b * a.A;
-    float* ocounts = a.out_counts + (size_t)b * a.A * K;
-    const unsigned long long* key = a.key + (size_t)b * a.A;
+    const int32_t* sanchor = a.slot_anchor + (size_t)b * a.slot_stride;
+    const float* scounts = a.slot_counts + (size_t)b * a.slot_stride * K;
+    int32_t* oanchor = a.out_anchor + (size_t)b * a.slot_stride;
+    float* ocounts = a.out_counts + (size_t)b * a.slot_stride * K;
+    const unsigned long long* key = a.key + (size_t)b * a.slot_stride;
     int kept = 0;
     for (int c0 = 0; c0 < cnt; c0 += 32) {
         const int j = c0 + lane;
@@ -317,8 +317,14 @@ k2_posterior_kernel(K2Args a, AnchorLevels L) {
         int lo = 0, hi = a.tiles;                                            // off[lo] <= s < off[hi]
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= s) lo = mid; else hi = mid; }
         const int slot = lo * kTileAnchors + (s - off[lo]);
-        const int anchor = a.slot_anchor[(size_t)b * a.A + slot];
-        const float* cn = a.slot_counts + ((size_t)b * a.A + slot) * K;
+        const int anchor = a.slot_anchor[(size_t)b * a.tiles * kTileAnchors + slot];
+        const float* cn = a.slot_counts + ((size_t)b * a.tiles * kTileAnchors + slot) * K;
+        // the level that holds this anchor (one tensor per kind: a single level)
+        int lvl = 0;
+#pragma unroll
+        for (int i = 1; i < kMaxLevels; ++i) lvl += (anchor >= a.lv.first_anchor[i]) ? 1 : 0;     // entries past n hold INT_MAX
+        const int A_l = a.lv.rows[lvl];                                  // anchors per sample of the level's tensors
+        const int local = anchor - a.lv.first_anchor[lvl] + a.lv.row0[lvl];
 
         const float4 an = (a.anchor_mode == 1) ? anchor_of(L, anchor)
                                                : __ldg(reinterpret_cast<const float4*>(a.anchors) + anchor);
@@ -328,9 +334,9 @@ k2_posterior_kernel(K2Args a, AnchorLevels L) {
         // [N,A,4,4] covariance head of the same sample are summed in the same pass (:67) and everything a
         // sample needs is requested one sample ahead: ten independent 16-byte gathers in flight per thread
         // while the decode (two binary64 exps) of the current sample runs.
-        const float4* boxp = reinterpret_cast<const float4*>(a.box) + (size_t)b * N * a.A + anchor;
+        const float4* boxp = reinterpret_cast<const float4*>(a.lv.box[lvl]) + (size_t)b * N * A_l + local;
         const bool cov16 = a.cov_layout == 1;
-        const float4* covp = cov16 ? reinterpret_cast<const float4*>(a.cov) + ((size_t)b * N * a.A + anchor) * 4 : nullptr;
+        const float4* covp = cov16 ? reinterpret_cast<const float4*>(a.lv.cov[lvl]) + ((size_t)b * N * A_l + local) * 4 : nullptr;
         float mu[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         float abar[4][4];
 #pragma unroll
@@ -347,10 +353,10 @@ k2_posterior_kernel(K2Args a, AnchorLevels L) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) cr[i] = c_nx[i];
             if (n + 1 < N) {
-                t_nx = __ldg(boxp + (size_t)(n + 1) * a.A);
+                t_nx = __ldg(boxp + (size_t)(n + 1) * A_l);
                 if (cov16) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) c_nx[i] = __ldg(covp + (size_t)(n + 1) * a.A * 4 + i);
+                    for (int i = 0; i < 4; ++i) c_nx[i] = __ldg(covp + (size_t)(n + 1) * A_l * 4 + i);
                 }
             }
             const float v = ah * t.x / 10.0f + av;
@@ -401,9 +407,9 @@ k2_posterior_kernel(K2Args a, AnchorLevels L) {
             if (a.cov_layout == 1) {
                 // summed with the box samples above
             } else {
-                const float* cp = a.cov + ((size_t)b * N * a.A + anchor) * 10;
+                const float* cp = a.lv.cov[lvl] + ((size_t)b * N * A_l + local) * 10;
                 for (int n = 0; n < N; ++n) {
-                    const float2* q = reinterpret_cast<const float2*>(cp + (size_t)n * a.A * 10);
+                    const float2* q = reinterpret_cast<const float2*>(cp + (size_t)n * A_l * 10);
                     float x[10];
 #pragma unroll
                     for (int i = 0; i < 5; ++i) { const float2 v2 = __ldg(q + i); x[2 * i] = v2.x; x[2 * i + 1] = v2.y; }

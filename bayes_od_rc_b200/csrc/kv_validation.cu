@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(kTileAnchors) val_filter_kernel(ValArgs a) {
     }
     if (keep) {
         const int slot = tile * kTileAnchors + base + __popc(ballot & ((1u << lane) - 1u));
-        a.slot_anchor[(size_t)b * a.A + slot] = anchor;
-        float* o = a.slot_counts + ((size_t)b * a.A + slot) * K;
+        a.slot_anchor[(size_t)b * a.tiles * kTileAnchors + slot] = anchor;
+        float* o = a.slot_counts + ((size_t)b * a.tiles * kTileAnchors + slot) * K;
 #pragma unroll
         for (int k = 0; k < K; ++k) o[k] = p[k];
     }
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(128) val_survivor_kernel(ValArgs a) {
     int lo = 0, hi = a.tiles;                                            // off[lo] <= s < off[hi]
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= s) lo = mid; else hi = mid; }
     const int slot = lo * kTileAnchors + (s - off[lo]);
-    const int anchor = a.slot_anchor[(size_t)b * a.A + slot];
-    const float* pr = a.slot_counts + ((size_t)b * a.A + slot) * K;
+    const int anchor = a.slot_anchor[(size_t)b * a.tiles * kTileAnchors + slot];
+    const float* pr = a.slot_counts + ((size_t)b * a.tiles * kTileAnchors + slot) * K;
     const size_t row = (size_t)b * a.capacity + s;
     float best = pr[0];
     float* oc = a.cnt_post + row * K;

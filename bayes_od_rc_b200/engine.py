@@ -47,6 +47,7 @@ class BayesODConfig:
     max_survivors: int = 0
     emit_probs: bool = False
     pipeline_depth: int = 1
+    level_anchors: tuple = ()       # anchors per FPN level (P3->P7) when the head outputs come per level (run_levels)
 
     @classmethod
     def from_reference(cls, bayes_od_config: dict, nms_config: dict, use_full_covar: bool = False, **kw):
@@ -73,7 +74,8 @@ class BayesODConfig:
             image_id_base=self.image_id_base, score_threshold=self.score_threshold,
             pre_nms_top_k=self.pre_nms_top_k, anchor_mode=self.anchor_mode, im_h=self.im_h, im_w=self.im_w,
             max_survivors=self.max_survivors, emit_probs=int(self.emit_probs),
-            pipeline_depth=int(self.pipeline_depth))
+            pipeline_depth=int(self.pipeline_depth), n_levels=len(self.level_anchors),
+            level_anchors=(C.c_int32 * 8)(*[int(x) for x in self.level_anchors]))
 
 
 # --------------------------------------------------------------------------
@@ -246,6 +248,25 @@ class BayesODEngine:
         self._keeps.append((cls, box, cov, anchors, counts, keep))
         del self._keeps[:-max(1, int(self.config.pipeline_depth))]
         self._check(self.lib.bod_run(self._ctx, p_cls, p_box, p_cov, p_anc, p_cnt, C.c_void_p(int(stream) or None)))
+
+    def run_levels(self, cls, box, cov=None, anchors=None, counts=None, stream=0):
+        """bod_run_levels: ``cls`` / ``box`` / ``cov`` are sequences with one device array per FPN level
+        ([B,N,A_l,K], [B,N,A_l,4], [B,N,A_l,4,4] | [B,N,A_l,10]) -- the head outputs before the reference
+        concatenates them (retinanet_model.py:89-112)."""
+        B, N, K = self.B, self.N, self.K
+        la = list(self.config.level_anchors)
+        keep = []
+        ptrs = lambda seq, width: (C.c_void_p * len(la))(*[device_ptr(t, B * N * a * width, keep) for t, a in zip(seq, la)])   # noqa: E731
+        if len(cls) != len(la) or len(box) != len(la) or (self.cov_width and len(cov) != len(la)):
+            raise ValueError(f"expected {len(la)} tensors per kind (one per level)")
+        p_cls, p_box = ptrs(cls, K), ptrs(box, 4)
+        p_cov = ptrs(cov, self.cov_width) if self.cov_width else None
+        p_anc = device_ptr(anchors, self.A * 4, keep) if self.config.anchor_mode == _cabi.ANCHORS_TENSOR else None
+        p_cnt = device_ptr(counts, B * self.A * K, keep) if counts is not None else None
+        self._keeps = getattr(self, "_keeps", [])
+        self._keeps.append((cls, box, cov, anchors, counts, keep))
+        del self._keeps[:-max(1, int(self.config.pipeline_depth))]
+        self._check(self.lib.bod_run_levels(self._ctx, p_cls, p_box, p_cov, p_anc, p_cnt, C.c_void_p(int(stream) or None)))
 
     def validate(self, cls, box, anchors, scaling=None, stream=0):
         """validation_utils.post_process_predictions for the batch (bod_validate_run): device arrays

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BOD_ABI_VERSION 5
+#define BOD_ABI_VERSION 6
 
 typedef enum bod_status {
     BOD_OK            = 0,
@@ -96,6 +96,11 @@ typedef struct bod_config {
                                     SM per image); small batches want more lanes.  The caller's
                                     stream then only waits for the part that reads the inputs;
                                     results are complete at bod_fetch or after bod_wait_results */
+    int32_t  n_levels;           /* 0/1: the head outputs come as one tensor per kind.  2..8:
+                                    bod_run_levels may hand them over per FPN level, i.e. BEFORE
+                                    the tf.concat(axis=1) of retinanet_model.py:89-112; level l
+                                    holds level_anchors[l] anchors, sum = A, order P3 -> P7       */
+    int32_t  level_anchors[8];
 } bod_config;
 
 typedef struct bod_ctx bod_ctx;
@@ -176,6 +181,18 @@ int bod_run(bod_ctx* ctx, const float* cls, const float* box, const float* cov,
  * by consumers that read bod_device_results_of on their own stream; a no-op
  * otherwise (the run is already ordered on the caller's stream). */
 int bod_wait_results(bod_ctx* ctx, void* cuda_stream);
+
+/*
+ * bod_run with the head outputs still split per FPN level: what the
+ * reference's headers return for each pyramid layer before retinanet_model.py:89 / :99 / :109
+ * concatenates them along the anchor axis.  cls[l] [B,N,A_l,K], box[l] [B,N,A_l,4],
+ * cov[l] [B,N,A_l,16|10] (cov may be NULL when cov_layout = NONE), l < cfg.n_levels, device
+ * memory, 16-byte aligned.  The concat copies (the whole [N,A,K+4+16] volume, once more through
+ * HBM) are never made; everything else is bod_run.  The context's tile grid follows the level
+ * structure, and bod_run (one tensor per kind) keeps working on the same context.
+ */
+int bod_run_levels(bod_ctx* ctx, const float* const* cls, const float* const* box, const float* const* cov,
+                   const float* anchors, const float* counts, void* cuda_stream);
 
 /*
  * The validation post-process: validation_utils.post_process_predictions

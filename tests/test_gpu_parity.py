@@ -342,6 +342,49 @@ def test_full_size_bdd_image_bit_exact():
         compare_image_with_oracle(eng, res, b, r, 8, check_probs=False)
 
 
+@pytest.mark.parametrize("case", ["covar_k8", "packed_k11_topk", "kendall_pipelined"])
+def test_per_level_inputs_equal_concatenated(case):
+    """bod_run_levels (head outputs still split per FPN level, before retinanet_model.py:89-112 concatenates
+    them) gives the bits of bod_run on the concatenated tensors; the same context also still takes the
+    concatenated form."""
+    import torch
+    from gpu_common import engine_config_from_oracle
+    from bayes_od_rc_b200.engine import BayesODEngine
+    kw = dict(covar_k8=dict(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=81),
+              packed_k11_topk=dict(im_h=100, im_w=180, N=6, K=11, g_min=6, g_max=10, box_hi=90., config_id=82, packed_cov=True),
+              kendall_pipelined=dict(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=83))[case]
+    okw = dict(covar_k8={}, packed_k11_topk=dict(cov_layout=2, pre_nms_top_k=150), kendall_pipelined=dict(use_full_covar=False))[case]
+    depth = 3 if case == "kendall_pipelined" else 1
+    spec = synthetic.SceneSpec(**kw)
+    B = 3
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, B))
+    oc = oracle.OracleConfig(**okw)
+    _, ref = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"], emit_probs=False)
+    la = anchors_mod.level_anchor_counts(spec.im_h, spec.im_w)
+    N, A, K = batch["cls"].shape[1:]
+    assert sum(la) == A and any(a % 128 for a in la)          # level boundaries do not fall on tile boundaries
+    eng = BayesODEngine(B, N, A, K, engine_config_from_oracle(oc, level_anchors=tuple(la), pipeline_depth=depth))
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()   # noqa: E731
+    cuts = np.cumsum([0] + la)
+    split = lambda x: [dev(x[:, :, cuts[l]:cuts[l + 1]]) for l in range(len(la))]   # noqa: E731
+    cls_l, box_l, cov_l = split(batch["cls"]), split(batch["box"]), split(batch["cov"])
+    anc, cnt = dev(batch["anchors"]), dev(batch["counts"])
+    torch.cuda.synchronize()
+    keys = ("num_dets", "num_survivors", "means", "covs", "cat_param", "cat_count", "nms_indices", "centre_anchor_idx",
+            "centre_scores")
+    for _ in range(depth + 1):
+        eng.run_levels(cls_l, box_l, cov_l, anc, cnt)
+    res = eng.fetch()
+    for k in keys:
+        assert_bit_equal(getattr(res, k), getattr(ref, k), f"per level: {k}")
+    r = oracle.run_image(oc, batch["cls"][1], batch["box"][1], batch["cov"][1], batch["anchors"], batch["counts"][1])
+    compare_image_with_oracle(eng, res, 1, r, K, check_probs=False)
+    eng.run(dev(batch["cls"]), dev(batch["box"]), dev(batch["cov"]), anc, cnt)      # concatenated, same context
+    res2 = eng.fetch()
+    for k in keys:
+        assert_bit_equal(getattr(res2, k), getattr(ref, k), f"concatenated on a level context: {k}")
+
+
 def test_full_size_batch_properties():
     """The bench workload at full size (8 BDD-shape images, N = 10, K = 11, Philox sampler) through
     size-independent properties: survivors ascending, centres unique and in selection-score order, every
