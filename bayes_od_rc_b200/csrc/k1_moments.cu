@@ -164,10 +164,15 @@ BOD_DEVINL bool philox_counts(const float (&p)[K], uint32_t anchor, uint32_t ima
 // tile of the per-image grid -> level, first local anchor of the tile, anchors of the level
 struct TileRef { int level, a0, A_l, anchor0, rows, row; };   // rows: anchors per sample of the level's tensor; row: the tile's first row in it
 BOD_DEVINL TileRef tile_ref(const LevelTable& lv, int tile) {
+    TileRef r;
+    if (lv.n == 1) {                                     // one tensor per kind (uniform branch)
+        r.level = 0; r.a0 = tile * kTileAnchors; r.A_l = lv.count[0]; r.anchor0 = r.a0;
+        r.rows = lv.rows[0]; r.row = lv.row0[0] + r.a0;
+        return r;
+    }
     int l = 0;
 #pragma unroll
     for (int i = 1; i < kMaxLevels; ++i) l += (tile >= lv.first_tile[i]) ? 1 : 0;     // entries past n hold INT_MAX
-    TileRef r;
     r.level = l;
     r.a0 = (tile - lv.first_tile[l]) * kTileAnchors;
     r.A_l = lv.count[l];
