@@ -203,6 +203,11 @@ constexpr int kTop1 = 128 / kK3Warps;  // keys every warp lists per round
 constexpr int kTop = 16;              // candidates examined per round
 constexpr int kBatch = 16;            // centres selected per round at most
 constexpr int kExpTab = 129;
+constexpr int kTeamWarps = 4;         // warps that share a round's acceptance work
+
+BOD_DEVINL void team_barrier() {      // named barrier 1: the acceptance team only
+    asm volatile("bar.sync 1, %0;" ::"n"(kTeamWarps * 32) : "memory");
+}
 
 struct K3Smem {
     unsigned long long warp_best[2][32];         // generic kernel scratch
@@ -469,7 +474,7 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
         if (queued) t2k.add(make_key(sc, s));
     }
 
-    long long tA = 0, tB = 0, tC = 0, tL = 0, t0 = 0, t1 = 0, t2c = 0, t3 = 0;
+    long long tA = 0, tB = 0, tC = 0, tL = 0, t0 = 0, t1 = 0, t2c = 0, t3 = 0, tm = 0, tw = 0, tM = 0, tW = 0, tx1 = 0, tx2 = 0, tR = 0, tP = 0;
     int r = 0, rounds = 0;
     while (r < Dmax) {
         if (a.dbg && tid == 0) t0 = clock64();
@@ -485,78 +490,78 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
             }
             if (lane == 0) sm.bound_w[warp] = bound;
         }
+        if (tid < kTop) { sm.cand_key[tid] = 0ull; sm.rowmask[tid] = 0u; }     // filled by the acceptance team below
+        if (a.dbg && tid == 0) tm = clock64();
         __syncthreads();
-        if (warp == 0) {
-            // merge the kK3Warps sorted lists (lane l: four consecutive entries of one warp's list; a lane's head
-            // can only surface after the larger entries of the same list were popped), then accept centres in
-            // key order (see header)
-            static_assert(kK3Warps * kTop1 == 128 && kTop1 % 4 == 0, "four list entries of one warp per lane of warp 0");
-            unsigned long long h[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = (&sm.top_w[0][0])[4 * lane + i];
-            unsigned long long G = (lane < kK3Warps) ? sm.bound_w[lane] : 0ull;
-            G = warp_max_u64(G);
-            unsigned long long t2[kTop];
-#pragma unroll
-            for (int q = 0; q < kTop; ++q) {
-                const unsigned long long mx = warp_max_u64(h[0]);
-                t2[q] = (mx >= G) ? mx : 0ull;                            // below G an untracked key might outrank it
-                if (mx != 0ull && h[0] == mx) { h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = 0ull; }
-            }
-            // lane p < kTop publishes candidate p
-            unsigned long long myk = t2[0];
-#pragma unroll
-            for (int q = 1; q < kTop; ++q) myk = (lane == q) ? t2[q] : myk;
-            if (lane >= kTop) myk = 0ull;
-            if (lane < kTop) {
-                sm.cand_key[lane] = myk;
-                if (myk != 0ull) sm.cand_box[lane] = corn[key_index(myk)];
-            }
-            __syncwarp();
-            // pairwise weights among the examined candidates: lane 2q+h does candidate q against candidates
-            // [8h, 8h+8) below q
-            static_assert(kTop == 16, "two lanes per examined candidate");
+        if (a.dbg && tid == 0) tw = clock64();
+        if (warp < kTeamWarps) {
+            // ---- acceptance, by the first four warps (named barrier 1 among them) ----
+            // (i) the block's top-kTop keys: thread t ranks entry t of the kK3Warps x kTop1 = 128 listed keys
+            // by counting the larger ones; G = the largest cut of any warp's list: below it an untracked key
+            // might outrank a listed one, so such entries are dropped (validity is a prefix of the order)
+            static_assert(kK3Warps * kTop1 == kTeamWarps * 32, "one listed key per thread of the acceptance team");
+            const unsigned long long* flat = &sm.top_w[0][0];
             {
-                const int q = lane >> 1, i0 = (lane & 1) * 8;
-                const unsigned long long kq = sm.cand_key[q];
-                uint32_t bits = 0u, hot = 0u;
-                float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kq != 0ull) {
-                    bq = sm.cand_box[q];
-                    const int i1 = min(q, i0 + 8);
-                    // most pairs do not intersect at all (weight exactly 1): find the few that do with the lean
-                    // test first, so that the division + exp below runs once per intersecting pair, not per pair
-                    for (int i = i0; i < i1; ++i) {
-                        const float4 bi = sm.cand_box[i];
-                        const float dx = fminf(bq.w, bi.w) - fmaxf(bq.y, bi.y);
-                        const float dy = fminf(bq.z, bi.z) - fmaxf(bq.x, bi.x);
-                        if ((dx > 0.0f && dy > 0.0f) || sm.malformed != 0) hot |= 1u << i;
-                        else sm.wpair[q][i] = 1.0f;
+                unsigned long long G = (lane < kK3Warps) ? sm.bound_w[lane] : 0ull;
+                G = warp_max_u64(G);
+                const unsigned long long key = flat[tid];
+                if (key != 0ull && key >= G) {
+                    // the listed scores are non-negative floats in practice, so the high words alone decide almost
+                    // every comparison: count on 32-bit words, resolve equal scores (ties) on the index words
+                    const uint32_t khi = (uint32_t)(key >> 32), klo = (uint32_t)key;
+                    const uint4* f4 = reinterpret_cast<const uint4*>(flat);        // (lo, hi, lo, hi) of two keys
+                    int r0 = 0, r1 = 0;
+#pragma unroll 16
+                    for (int j = 0; j < kTeamWarps * 16; ++j) {
+                        const uint4 kk = f4[j];
+                        r0 += (kk.y > khi) || (kk.y == khi && kk.x > klo);
+                        r1 += (kk.w > khi) || (kk.w == khi && kk.z > klo);
                     }
+                    const int rank = r0 + r1;
+                    if (rank < kTop) { sm.cand_key[rank] = key; sm.cand_box[rank] = corn[key_index(key)]; }
                 }
-                while (__any_sync(0xffffffffu, hot != 0u)) {
-                    if (hot) {
-                        const int i = __ffs(hot) - 1;
-                        hot &= hot - 1;
-                        const float w = nms_weight_fast(tf_iou(bq, sm.cand_box[i]), C.scale, C.is_soft, C.thr, sm.exp_tab);
-                        sm.wpair[q][i] = w;
-                        if (w != 1.0f) bits |= 1u << i;
-                    }
-                }
-                bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-                if ((lane & 1) == 0) sm.rowmask[q] = bits;
             }
-            __syncwarp();
+            team_barrier();
+            if (a.dbg && tid == 0) tx1 = clock64();
+            // (ii) pairwise weights among the examined candidates, one pair (q, i), i < q, per thread.  Most pairs
+            // do not intersect at all (weight exactly 1): the division + exp runs only for those that do
+            if (tid < kTop * (kTop - 1) / 2) {
+                int q = 1, base = 0;
+                while (base + q <= tid) { base += q; ++q; }
+                const int i = tid - base;
+                if (sm.cand_key[q] != 0ull) {                             // then candidate i < q exists too
+                    const float4 bq = sm.cand_box[q], bi = sm.cand_box[i];
+                    const float dx = fminf(bq.w, bi.w) - fmaxf(bq.y, bi.y);
+                    const float dy = fminf(bq.z, bi.z) - fmaxf(bq.x, bi.x);
+                    float w = 1.0f;
+                    if ((dx > 0.0f && dy > 0.0f) || sm.malformed != 0)
+                        w = nms_weight_fast(tf_iou(bq, bi), C.scale, C.is_soft, C.thr, sm.exp_tab);
+                    sm.wpair[q][i] = w;
+                    if (w != 1.0f) atomicOr(&sm.rowmask[q], 1u << i);
+                }
+            }
+            team_barrier();
+            if (a.dbg && tid == 0) tx2 = clock64();
+        }
+        if (warp == 0) {
+            // (iii) accept centres in key order (see header); every lane walks, lane p < kTop owns candidate p
+            const unsigned long long myk = (lane < kTop) ? sm.cand_key[lane] : 0ull;
+            const int nvalid = __popc(__ballot_sync(0xffffffffu, myk != 0ull));      // candidates are a prefix
+            // everything the walk reads is fetched up front; only the accept / skip decisions are sequential
+            float sqv[kTop];
+            uint32_t rowv[kTop];
+#pragma unroll
+            for (int q = 0; q < kTop; ++q) { sqv[q] = key_score(sm.cand_key[q]); rowv[q] = sm.rowmask[q]; }
             int m = 0;
             uint32_t acc = 0u;                                           // accepted candidates (bit q)
-            if (t2[0] != 0ull) {
+            if (nvalid > 0) {
                 acc = 1u; m = 1;
                 float ub_max = -INFINITY;                                // best score a skipped candidate can still reach
 #pragma unroll
                 for (int q = 1; q < kTop; ++q) {
-                    if (t2[q] == 0ull || r + m >= Dmax || m >= kBatch) break;
-                    const float sq = key_score(t2[q]);
-                    const uint32_t hit = sm.rowmask[q] & acc;            // accepted centres it overlaps
+                    if (q >= nvalid || r + m >= Dmax || m >= kBatch) break;
+                    const float sq = sqv[q];
+                    const uint32_t hit = rowv[q] & acc;                  // accepted centres it overlaps
                     if (hit == 0u) {
                         if (!(sq > ub_max)) break;                       // a skipped candidate might still outrank it
                         acc |= 1u << q; ++m;
@@ -577,7 +582,6 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
                 ucur[x] = -INFINITY;                                     // leaves the queue
                 a.nms_idx[(size_t)b * Dmax + pos] = x;
                 a.nms_score[(size_t)b * Dmax + pos] = key_score(myk);
-                a.centre_anchor[(size_t)b * Dmax + pos] = a.surv_anchor[(size_t)b * a.capacity + x];
             }
             if (lane == 0) sm.batch_n = m;
         }
@@ -659,17 +663,20 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
             }
         }
         __syncwarp();
-        if (a.dbg && tid == 0) { t3 = clock64(); tC += t1 - t0; tA += t2c - t1; tB += t3 - t2c; tL += cnt; }
+        if (a.dbg && tid == 0) { t3 = clock64(); tC += t1 - tx2; tM += tm - t0; tW += tw - tm; tR += tx1 - tw; tP += tx2 - tx1; tA += t2c - t1; tB += t3 - t2c; tL += cnt; }
         r += m;
         ++rounds;
         // no barrier here: the warp lists of the next round go to sm.top_w, which warp 0 finished reading
         // before the batch barrier; seg_n / list / wl are next written after the top-of-round barrier
     }
     if (a.dbg && tid == 0) {
-        a.dbg[b * 8 + 0] = tA; a.dbg[b * 8 + 1] = tB; a.dbg[b * 8 + 2] = tL; a.dbg[b * 8 + 3] = rounds; a.dbg[b * 8 + 4] = S;
-        a.dbg[b * 8 + 5] = tC; a.dbg[b * 8 + 6] = r; a.dbg[b * 8 + 7] = psm;
+        a.dbg[b * 8 + 0] = tA; a.dbg[b * 8 + 1] = tB; a.dbg[b * 8 + 2] = tR; a.dbg[b * 8 + 3] = rounds; a.dbg[b * 8 + 4] = tP; (void)tL;
+        a.dbg[b * 8 + 5] = tC; a.dbg[b * 8 + 6] = tM; a.dbg[b * 8 + 7] = tW;
     }
     if (tid == 0) a.num_dets[b] = r;
+    __syncthreads();                                         // sel_key of the last round
+    for (int d = tid; d < r; d += kK3Threads)               // off the rounds' critical path: one gather at the end
+        a.centre_anchor[(size_t)b * Dmax + d] = a.surv_anchor[(size_t)b * a.capacity + key_index(sm.sel_key[d])];
     for (int d = r + tid; d < Dmax; d += kK3Threads) {       // padding rows
         a.nms_idx[(size_t)b * Dmax + d] = -1;
         a.centre_anchor[(size_t)b * Dmax + d] = -1;

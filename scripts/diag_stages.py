@@ -17,6 +17,10 @@ if os.environ.get('BOD_K3_DEBUG'):
     lib=_cabi.load(); lib.bod_debug_k3_counters.argtypes=[C.c_void_p,C.c_void_p]
     print('rc',lib.bod_debug_k3_counters(eng._ctx,out))
     a=np.array(out[:]).reshape(B,8)
-    print('rounds',a[:8,3],'dets',a[:8,6],'S',a[:8,4])
-    print('per round cycles: C',(a[:,5]/a[:,3]).round(0)[:8],'A',(a[:,0]/a[:,3]).round(0)[:8],'B',(a[:,1]/a[:,3]).round(0)[:8],'list/round',(a[:,2]/a[:,3]).round(1)[:8])
-    print('total cycles per image (max)', (a[:,0]+a[:,1]+a[:,5]).max(), 'mean', (a[:,0]+a[:,1]+a[:,5]).mean())
+    r=a[:,3]
+    names=['pass A','pass B','rank','rounds','pairwise','walk+writes','warp merge','wait at barrier']
+    print('rounds',a[:8,3])
+    tot=sum(a[:,i] for i in (0,1,2,4,5,6,7))
+    for i in (6,7,2,4,5,0,1):
+        print('%-16s per round %s share %.2f' % (names[i], (a[:,i]/r).round(0)[:8], a[:,i].sum()/tot.sum()))
+    print('total cycles per image (max)', tot.max(), 'mean', tot.mean())
