@@ -40,16 +40,19 @@ def test_config_struct_layout_matches_header():
     #include <stdio.h>
     #include <stddef.h>
     #include "bayesod.h"
-    int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(bod_config), offsetof(bod_config, seed),
-        offsetof(bod_config, image_id_base), offsetof(bod_config, anchor_mode), offsetof(bod_config, emit_probs)); return 0; }
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(bod_config), offsetof(bod_config, seed),
+        offsetof(bod_config, image_id_base), offsetof(bod_config, anchor_mode), offsetof(bod_config, emit_probs),
+        offsetof(bod_config, pipeline_depth), offsetof(bod_config, level_anchors), sizeof(bod_val_scaling)); return 0; }
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(probe)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")], check=True)
         out = subprocess.run([os.path.join(d, "p")], check=True, capture_output=True, text=True).stdout.split()
+    from bayes_od_rc_b200._cabi import BodValScaling
     got = [ctypes.sizeof(BodConfig), BodConfig.seed.offset, BodConfig.image_id_base.offset, BodConfig.anchor_mode.offset,
-           BodConfig.emit_probs.offset]
+           BodConfig.emit_probs.offset, BodConfig.pipeline_depth.offset, BodConfig.level_anchors.offset,
+           ctypes.sizeof(BodValScaling)]
     assert got == [int(x) for x in out]
 
 
@@ -67,6 +70,31 @@ def test_no_cpu_fallback():
     with pytest.raises(BodError):
         fast.bayes_od_clustering(np.ones((4, 8), np.float32), np.zeros((4, 4, 1), np.float32),
                                  np.tile(np.eye(4, dtype=np.float32), (4, 1, 1)), np.array([0]), np.ones((4, 4), np.float32), 0.5)
+
+
+def test_create_rejects_bad_configs_before_touching_the_device():
+    """Argument validation of bod_create (runs without a GPU: the checks come before cudaSetDevice)."""
+    from bayes_od_rc_b200 import _cabi
+    from bayes_od_rc_b200.engine import BayesODConfig
+    lib = _cabi.load()
+
+    def create(B=1, N=10, A=1161, K=8, **kw):
+        cfg = BayesODConfig(**kw).to_c(B, N, A, K)
+        ctx = ctypes.c_void_p()
+        rc = lib.bod_create(ctypes.byref(ctx), 0, ctypes.byref(cfg))
+        if rc == 0:
+            lib.bod_destroy(ctx)
+        return rc, (lib.bod_last_error(None) or b"").decode()
+
+    for kw, what in [(dict(B=0), "B must"), (dict(N=0), "N (mc"), (dict(K=1), "unsupported K"), (dict(K=14), "unsupported K"),
+                     (dict(max_output_size=0), "max_output_size"), (dict(max_output_size=256), "max_output_size"),
+                     (dict(iou_threshold=-0.1), "iou_threshold"), (dict(soft_nms_sigma=-1.0), "soft_nms_sigma"),
+                     (dict(num_draws=0), "num_draws"), (dict(pre_nms_top_k=-1), "pre_nms_top_k"),
+                     (dict(level_anchors=(1000, 100)), "do not sum"), (dict(level_anchors=(1161, 0)), "positive"),
+                     (dict(anchor_mode=_cabi.ANCHORS_GENERATE, im_h=64, im_w=64), "anchor_mode=GENERATE")]:
+        pos = {k: kw.pop(k) for k in ("B", "N", "K") if k in kw}
+        rc, msg = create(**pos, **kw)
+        assert rc == -1 and what in msg, (kw, rc, msg)
 
 
 def test_product_never_imports_oracle():
