@@ -19,19 +19,15 @@
 // popped now (t_i times the weights of the boxes selected since, newest first).
 // u_i <= t_i (scores are >= 0), so the candidate TF selects next is
 // x = argmax_i (u_i, -i); on the way TF pops, updates and re-pushes exactly the
-// candidates whose stale key (t_i, -i) exceeds (u_x, -x).  One ROUND per selected
-// box therefore needs one block-wide arg-max plus one pass in which every
-// candidate tests the new box; the multiplication order inside each candidate
-// (newest selected first within an update epoch) is kept by recomputing u_i from
-// t_i over the candidate's pending-selection bitmask.  Weights equal to exactly
+// candidates whose stale key (t_i, -i) exceeds (u_x, -x).  Weights equal to exactly
 // 1.0f (IoU 0, the overwhelmingly common case) leave a score bit-identical, so
-// boxes that do not overlap the new centre need no arithmetic at all.
+// boxes that do not overlap a new centre need no arithmetic at all.
 //
-// Fast kernel (S <= kFastS): corners and current scores live in shared memory;
-// a round is (A) one pass of cheap overlap tests that also folds the arg-max of
-// the untouched candidates, (B) a dense pass over the compacted list of
-// overlapping candidates (IoUs, exp, membership bits).  Two block barriers per
-// round.  One CTA per image (images are independent); B CTAs run concurrently.
+// Three kernels-in-one, chosen per image by its survivor count S:
+//   S <= shared-memory pool (~7.4 k): the fast path below, every per-candidate array in shared memory;
+//   S <= 65 535: the same code with the per-candidate arrays in (L2-resident) global scratch rows;
+//   beyond: k3_generic, the literal one-round-per-selection formulation (list entries hold 16-bit indices).
+// One CTA per image (images are independent); B CTAs run concurrently.
 #include "bod_common.cuh"
 #include "bod_kernels.h"
 
@@ -183,19 +179,23 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
 // first comparison of its next walk.
 // (3) The block-wide top-kTop of the NEXT round is folded into the same passes:
 // every thread tracks the best two keys it has seen (untouched candidates in
-// pass A, updated ones in pass B); warps merge by popping heads (REDUX), warp 0
-// merges the warps' lists.  A list is cut where a thread runs out of tracked
+// pass A, updated ones in pass B); warps merge by popping heads (REDUX) into a
+// list of kTop1 keys each.  A list is cut where a thread runs out of tracked
 // keys (its third best is unknown), and the acceptance walk stops at the largest
 // such cut -- fewer centres in that round, never a wrong one.
 // (4) The expensive arithmetic runs one (candidate, centre) PAIR per thread.
-// A round is: acceptance (warp 0) | pass A: one lean geometric overlap test of
-// every candidate against the batch, overlapping pairs compacted into per-warp
-// list segments | pass B1: IoU + exp for every listed pair, and the pair's
-// cluster-membership bit (bbox_iou_vuvu > threshold, inference_utils.py:316) |
-// pass B2: the epoch walk of every listed candidate over its precomputed
-// weights.  Four block barriers per round, no global memory on the critical
-// path: the first psm pending weights of every candidate live in shared memory
-// (psm is chosen per image from its survivor count), the rest spill to global.
+// A round is: acceptance (a team of four warps behind a named barrier: rank the
+// 128 listed keys by counting, one pair of examined candidates per thread, then
+// warp 0 walks them) | pass A: one lean overlap test of every survivor against
+// the batch (a superset filter: the centre grown by 2 px), overlapping pairs
+// compacted into the warp's own list segment | pass B1: IoU + exp for every
+// listed pair, and the pair's cluster-membership bit (bbox_iou_vuvu > threshold,
+// inference_utils.py:316) | pass B2: the epoch walk of every listed candidate
+// over its precomputed weights.  A survivor is scanned by the same thread every
+// round, so B1 / B2 work on the warp's own segment without a block barrier: two
+// block barriers per round, no global memory on the critical path: the first
+// psm pending weights of every candidate live in shared memory (psm is chosen
+// per image from its survivor count), the rest spill to global rows.
 // ---------------------------------------------------------------------------
 constexpr int kK3Warps = kK3Threads / 32;
 constexpr int kSegCap = 4096 / kK3Warps; // (candidate, centre) pairs listed per warp and round
