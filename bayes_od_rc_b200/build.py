@@ -55,6 +55,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJDIR, unit.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
+            extra = extra + (os.environ.get("BOD_EXTRA_NVCC_" + unit.split(".")[0].upper(), "").split())
             cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             if verbose or r.returncode:

@@ -78,6 +78,7 @@ struct bod_ctx {
     bool host_copy_all = false;       // BOD_HOST_COPY_ALL: never read box/cov in place from pinned host memory
     int k1_debug = 0;                 // BOD_K1_DEBUG (diagnostics)
     long long* k3_dbg = nullptr;      // BOD_K3_DEBUG (diagnostics): [B][8] cycle counters
+    bool k2_on_tail = true;           // pipelined contexts: K2 rides with the tail (see run_range); BOD_K2_TAIL=0 keeps it on the head
     int k3_seg_cap = -1, k3_psm_max = -1;   // BOD_K3_SEGCAP / BOD_K3_PSM_MAX (tests: reach the overflow paths on small inputs)
 };
 
@@ -255,6 +256,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
     if (const char* d = getenv("BOD_K1_DEBUG")) c->k1_debug = atoi(d);
     c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
+    if (const char* d = getenv("BOD_K2_TAIL")) c->k2_on_tail = atoi(d) != 0;
     if (const char* d = getenv("BOD_K3_SEGCAP")) { int v = atoi(d); if (v >= 0) c->k3_seg_cap = v; }
     if (const char* d = getenv("BOD_K3_PSM_MAX")) c->k3_psm_max = atoi(d);
     if (getenv("BOD_K3_DEBUG")) { cudaMalloc(&c->k3_dbg, (size_t)B * 8 * sizeof(long long)); cudaMemset(c->k3_dbg, 0, (size_t)B * 8 * sizeof(long long)); }
@@ -308,6 +310,10 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     const size_t slots = (size_t)c->tiles * kTileAnchors;
     const int cw = cov_width(g.cov_layout);
 
+    // K2 with the tail: the head stream then carries K1 + scan only, so the next run's K1 starts as soon as
+    // this one's logits are consumed (not with the pre-NMS filter: its scratch is shared between lanes)
+    const bool k2_tail = (hs != ts) && c->k2_on_tail && !c->prefilter;
+    if (k2_tail && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));   // the lane's slot lists are still being read
     if (record) CU(c, cudaEventRecord(c->ev[0], hs));
     K1Args k1{};
     k1.lv = lv; k1.counts_in = counts;
@@ -318,6 +324,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     k1.B = nb; k1.N = g.N; k1.A = g.A; k1.K = g.K; k1.tiles = c->tiles;
     k1.num_draws = g.num_draws; k1.seed = g.seed; k1.image_id_base = g.image_id_base + (uint32_t)b0;
     k1.debug = c->k1_debug;
+    k1.leave_room = (hs != ts) ? 1 : 0;
     k1.ticket = c->ticket; k1.ticket_base = c->ticket_next;
     c->ticket_next += k1_tickets_per_launch(k1);           // K1 launches of a context never overlap each other
     CU(c, launch_k1(k1, hs));
@@ -354,8 +361,14 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     if (record) CU(c, cudaEventRecord(c->ev[2], hs));
 
     // K2 overwrites what the previous tail on this lane (two runs ago) reads
-    // (K2 stays on the head stream: with it on the tail, the tail becomes the longer leg -- measured)
-    if (hs != ts && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
+    cudaStream_t k2s = hs;
+    if (k2_tail) {
+        CU(c, cudaEventRecord(L.head_done, hs));
+        CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));
+        k2s = ts;
+    } else if (hs != ts && L.tail_pending) {
+        CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
+    }
     K2Args k2{};
     k2.lv = lv; k2.anchors = anchors;
     if (!cw) for (int l = 0; l < k2.lv.n; ++l) k2.lv.cov[l] = nullptr;
@@ -372,10 +385,10 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
                          g.dirichlet_prior != BOD_PRIOR_NONE) ? 1 : 0;
     k2.isotropic_variance = g.isotropic_variance; k2.scale_v = g.scale_v; k2.scale_u = g.scale_u;
     k2.anchor_mode = g.anchor_mode; k2.im_h = g.im_h; k2.im_w = g.im_w;
-    CU(c, launch_k2(k2, hs));
-    if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, hs)); ++launches; }
-    if (record) CU(c, cudaEventRecord(c->ev[3], hs));
-    if (hs != ts) {
+    CU(c, launch_k2(k2, k2s));
+    if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, k2s)); ++launches; }
+    if (record) CU(c, cudaEventRecord(c->ev[3], k2s));
+    if (hs != ts && !k2_tail) {
         CU(c, cudaEventRecord(L.head_done, hs));
         CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));
     }

@@ -37,6 +37,7 @@ struct K1Args {
     uint64_t seed;
     uint32_t image_id_base;
     int debug;               // diagnostics only: 1 = skip sampler/compaction, 2 = also skip the softmax
+    int leave_room;          // pipelined context: size the ring so that other stages' CTAs fit beside K1's
     uint32_t* ticket;        // dynamic tile scheduler: global ticket counter (never reset) ...
     uint32_t ticket_base;    // ... and its value when this launch starts
 };

@@ -343,7 +343,13 @@ constexpr int kConsumerWarps = kTileAnchors / 32;
 constexpr int kPipeCtasPerSM = 6;   // resident CTAs per SM: their finalise phases overlap each other's streaming
 
 template <int K>
-__global__ void __launch_bounds__(kTileAnchors + 32, kPipeCtasPerSM)
+// Register cap of the pipeline kernel: 65536 / (MINBLOCKS * 160) -> 56 per thread.  Six CTAs of 56
+// registers leave ~11.7 k registers per SM, enough for one fusion (K4) CTA to run beside them in a
+// pipelined context; at 64 the kernel is ~1 % faster alone and the pipelined step ~2 % slower (measured).
+#ifndef BOD_K1_MINBLOCKS
+#define BOD_K1_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(kTileAnchors + 32, BOD_K1_MINBLOCKS)
 k1_moments_pipe_kernel(K1Args a, int NS) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
@@ -544,7 +550,11 @@ static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     cudaError_t e;
     if (aligned) {
         // persistent pipeline: kPipeCtasPerSM CTAs per SM, each with a ring of NS one-sample slabs
-        int NS = (int)(((216u * 1024u) / k1_ctas_per_sm() - 1024u) / slab);
+        // ring depth: all the shared memory of the SM when K1 runs alone; in a pipelined context ~56 KB per SM
+        // are left for the posterior / fusion CTAs that run beside it (one of each fits)
+        const unsigned budget = a.leave_room ? 176u * 1024u : 216u * 1024u;
+        int NS = (int)((budget / k1_ctas_per_sm() - 1024u - (a.leave_room ? 1792u : 0u)) / slab);
+        if (const char* e2 = getenv("BOD_K1_NS")) { const int x = atoi(e2); if (x >= 2 && x < NS) NS = x; }   // experiment: shallower ring
         if (NS > kMaxStages) NS = kMaxStages;
         if (NS < 2) NS = 2;
         const size_t ring = (size_t)NS * slab;

@@ -286,8 +286,11 @@ constexpr int kK2Threads = 128;
 // (retinanet_model.py:110): rows of concat(x[4:], reverse(x)) reshaped 4x4.
 __device__ __constant__ int kPackedOf[16] = {4, -1, -1, -1, 8, 9, -1, -1, 7, 6, 5, -1, 3, 2, 1, 0};
 
+#ifndef BOD_K2_MINBLOCKS
+#define BOD_K2_MINBLOCKS 5
+#endif
 template <int K>
-__global__ void __launch_bounds__(kK2Threads)
+__global__ void __launch_bounds__(kK2Threads, BOD_K2_MINBLOCKS)
 k2_posterior_kernel(K2Args a, AnchorLevels L) {
     extern __shared__ float sbox[];          // decoded boxes [N][4][kK2Threads]
     __shared__ int chunk_first[129];         // prefix of 128-survivor chunks over the images of the batch

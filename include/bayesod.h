@@ -89,13 +89,16 @@ typedef struct bod_config {
     int32_t  emit_probs;         /* keep the [B,A,K] mean class probabilities (parity)     */
     int32_t  pipeline_depth;     /* 0/1: every bod_run is issued whole, in order, on the
                                     caller's stream.  L = 2..8: L sets of buffers (lanes);
-                                    run i+1 streams its logits (K1, scan, K2) on the context's
-                                    own stream while runs i, i-1, .. are still selecting centres
-                                    and fusing (soft-NMS, K4), each on its lane's own stream.
-                                    2 is enough once a batch fills the GPU (soft-NMS holds one
-                                    SM per image); small batches want more lanes.  The caller's
-                                    stream then only waits for the part that reads the inputs;
-                                    results are complete at bod_fetch or after bod_wait_results */
+                                    run i+1 streams its logits (K1, scan) on the context's own
+                                    stream while runs i, i-1, .. are still computing posteriors,
+                                    selecting centres and fusing (K2, soft-NMS, K4), each on its
+                                    lane's own stream.  3-4 lanes are enough once a batch fills
+                                    the GPU (soft-NMS holds one SM per image); small batches want
+                                    more.  The caller's stream then only waits until the logits
+                                    have been consumed: `box`, `cov` and `anchors` of run i must
+                                    stay untouched until run i's results are complete (bod_fetch
+                                    or bod_wait_results), i.e. a streaming producer keeps L sets
+                                    of input buffers in flight                                    */
     int32_t  n_levels;           /* 0/1: the head outputs come as one tensor per kind.  2..8:
                                     bod_run_levels may hand them over per FPN level, i.e. BEFORE
                                     the tf.concat(axis=1) of retinanet_model.py:89-112; level l
