@@ -528,6 +528,7 @@ static int k1_pipe_ctas(const K1Args& a) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* e = getenv("BOD_K1_SMS")) { const int x = atoi(e); if (x >= 1 && x < sms) sms = x; }   // experiment: leave SMs free
     int ctas = k1_ctas_per_sm() * sms;
     if (ctas > a.B * a.tiles) ctas = a.B * a.tiles;
     return ctas;

@@ -320,6 +320,12 @@ def main():
         }
         if serial:
             line["serial"] = serial           # pipeline_depth = 1: whole steps back to back, stage times undisturbed
+            k1_alone = serial["stage_ms"]["moments_filter"]
+            if k1_alone > 0:                  # the same kernel with nothing running beside it (one step at a time)
+                line["roofline"]["alone"] = {"launch_ms": k1_alone, "achieved": round(k1_bytes / (k1_alone * 1e-3) / 1e9, 1),
+                                             "frac": round(k1_bytes / (k1_alone * 1e-3) / 1e9 / peak, 4),
+                                             "note": "pipeline_depth=1; in the timed (pipelined) region the posterior, soft-NMS and "
+                                                     "fusion kernels of earlier steps share the SMs with this launch"}
         if e2e:
             e2e_value = world * B * e2e["steps"] / e2e_seconds
             line["e2e"] = {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(e2e["h2d"]),
