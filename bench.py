@@ -168,6 +168,16 @@ def main():
     from bayes_od_rc_b200.engine import BayesODConfig, BayesODEngine
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    # keep this rank (and the pinned host buffers it will first-touch for the end-to-end leg) on the CPUs /
+    # NUMA node its GPU hangs off: with 8 ranks the host side of the PCIe copies is what limits e2e
+    numa_note = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa_note = f"rank pinned to the GPU's CPU set ({len(os.sched_getaffinity(0))} cpus)"
+    except Exception as e:  # pragma: no cover
+        numa_note = f"cpu affinity not set: {e!r}"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -331,7 +341,7 @@ def main():
             line["e2e"] = {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]), "steps": e2e["steps"],
                            "h2d_copied": int(e2e["h2d_copied"]), "h2d_gathered_in_place": int(e2e["h2d_gathered"]),
-                           "host_input_bytes": int(e2e["host_bytes"]),
+                           "host_input_bytes": int(e2e["host_bytes"]), "host_placement": numa_note,
                            "api": "bod_run_host: pinned host buffers -> padded host result blocks; cls is copied in "
                                   "image chunks overlapped with compute, box/cov rows of the survivors are "
                                   "gathered in place from pinned memory"}
