@@ -433,6 +433,46 @@ def test_random_configurations_bit_exact(seed):
         compare_image_with_oracle(eng, res, b, r, K)
 
 
+@pytest.mark.parametrize("case", [
+    dict(soft_nms_sigma=0.1, max_output_size=255), dict(soft_nms_sigma=1.5, max_output_size=200, iou_threshold=0.3),
+    dict(soft_nms_sigma=0.0, iou_threshold=0.7, max_output_size=255), dict(soft_nms_sigma=0.0, iou_threshold=0.3),
+    dict(soft_nms_sigma=0.5, max_output_size=255, ranking_method="joint_entropy"),
+    dict(soft_nms_sigma=0.25, max_output_size=150, use_full_covar=False, pre_nms_top_k=2000)])
+def test_full_size_image_other_knobs(case):
+    """Full BDD-shape images (S ~ 3000) with NMS settings away from the YAML defaults: long pending lists
+    (small sigma, 255 centres), hard NMS, joint-entropy ranking, pre-NMS top-k."""
+    spec = synthetic.SceneSpec(config_id=60 + len(case), K=8)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, 2))
+    oc = oracle.OracleConfig(**case)
+    eng, res = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], batch["counts"], emit_probs=False)
+    for b in range(2):
+        r = oracle.run_image(oc, batch["cls"][b], batch["box"][b], batch["cov"][b], batch["anchors"], batch["counts"][b],
+                             with_probs=False)
+        assert len(r.keep) > 1000
+        compare_image_with_oracle(eng, res, b, r, 8, check_probs=False)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_validation_random(seed):
+    rng = np.random.default_rng(500 + seed)
+    K = int(rng.choice([2, 4, 8, 11]))
+    spec = synthetic.SceneSpec(im_h=int(rng.integers(64, 200)), im_w=int(rng.integers(96, 330)), N=2, K=K, g_min=2, g_max=9,
+                               box_hi=60., config_id=950 + seed, stray_frac=float(rng.choice([0.0, 0.01])))
+    B = int(rng.integers(1, 4))
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, B, with_counts=False))
+    cls, box = batch["cls"][:, 0], batch["box"][:, 0]
+    ckw = dict(soft_nms_sigma=float(rng.choice([0.0, 0.1, 0.5])), iou_threshold=float(rng.choice([0.3, 0.5])),
+               max_output_size=int(rng.choice([5, 100, 255])))
+    mode = int(rng.integers(0, 3))
+    scaling = None if mode == 0 else (mode, (4., 2., 4., 2.), (float(spec.im_h - 8), float(spec.im_w - 4)), (375., 1242.))
+    okw = dict(ckw, scale_mode=mode)
+    if mode:
+        okw.update(shift=scaling[1], norm_hw=scaling[2], scale_hw=scaling[3])
+    eng, res = _run_validate(cls, box, batch["anchors"], scaling=scaling, **ckw)
+    for b in range(B):
+        _compare_validate(eng, res, b, oracle.val_postprocess(cls[b], box[b], batch["anchors"], **okw), K)
+
+
 def test_full_size_batch_properties():
     """The bench workload at full size (8 BDD-shape images, N = 10, K = 11, Philox sampler) through
     size-independent properties: survivors ascending, centres unique and in selection-score order, every
