@@ -77,6 +77,7 @@ struct bod_ctx {
     int64_t h2d_copied = 0, h2d_mapped_rows = 0, d2h_copied = 0;   // traffic of the last bod_run_host
     bool host_copy_all = false;       // BOD_HOST_COPY_ALL: never read box/cov in place from pinned host memory
     int k1_debug = 0;                 // BOD_K1_DEBUG (diagnostics)
+    int skip_mask = 0;                // BOD_DEBUG_SKIP (diagnostics, results invalid): 1 = no K2, 2 = no soft-NMS, 4 = no K4
     long long* k3_dbg = nullptr;      // BOD_K3_DEBUG (diagnostics): [B][8] cycle counters
     bool k2_on_tail = true;           // pipelined contexts: K2 rides with the tail (see run_range); BOD_K2_TAIL=0 keeps it on the head
     int k3_seg_cap = -1, k3_psm_max = -1;   // BOD_K3_SEGCAP / BOD_K3_PSM_MAX (tests: reach the overflow paths on small inputs)
@@ -255,6 +256,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     for (auto& ev : c->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
     if (const char* d = getenv("BOD_K1_DEBUG")) c->k1_debug = atoi(d);
+    if (const char* d = getenv("BOD_DEBUG_SKIP")) c->skip_mask = atoi(d);
     c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
     if (const char* d = getenv("BOD_K2_TAIL")) c->k2_on_tail = atoi(d) != 0;
     if (const char* d = getenv("BOD_K3_SEGCAP")) { int v = atoi(d); if (v >= 0) c->k3_seg_cap = v; }
@@ -385,7 +387,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
                          g.dirichlet_prior != BOD_PRIOR_NONE) ? 1 : 0;
     k2.isotropic_variance = g.isotropic_variance; k2.scale_v = g.scale_v; k2.scale_u = g.scale_u;
     k2.anchor_mode = g.anchor_mode; k2.im_h = g.im_h; k2.im_w = g.im_w;
-    CU(c, launch_k2(k2, k2s));
+    if (!(c->skip_mask & 1)) CU(c, launch_k2(k2, k2s));
     if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, k2s)); ++launches; }
     if (record) CU(c, cudaEventRecord(c->ev[3], k2s));
     if (hs != ts && !k2_tail) {
@@ -406,7 +408,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     k3.iou_threshold = g.iou_threshold; k3.soft_nms_sigma = g.soft_nms_sigma;
     k3.dbg = c->k3_dbg ? c->k3_dbg + (size_t)b0 * 8 : nullptr;
     k3.seg_cap = c->k3_seg_cap; k3.psm_max = c->k3_psm_max;
-    CU(c, launch_k3(k3, ts));
+    if (!(c->skip_mask & 2)) CU(c, launch_k3(k3, ts));
     if (record) CU(c, cudaEventRecord(c->ev[4], ts));
 
     K4Args k4{};
@@ -416,7 +418,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     k4.out_param = L.out_param + b0 * D * K; k4.out_count = L.out_count + b0 * D * K;
     k4.B = nb; k4.K = g.K; k4.capacity = c->capacity; k4.Dmax = c->Dmax; k4.words = c->words;
     k4.calibration = g.cov_calibration;
-    CU(c, launch_k4(k4, ts));
+    if (!(c->skip_mask & 4)) CU(c, launch_k4(k4, ts));
     if (record) CU(c, cudaEventRecord(c->ev[5], ts));
     if (hs != ts) { CU(c, cudaEventRecord(L.tail_done, ts)); L.tail_pending = true; }
     c->launches += launches + 2;   // + soft-NMS (with the membership bits), K4
