@@ -92,6 +92,9 @@ SYMBOLS = {
     "bod_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "bod_stage_ms_accum": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "bod_last_launch_count": (C.c_int, [C.c_void_p]),
+    "bod_write_results_npy": (C.c_int, [C.POINTER(BodHostResults), C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p,
+                                        C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int32]),
+    "bod_write_npy": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32]),
     "bod_generate_anchors": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

@@ -27,6 +27,7 @@ UNITS = {
     "k4_fusion.cu": ["-fmad=false"],
     "kv_validation.cu": ["-fmad=false"],
     "bod_api.cu": ["-fmad=false"],
+    "bod_io.cu": [],                          # host-only: npy writers
 }
 HEADERS = ["bod_common.cuh", "bod_kernels.h", os.path.join("..", "..", "include", "bayesod.h")]
 

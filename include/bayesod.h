@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BOD_ABI_VERSION 6
+#define BOD_ABI_VERSION 7
 
 typedef enum bod_status {
     BOD_OK            = 0,
@@ -283,6 +283,18 @@ int bod_set_stage_timing(bod_ctx* ctx, int enabled);
 int bod_stage_ms_accum(bod_ctx* ctx, float sum_ms[6], int32_t* runs);
 /* Number of kernels the last bod_run launched. */
 int bod_last_launch_count(const bod_ctx* ctx);
+
+/* Batched result writers (host code): the np.save x 4 that ends every iteration of
+ * run_inference.py's loop (:241-244), for the B images of a fetched result block, on
+ * `nthreads` host threads.  Image b writes <dir>/<sample_ids[b]>.npy in each of the four
+ * directories: means [D,4], covs [D,4,4], cat_param [D,K], cat_count [D,K] (float32,
+ * byte-identical to numpy.save); an image without detections writes the empty
+ * (0,4,1) array four times, as run_inference.py:153-161 does. */
+int bod_write_results_npy(const bod_host_results* res, int32_t B, int32_t Dmax, int32_t K,
+                          const char* mean_dir, const char* cov_dir, const char* cat_param_dir,
+                          const char* cat_count_dir, const char* const* sample_ids, int32_t nthreads);
+/* One float32 array as a .npy file (numpy format 1.0, C order). */
+int bod_write_npy(const char* path, const float* data, const int32_t* shape, int32_t ndim);
 
 /* FPN anchors exactly as fpn_anchor_generator.py:21-59 produces them for levels
  * 3..7, 3 aspect ratios x 3 scales, concatenated P3->P7

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bayesod.h but not exported"
         assert n in _cabi.SYMBOLS, f"{n} has no ctypes prototype"
-    assert lib.bod_abi_version() == 6
+    assert lib.bod_abi_version() == 7
     assert lib.bod_status_string(-5).decode().startswith("more survivors")
 
 
@@ -95,6 +95,40 @@ def test_create_rejects_bad_configs_before_touching_the_device():
         pos = {k: kw.pop(k) for k in ("B", "N", "K") if k in kw}
         rc, msg = create(**pos, **kw)
         assert rc == -1 and what in msg, (kw, rc, msg)
+
+
+def test_npy_writers_are_byte_identical_to_numpy(tmp_path):
+    """bod_write_results_npy vs what run_inference.py:241-244 writes with np.save (no GPU needed)."""
+    from bayes_od_rc_b200 import writers
+    rng = np.random.default_rng(0)
+    B, D, K = 5, 100, 11
+    nd = np.array([100, 0, 7, 1, 63], np.int32)
+    res = dict(num_dets=nd, means=rng.normal(size=(B, D, 4)).astype(np.float32),
+               covs=rng.normal(size=(B, D, 4, 4)).astype(np.float32),
+               cat_param=rng.random((B, D, K)).astype(np.float32), cat_count=rng.random((B, D, K)).astype(np.float32))
+    ids = [f"img_{b:04d}" for b in range(B)]
+    dirs = [str(tmp_path / n) for n in ("mean", "cov", "cat_param", "cat_count")]
+    writers.save_batch(res, ids, *dirs, nthreads=3)
+    for b in range(B):
+        d = int(nd[b])
+        empty = np.zeros((0, 4, 1), np.float32)
+        want = [res["means"][b, :d], res["covs"][b, :d], res["cat_param"][b, :d], res["cat_count"][b, :d]] if d else [empty] * 4
+        for dirname, arr in zip(dirs, want):
+            ref = tmp_path / "ref.npy"
+            np.save(ref, np.ascontiguousarray(arr))
+            got = open(os.path.join(dirname, ids[b] + ".npy"), "rb").read()
+            assert got == open(ref, "rb").read(), (b, dirname)
+            assert np.array_equal(np.load(os.path.join(dirname, ids[b] + ".npy")), arr)
+    from bayes_od_rc_b200._cabi import BodError
+    with pytest.raises(BodError):
+        import ctypes as C
+        from bayes_od_rc_b200 import _cabi
+        r = _cabi.BodHostResults(num_dets=nd.ctypes.data, means=res["means"].ctypes.data, covs=res["covs"].ctypes.data,
+                                 cat_param=res["cat_param"].ctypes.data, cat_count=res["cat_count"].ctypes.data)
+        idp = (C.c_char_p * B)(*[i.encode() for i in ids])
+        rc = _cabi.load().bod_write_results_npy(C.byref(r), B, D, K, b"/nonexistent/a", b"/nonexistent/b", b"/nonexistent/c",
+                                                b"/nonexistent/d", idp, 2)
+        raise BodError(rc, "x") if rc else AssertionError("expected a failure")
 
 
 def test_product_never_imports_oracle():
