@@ -46,6 +46,8 @@ WORKLOADS = {
     "stress_b16_n40_k11": dict(im_h=720, im_w=1280, N=40, K=11, B=16, use_full_covar=True, config_id=5,
                                spec=dict(g_min=80, g_max=120, fg_iou=0.2, fg_logit=1.0, bg_logit_for_fg=0.0, stray_frac=0.02),
                                score_threshold=0.01, pre_nms_top_k=10000),
+    # BASELINE.json config 1 shape on the GPU: one image per call, as run_inference.py drives the path (:68, :137-149)
+    "bdd_covar_b1_k8": dict(im_h=720, im_w=1280, N=10, K=8, B=1, use_full_covar=True, config_id=1),
     "tiny": dict(im_h=192, im_w=320, N=10, K=8, B=4, use_full_covar=True, config_id=9),
 }
 DEFAULT_WORKLOAD = "bdd_covar_b32_k11"
