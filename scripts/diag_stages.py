@@ -6,7 +6,7 @@ K=int(os.environ.get('DIAG_K','11')); B=32
 spec=synthetic.SceneSpec(N=10,K=K,config_id=3)
 batch=synthetic.make_batch(spec,B,device='cuda',with_counts=False)
 A=batch['anchors'].shape[0]
-cfg=BayesODConfig(use_full_covar=True,max_survivors=32768)
+cfg=BayesODConfig(use_full_covar=True,max_survivors=32768,ranking_method=os.environ.get('DIAG_RANK','score'))
 eng=BayesODEngine(B,10,A,K,cfg)
 for i in range(5): eng.run(batch['cls'],batch['box'],batch['cov'],batch['anchors'],None)
 eng.stage_ms_accum()
