@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libbayesod.so")
 
 BOD_OK = 0
+BOD_ERR_STATE = -4
 STATUS_NAMES = {0: "BOD_OK", -1: "BOD_ERR_INVALID", -2: "BOD_ERR_CUDA", -3: "BOD_ERR_NOMEM",
                 -4: "BOD_ERR_STATE", -5: "BOD_ERR_OVERFLOW"}
 
@@ -95,6 +96,13 @@ SYMBOLS = {
     "bod_write_results_npy": (C.c_int, [C.POINTER(BodHostResults), C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p,
                                         C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int32]),
     "bod_write_npy": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32]),
+    "bod_bdd_json_open": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.POINTER(C.c_char_p), C.c_int32]),
+    "bod_bdd_json_append": (C.c_int, [C.c_void_p, C.POINTER(BodHostResults), C.c_int32, C.c_int32, C.c_int32,
+                                      C.POINTER(C.c_char_p)]),
+    "bod_bdd_json_close": (C.c_int, [C.c_void_p]),
+    "bod_write_results_kitti_txt": (C.c_int, [C.POINTER(BodHostResults), C.c_int32, C.c_int32, C.c_int32, C.c_char_p,
+                                              C.POINTER(C.c_char_p), C.c_int32]),
+    "bod_format_float": (C.c_int, [C.c_double, C.c_int32, C.c_char_p, C.c_int32]),
     "bod_generate_anchors": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

@@ -296,6 +296,37 @@ int bod_write_results_npy(const bod_host_results* res, int32_t B, int32_t Dmax, 
 /* One float32 array as a .npy file (numpy format 1.0, C order). */
 int bod_write_npy(const char* path, const float* data, const int32_t* shape, int32_t ndim);
 
+/* BDD / COCO / Pascal predictions.json (host code).  Replaces, for the images of
+ * fetched result blocks, validation_utils.py:183-213 (predictions_to_bdd_format: one
+ * entry per detection whose first-maximum class is < n_categories; "bbox" =
+ * [u_min, v_min, u_max, v_max] of box_utils.vuhw_to_vuvu_np in float32; "score" = that
+ * class probability), run_inference.py:206-212 (final_results_list.extend per image)
+ * and :258-260 (json.dump(..., indent=4, separators=(',', ': '))).  The file is
+ * byte-identical to the reference's: floats are written as Python's float.__repr__
+ * of the binary64 value, strings as json's ensure_ascii encoder writes them.
+ * open -> append once per result block, in dataset order -> close (which terminates
+ * the list; a writer that saw no detection writes "[]").  `res->means` and
+ * `res->cat_param` are read ([B,Dmax,4], [B,Dmax,K]); pass the class block
+ * map_dataset_classes produced when training and test data sets differ. */
+typedef struct bod_json_writer bod_json_writer;
+int bod_bdd_json_open(bod_json_writer** out, const char* path, const char* const* categories, int32_t n_categories);
+int bod_bdd_json_append(bod_json_writer* w, const bod_host_results* res, int32_t B, int32_t Dmax, int32_t K,
+                        const char* const* sample_ids);
+int bod_bdd_json_close(bod_json_writer* w);
+
+/* KITTI label files (host code): <dir>/<sample_ids[b]>.txt for every image of a result
+ * block, byte-identical to run_inference.py:176-201 writing the rows of
+ * validation_utils.py:216-272 (predictions_to_kitti_format) with
+ * np.savetxt(..., newline='\r\n', fmt='%s'): "Car" / "Pedestrian" rows for detections
+ * whose first-maximum class is 0 / 1, "-1 -1 -10 u_min v_min u_max v_max -10 x7 score",
+ * numbers as str(numpy.float32); an image without such a detection gets an empty file. */
+int bod_write_results_kitti_txt(const bod_host_results* res, int32_t B, int32_t Dmax, int32_t K, const char* dir,
+                                const char* const* sample_ids, int32_t nthreads);
+/* The two number formats the text writers use, exposed for tests: style 0 = Python
+ * float.__repr__ (json spellings for non-finite values), style 1 = str(numpy.float32(value)).
+ * Returns the length written (NUL-terminated) or BOD_ERR_INVALID if `cap` is too small. */
+int bod_format_float(double value, int32_t style, char* out, int32_t cap);
+
 /* FPN anchors exactly as fpn_anchor_generator.py:21-59 produces them for levels
  * 3..7, 3 aspect ratios x 3 scales, concatenated P3->P7
  * (bdd_dataset_handler.py:161-186).  Writes [A,4] to device memory `anchors`

@@ -131,6 +131,76 @@ def test_npy_writers_are_byte_identical_to_numpy(tmp_path):
         raise BodError(rc, "x") if rc else AssertionError("expected a failure")
 
 
+def test_bdd_json_writer_matches_reference_bytes(tmp_path):
+    """BddJsonWriter vs predictions_to_bdd_format + json.dump of the reference, executed verbatim when the
+    fixture was minted (tests/golden/make_writer_golden.py): same bytes."""
+    from bayes_od_rc_b200 import writers
+    g = np.load(os.path.join(ROOT, "tests", "golden", "writers_bdd.npz"))
+    path = tmp_path / "predictions.json"
+    with writers.BddJsonWriter(path, [str(c) for c in g["categories"]]) as w:
+        for i in range(int(g["n_blocks"])):
+            w.append(dict(num_dets=g[f"num_dets{i}"], means=g[f"means{i}"], cat_param=g[f"cat_param{i}"]),
+                     [str(x) for x in g[f"ids{i}"]])
+    got = open(path, "rb").read()
+    assert got == g["json"].tobytes()
+    import json
+    assert len(json.loads(got)) == 24
+    with writers.BddJsonWriter(path, ["car"]):
+        pass
+    assert open(path, "rb").read() == g["json_empty"].tobytes() == b"[]"
+    # a class block override (map_dataset_classes output) with fewer columns
+    with writers.BddJsonWriter(path, ["car", "person"]) as w:
+        w.append(dict(num_dets=g["num_dets0"], means=g["means0"], cat_param=g["cat_param0"]), [str(x) for x in g["ids0"]],
+                 cat_param=np.ascontiguousarray(g["cat_param0"][:, :, :3]))
+    assert all(e["category"] in ("car", "person") for e in json.loads(open(path).read()))
+    from bayes_od_rc_b200._cabi import BodError
+    with pytest.raises(BodError):
+        writers.BddJsonWriter("/nonexistent/dir/predictions.json", ["car"])
+
+
+def test_kitti_txt_writer_matches_reference_bytes(tmp_path):
+    """save_kitti_txt_batch vs predictions_to_kitti_format + np.savetxt(fmt='%s', newline='\\r\\n') of the reference."""
+    from bayes_od_rc_b200 import writers
+    g = np.load(os.path.join(ROOT, "tests", "golden", "writers_kitti.npz"))
+    ids = [str(x) for x in g["ids"]]
+    writers.save_kitti_txt_batch(dict(num_dets=g["num_dets"], means=g["means"], cat_param=g["cat_param"]), ids,
+                                 tmp_path / "data", nthreads=3)
+    for b, i in enumerate(ids):
+        assert open(tmp_path / "data" / (i + ".txt"), "rb").read() == g[f"txt{b}"].tobytes(), i
+    assert len(g["txt0"]) > 0 and len(g["txt1"]) == 0
+
+
+def test_float_formats_match_python_and_numpy():
+    """The two number formats of the text writers against the interpreters themselves: float.__repr__ (json) and
+    str(numpy.float32) (np.savetxt of the KITTI rows), on random bit patterns and the layout thresholds."""
+    import ctypes as C
+    from bayes_od_rc_b200 import _cabi
+    lib = _cabi.load()
+    buf = C.create_string_buffer(64)
+
+    def fmt(v, style):
+        n = lib.bod_format_float(float(v), style, buf, 64)
+        assert n > 0
+        return buf.value.decode()
+
+    rng = np.random.default_rng(5)
+    f32 = rng.integers(0, 2 ** 32, 20000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    f32 = np.concatenate([f32[np.isfinite(f32)], np.float32([0.0, -0.0, 1e-4, 9.9999e-5, 1e16, 9.9999e15, 1.0, 100.0, 0.1,
+                                                           16777216.0, 1e-45, 3.4028235e38, 5e-324, 1e15, 123456.79])])
+    for v in f32:
+        assert fmt(v, 1) == str(v), (v, fmt(v, 1))
+        assert fmt(v, 0) == repr(float(v)), (v, fmt(v, 0))
+    f64 = rng.integers(0, 2 ** 63, 20000, dtype=np.uint64).view(np.float64)
+    f64 = np.concatenate([f64[np.isfinite(f64)], [1e16, 9999999999999998.0, 1e-4, 9.999999999999999e-05, 1e22, 1e23, 5e-324,
+                                                  1.7976931348623157e308, 0.30000000000000004, 2.0 ** 53]])
+    for v in f64:
+        assert fmt(v, 0) == repr(float(v)), v
+        assert fmt(-v, 0) == repr(float(-v)), v
+    assert fmt(float("nan"), 0) == "NaN" and fmt(float("inf"), 0) == "Infinity" and fmt(float("-inf"), 0) == "-Infinity"
+    assert fmt(float("nan"), 1) == "nan" and fmt(float("-inf"), 1) == "-inf"
+    assert lib.bod_format_float(1.2345678901234567, 0, buf, 4) == -1
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "bayes_od_rc_b200")
     for dirpath, _, files in os.walk(pkg):
