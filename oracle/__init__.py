@@ -26,8 +26,10 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (make -C oracle). Returns the .so path."""
-    src = os.path.join(_HERE, "bayesod_oracle.c")
-    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+    stale = False
+    for name, out in (("bayesod_oracle.c", _LIB_PATH), ("pdq_oracle.c", os.path.join(_HERE, "_build", "libpdq_oracle.so"))):
+        src = os.path.join(_HERE, name)
+        stale = stale or (not os.path.exists(out)) or os.path.getmtime(out) < os.path.getmtime(src)
     if force or stale:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
