@@ -103,6 +103,13 @@ SYMBOLS = {
     "bod_write_results_kitti_txt": (C.c_int, [C.POINTER(BodHostResults), C.c_int32, C.c_int32, C.c_int32, C.c_char_p,
                                               C.POINTER(C.c_char_p), C.c_int32]),
     "bod_format_float": (C.c_int, [C.c_double, C.c_int32, C.c_char_p, C.c_int32]),
+    "bod_pdq_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32]),
+    "bod_pdq_destroy": (None, [C.c_void_p]),
+    "bod_pdq_last_error": (C.c_char_p, [C.c_void_p]),
+    "bod_pdq_heatmaps": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "bod_pdq_losses": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 8),
+    "bod_pdq_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bod_pdq_bvn_cdf": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bod_generate_anchors": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

@@ -27,7 +27,8 @@ UNITS = {
     "k4_fusion.cu": ["-fmad=false"],
     "kv_validation.cu": ["-fmad=false"],
     "bod_api.cu": ["-fmad=false"],
-    "bod_io.cu": [],                          # host-only: npy writers
+    "bod_io.cu": [],                          # host-only: npy / json / txt writers
+    "kp_pdq.cu": [],                          # PDQ heat maps and loss sums: binary64 CDF, tolerance-checked
 }
 HEADERS = ["bod_common.cuh", "bod_kernels.h", os.path.join("..", "..", "include", "bayesod.h")]
 

@@ -327,6 +327,41 @@ int bod_write_results_kitti_txt(const bod_host_results* res, int32_t B, int32_t 
  * Returns the length written (NUL-terminated) or BOD_ERR_INVALID if `cap` is too small. */
 int bod_format_float(double value, int32_t style, char* out, int32_t cap);
 
+/* ---------------------------------------------------------------------------------------
+ * PDQ spatial quality: the Gaussian-corner heat maps of
+ * offline_eval/pdq_data_holders.py:92-247 (PBoxDetInst.calc_heatmap, find_roi,
+ * gen_single_heatmap) and the foreground / background loss sums of offline_eval/pdq.py:199-230,
+ * for box-shaped ground truth as bdd/compute_pdq.py:93-124 and kitti/compute_pdq.py build it.
+ * A context is bound to one image size; calls are synchronous (results are on the host when
+ * they return) and one at a time per context.  All pointers are HOST pointers unless stated.
+ *   boxes [D,4] int32   detection corners [x1, y1, x2, y2] (compute_pdq.py:118-120)
+ *   covs  [D,2,2,2] f64 the two corner covariances [[var_x, c], [c, var_y]] (top-left, bottom-right; :121)
+ * Errors: BOD_ERR_INVALID also where the reference itself raises (a corner mean outside its
+ * own 5-sigma window clipped to the image) or a variance is not positive; bod_pdq_last_error
+ * names the detection. */
+typedef struct bod_pdq_ctx bod_pdq_ctx;
+int  bod_pdq_create(bod_pdq_ctx** out, int device, int32_t im_h, int32_t im_w);
+void bod_pdq_destroy(bod_pdq_ctx* ctx);
+const char* bod_pdq_last_error(const bod_pdq_ctx* ctx);   /* ctx == NULL: why the last bod_pdq_create failed */
+/* Dense heat maps, out [D, im_h, im_w] float32 = calc_heatmap of every detection; `out` is a
+ * device pointer when out_on_device != 0. */
+int bod_pdq_heatmaps(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxes, const double* covs, float* out, int32_t out_on_device);
+/* Loss sums for a batch of images without materialising any map.  Image b owns detections
+ * [det_offsets[b], det_offsets[b+1]) and ground-truth boxes [gt_offsets[b], gt_offsets[b+1])
+ * (gt_boxes [G,4] int32 [x1, y1, x2, y2]: foreground = rows [y1,y2) x columns [x1,x2) as
+ * compute_pdq.py:108-110 fills the mask, background = everything outside the inclusive box,
+ * pdq.py:162-165).  Outputs: fg_loss / bg_loss = the [G_b, D_b] matrices of _calc_fg_loss /
+ * _calc_bg_loss, row-major, concatenated in image order; bg_total [D] = the background term
+ * over the whole image (pdq.py:423-424, false-positive spatial quality).  binary64 sums of
+ * binary32 terms. */
+int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t* det_offsets, const int32_t* boxes, const double* covs,
+                   const int32_t* gt_offsets, const int32_t* gt_boxes, double* fg_loss, double* bg_loss, double* bg_total);
+/* Device time of the last call in ms: [0] ROI kernel, [1] ROI read-back + table layout + CDF
+ * tables, [2] loss sums or dense maps; floats in the CDF tables; kernels launched. */
+int bod_pdq_last_ms(const bod_pdq_ctx* ctx, float ms[3], int64_t* table_floats, int64_t* launches);
+/* The device's bivariate normal CDF P(X <= h, Y <= k; r) on n points (test hook). */
+int bod_pdq_bvn_cdf(bod_pdq_ctx* ctx, int32_t n, const double* h, const double* k, const double* r, double* out);
+
 /* FPN anchors exactly as fpn_anchor_generator.py:21-59 produces them for levels
  * 3..7, 3 aspect ratios x 3 scales, concatenated P3->P7
  * (bdd_dataset_handler.py:161-186).  Writes [A,4] to device memory `anchors`

@@ -20,7 +20,12 @@ def _all_cases():
 
 def golden_cases():
     """Fixtures of bayes_od_inference / bayes_od_clustering (inference_utils.py)."""
-    return [c for c in _all_cases() if not c.startswith("val_")]
+    return [c for c in _all_cases() if not c.startswith(("val_", "pdq_", "writers_"))]
+
+
+def pdq_golden_cases():
+    """Fixtures of offline_eval/pdq_data_holders.py + pdq.py (tests/golden/make_pdq_golden.py)."""
+    return [c for c in _all_cases() if c.startswith("pdq_")]
 
 
 def val_golden_cases():
