@@ -11,9 +11,10 @@
 // The reference materialises D dense [H,W] float32 maps per image (3.7 MB each at 720x1280) and contracts them with
 // G dense boolean masks.  Here nothing dense exists unless asked for (bod_pdq_heatmaps):
 //   P1 pdq_roi_kernel     one CTA per Gaussian corner: the Mahalanobis window scan of find_roi, block-reduced to the ROI
-//   P2 pdq_table_kernel   the CDF of every ROI pixel (binary64 Genz BVND, Gauss-Legendre nodes of the corner hoisted
-//                         to shared memory) + the two "outside the image" border vectors, as one compact float32
-//                         table per corner; every other pixel of a corner's map is a replica of a table entry
+//   P2 pdq_table_kernel   the CDF of every ROI pixel (binary64 Genz BVND; the Gauss-Legendre nodes depend on the
+//                         corner only: P1 computes them once, P2 keeps them in shared memory) + the two "outside
+//                         the image" border vectors, as one compact float32 table per corner, 1024 entries per CTA;
+//                         every other pixel of a corner's map is a replica of a table entry
 //   P3 pdq_sum_kernel     one work item per (detection, overlapping ground-truth box) and one per detection for the
 //                         whole-image term: heat-map pixels are rebuilt from the two tables on the fly, log terms in
 //                         binary32 like numpy's, sums in binary64, split over kSplit CTAs with a fixed reduction order
@@ -42,7 +43,6 @@ constexpr double kMahThresh = 3.439;        // pdq_data_holders.py:9
 constexpr double kSmall = 1e-14;            // pdq_data_holders.py:10, pdq.py:8
 constexpr int kThreads = 256;
 constexpr int kSplit = 8;                   // CTAs per work item of P3
-constexpr int kTableCtas = 32;              // CTAs per corner of P2 (grid-stride inside the corner)
 
 struct Corner {
     double mean[2];          // (y, x) in the corner's own frame
@@ -84,29 +84,27 @@ struct Quad {
     int n;                           // 0: r == 0 or the high-correlation branch
 };
 
-__device__ void quad_init(Quad& q, double r) {
-    q.r = r;
-    q.n = 0;
-    q.scale = 0;
-    if (fabs(r) < 0.925 && fabs(r) > 0) {
-        const int ng = fabs(r) < 0.3 ? 0 : fabs(r) < 0.75 ? 1 : 2;
-        const double asr = asin(r);
-        int n = 0;
-        for (int i = 0; i < cGLN[ng]; ++i)
-            for (int is = -1; is <= 1; is += 2) {
-                const double sn = sin(asr * (is * cGLX[ng][i] + 1) / 2);
-                q.sn[n] = sn;
-                q.inv[n] = 1.0 / (1 - sn * sn);
-                q.w[n] = cGLW[ng][i];
-                ++n;
-            }
-        q.n = n;
-        q.scale = asr / (4 * 3.14159265358979323846);
+// One node per calling thread (t in [0, 20)); thread 0 also writes the scalars.
+__device__ void quad_init_node(Quad& q, double r, int t) {
+    const bool mid = fabs(r) < 0.925 && fabs(r) > 0;
+    const int ng = fabs(r) < 0.3 ? 0 : fabs(r) < 0.75 ? 1 : 2;
+    const int n = mid ? 2 * cGLN[ng] : 0;
+    if (t == 0) { q.r = r; q.n = n; q.scale = mid ? asin(r) / (4 * 3.14159265358979323846) : 0.0; }
+    if (t < n) {
+        const int i = t >> 1, is = (t & 1) ? 1 : -1;                     // same node order as the serial loops of the oracle
+        const double sn = sin(asin(r) * (is * cGLX[ng][i] + 1) / 2);
+        q.sn[t] = sn;
+        q.inv[t] = 1.0 / (1 - sn * sn);
+        q.w[t] = cGLW[ng][i];
     }
 }
 
+__device__ void quad_init(Quad& q, double r) {
+    for (int t = 0; t < 20; ++t) quad_init_node(q, r, t);
+}
+
 // P(X > dh, Y > dk), |r| >= 0.925 (Genz 2004): same expansion as oracle/pdq_oracle.c, written for the device
-__device__ double bvnd_high(double dh, double dk, double r) {
+__device__ __noinline__ double bvnd_high(double dh, double dk, double r) {
     const double twopi = 6.283185307179586;
     double h = dh, k = dk, hk = h * k, bvn = 0.0;
     if (r < 0) { k = -k; hk = -hk; }
@@ -169,7 +167,7 @@ __device__ __forceinline__ int trunc_int(double v) { return (int)v; }
 // P1: find_roi.  One CTA per corner (corner = 2 * detection + {0: top-left, 1: bottom-right in the flipped frame}).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) pdq_roi_kernel(const int32_t* __restrict__ boxes, const double* __restrict__ covs,
-                                                           int H, int W, Corner* __restrict__ corners) {
+                                                           int H, int W, Corner* __restrict__ corners, Quad* __restrict__ quads) {
     const int ci = blockIdx.x, d = ci >> 1, which = ci & 1;
     __shared__ Corner c;
     __shared__ int s_box[4], s_win[6];       // bbox x1 y1 x2 y2; window: minx miny nx ny dmx dmy
@@ -209,9 +207,9 @@ __global__ void __launch_bounds__(kThreads) pdq_roi_kernel(const int32_t* __rest
         const double det = c.cov[0] * c.cov[3] - c.cov[1] * c.cov[2];
         const double v0 = c.cov[3] / det, v1 = -c.cov[1] / det, v2 = -c.cov[2] / det, v3 = c.cov[0] / det;
         int bx1 = nx, by1 = ny, bx2 = -1, by2 = -1;
-        const long long total = (long long)nx * ny;
-        for (long long i = threadIdx.x; i < total; i += kThreads) {
-            const int y = (int)(i / nx), x = (int)(i - (long long)y * nx);
+        const int total = nx * ny;                                                    // <= H * W
+        for (int i = threadIdx.x; i < total; i += kThreads) {
+            const int y = i / nx, x = i - y * nx;
             const int sy = (shy && y < dmy) ? y + 1 : y, sx = (shx && x < dmx) ? x + 1 : x;
             const double dy = (double)(sy + miny) - c.mean[0], dx = (double)(sx + minx) - c.mean[1];
             const double m = sqrt(dy * (v0 * dy + v1 * dx) + dx * (v2 * dy + v3 * dx));
@@ -230,36 +228,43 @@ __global__ void __launch_bounds__(kThreads) pdq_roi_kernel(const int32_t* __rest
         if (c.status == 0 && (c.x2 > W - 1 || c.y2 > H - 1 || c.x1 > c.x2 || c.y1 > c.y2)) c.status = -1;
         corners[ci] = c;
     }
+    // the corner's quadrature nodes, one per thread (P2 only loads them)
+    if (threadIdx.x < 20 && c.status != -2) quad_init_node(quads[ci], c.cov[1] / (sqrt(c.cov[0]) * sqrt(c.cov[3])), threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// P2: CDF tables.  grid (kTableCtas, corners).  Entries: P [rh*rw] | outx [rh] | outy [rw] | c00.
+// P2: CDF tables.  One CTA per chunk of kChunk table entries (the host lays the chunks out after reading the ROIs
+// back).  Entries of a corner: P [rh*rw] | outx [rh] | outy [rw] | c00.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) pdq_table_kernel(Corner* __restrict__ corners, float* __restrict__ pool) {
+constexpr int kChunk = 4 * kThreads;
+
+struct Chunk { int32_t corner, first; };
+
+__global__ void __launch_bounds__(kThreads) pdq_table_kernel(Corner* __restrict__ corners, const Quad* __restrict__ quads,
+                                                             const Chunk* __restrict__ chunks, float* __restrict__ pool) {
     __shared__ Corner c;
     __shared__ Quad q;
-    if (threadIdx.x == 0) {
-        c = corners[blockIdx.y];
-        quad_init(q, c.cov[1] / (sqrt(c.cov[0]) * sqrt(c.cov[3])));
-    }
+    const Chunk ch = chunks[blockIdx.x];
+    if (threadIdx.x == 0) c = corners[ch.corner];
+    for (int i = threadIdx.x; i < (int)(sizeof(Quad) / sizeof(double)); i += kThreads)
+        reinterpret_cast<double*>(&q)[i] = reinterpret_cast<const double*>(quads + ch.corner)[i];
     __syncthreads();
-    if (c.status != 0) return;
     const double sy = sqrt(c.cov[0]), sx = sqrt(c.cov[3]);
     const int rh = c.y2 - c.y1 + 1, rw = c.x2 - c.x1 + 1;
-    const long long np = (long long)rh * rw, total = np + rh + rw + 1;
+    const int np = rh * rw, total = np + rh + rw + 1, last = min(total, ch.first + kChunk);
     float* tab = pool + c.off;
-    for (long long e = (long long)blockIdx.x * kThreads + threadIdx.x; e < total; e += (long long)gridDim.x * kThreads) {
+    for (int e = ch.first + threadIdx.x; e < last; e += kThreads) {
         if (e < np) {                                                        // :199-207
-            const int ry = (int)(e / rw), rx = (int)(e - (long long)ry * rw);
+            const int ry = e / rw, rx = e - ry * rw;
             tab[e] = (float)corner_cdf(c, q, sy, sx, (double)(c.y1 + ry + 1) - kSmall, (double)(c.x1 + rx + 1) - kSmall);
         } else if (e < np + rh) {                                            // :217-223 (used when x1 == 0)
-            const int ry = (int)(e - np);
+            const int ry = e - np;
             tab[e] = c.x1 == 0 ? (float)corner_cdf(c, q, sy, sx, (double)(c.y1 + ry + 1) - kSmall, 0.0 - kSmall) : 0.f;
         } else if (e < np + rh + rw) {                                       // :230-235 (used when y1 == 0)
-            const int rx = (int)(e - np - rh);
+            const int rx = e - np - rh;
             tab[e] = c.y1 == 0 ? (float)corner_cdf(c, q, sy, sx, 0.0 - kSmall, (double)(c.x1 + rx + 1) - kSmall) : 0.f;
         } else {                                                             // :240-241
-            corners[blockIdx.y].c00 = (c.x1 == 0 && c.y1 == 0) ? corner_cdf(c, q, sy, sx, 0.0 - kSmall, 0.0 - kSmall) : 0.0;
+            corners[ch.corner].c00 = (c.x1 == 0 && c.y1 == 0) ? corner_cdf(c, q, sy, sx, 0.0 - kSmall, 0.0 - kSmall) : 0.0;
         }
     }
 }
@@ -304,9 +309,9 @@ __global__ void __launch_bounds__(kThreads) pdq_sum_kernel(const Corner* __restr
     const int w = it.x_hi - it.x_lo + 1, rows = it.y_hi - it.y_lo + 1;
     if (w > 0 && rows > 0) {
         const int my_rows = (rows - (int)blockIdx.x + kSplit - 1) / kSplit;     // rows y_lo + split + j * kSplit
-        const long long total = (long long)my_rows * w;
-        for (long long i = threadIdx.x; i < total; i += kThreads) {
-            const int j = (int)(i / w), x = it.x_lo + (int)(i - (long long)j * w), y = it.y_lo + (int)blockIdx.x + j * kSplit;
+        const int total = my_rows * w;                                           // <= H * W
+        for (int i = threadIdx.x; i < total; i += kThreads) {
+            const int j = i / w, x = it.x_lo + (i - j * w), y = it.y_lo + (int)blockIdx.x + j * kSplit;
             const float h = heat_value(c1, c2, pool, H, W, y, x);
             if (x < it.fx_end && y < it.fy_end) fg += (double)logf(h + eps);     // pdq.py:222-225
             if (h > 0.f) bg += (double)logf((1.f - h) + eps);                    // pdq.py:207-210
@@ -324,28 +329,45 @@ __global__ void __launch_bounds__(kThreads) pdq_sum_kernel(const Corner* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// P5: dense heat maps [D, H, W].  grid (ceil(H*W / (4*kThreads)), D); four consecutive pixels per thread.
+// P5: dense heat maps [D, H, W]: HBM-write bound (4*H*W bytes per detection, most of them zeros).
+// grid (ceil(H / kMapRows), D): a CTA owns kMapRows full rows, one float4 (four pixels of one row) per thread and
+// step, streaming stores; rows outside the support rectangle are written without touching the tables.
+// Needs W % 4 == 0; pdq_heatmap_scalar_kernel below covers other widths.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kMapRows = 8;
+
 __global__ void __launch_bounds__(kThreads) pdq_heatmap_kernel(const Corner* __restrict__ corners, const float* __restrict__ pool,
                                                                int H, int W, float* __restrict__ out) {
     __shared__ Corner c1, c2;
     if (threadIdx.x == 0) { c1 = corners[2 * blockIdx.y]; c2 = corners[2 * blockIdx.y + 1]; }
     __syncthreads();
-    const long long hw = (long long)H * W;
-    const long long p0 = ((long long)blockIdx.x * kThreads + threadIdx.x) * 4;
-    if (p0 >= hw) return;
     // support rectangle of the product: everything outside is exactly zero
     const int sy1 = c1.y1, sx1 = c1.x1, sy2 = H - 1 - c2.y1, sx2 = W - 1 - c2.x1;
-    float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long long p = p0 + i;
-        const int y = (int)(p / W), x = (int)(p - (long long)y * W);
-        v[i] = (p < hw && y >= sy1 && y <= sy2 && x >= sx1 && x <= sx2) ? heat_value(c1, c2, pool, H, W, y, x) : 0.f;
+    const int w4 = W >> 2, y0 = blockIdx.x * kMapRows, rows = min(kMapRows, H - y0);
+    float4* o = reinterpret_cast<float4*>(out + ((size_t)blockIdx.y * H + y0) * W);
+    for (int i = threadIdx.x; i < rows * w4; i += kThreads) {
+        const int r = i / w4, x = (i - r * w4) << 2, y = y0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= sy1 && y <= sy2 && x + 3 >= sx1 && x <= sx2) {
+            v.x = heat_value(c1, c2, pool, H, W, y, x);
+            v.y = heat_value(c1, c2, pool, H, W, y, x + 1);
+            v.z = heat_value(c1, c2, pool, H, W, y, x + 2);
+            v.w = heat_value(c1, c2, pool, H, W, y, x + 3);
+        }
+        __stcs(o + i, v);
     }
-    float* o = out + (size_t)blockIdx.y * hw + p0;
-    if ((hw & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-    else for (int i = 0; i < 4 && p0 + i < hw; ++i) o[i] = v[i];
+}
+
+__global__ void __launch_bounds__(kThreads) pdq_heatmap_scalar_kernel(const Corner* __restrict__ corners,
+                                                                      const float* __restrict__ pool, int H, int W,
+                                                                      float* __restrict__ out) {
+    __shared__ Corner c1, c2;
+    if (threadIdx.x == 0) { c1 = corners[2 * blockIdx.y]; c2 = corners[2 * blockIdx.y + 1]; }
+    __syncthreads();
+    const long long hw = (long long)H * W, p = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (p >= hw) return;
+    const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+    out[(size_t)blockIdx.y * hw + p] = heat_value(c1, c2, pool, H, W, y, x);
 }
 
 __global__ void pdq_bvn_probe_kernel(int n, const double* __restrict__ h, const double* __restrict__ k, const double* __restrict__ r,
@@ -381,6 +403,9 @@ struct bod_pdq_ctx {
     DevBuf<int32_t> d_boxes;
     DevBuf<double> d_covs, d_partials, d_probe;
     DevBuf<Corner> d_corners;
+    DevBuf<Quad> d_quads;
+    DevBuf<Chunk> d_chunks;
+    std::vector<Chunk> chunks;
     DevBuf<Item> d_items;
     DevBuf<float> pool, d_maps;
     std::vector<Corner> corners;
@@ -413,16 +438,18 @@ int build_tables(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxes, const double
     PDQ_CUDA(ctx->d_boxes.reserve((size_t)D * 4), "alloc boxes");
     PDQ_CUDA(ctx->d_covs.reserve((size_t)D * 8), "alloc covs");
     PDQ_CUDA(ctx->d_corners.reserve((size_t)D * 2), "alloc corners");
+    PDQ_CUDA(ctx->d_quads.reserve((size_t)D * 2), "alloc quadrature nodes");
     PDQ_CUDA(cudaMemcpyAsync(ctx->d_boxes.p, boxes, sizeof(int32_t) * 4 * D, cudaMemcpyHostToDevice, ctx->stream), "H2D boxes");
     PDQ_CUDA(cudaMemcpyAsync(ctx->d_covs.p, covs, sizeof(double) * 8 * D, cudaMemcpyHostToDevice, ctx->stream), "H2D covs");
     PDQ_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream), "event");
-    pdq_roi_kernel<<<2 * D, kThreads, 0, ctx->stream>>>(ctx->d_boxes.p, ctx->d_covs.p, ctx->H, ctx->W, ctx->d_corners.p);
+    pdq_roi_kernel<<<2 * D, kThreads, 0, ctx->stream>>>(ctx->d_boxes.p, ctx->d_covs.p, ctx->H, ctx->W, ctx->d_corners.p, ctx->d_quads.p);
     PDQ_CUDA(cudaGetLastError(), "pdq_roi_kernel");
     PDQ_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream), "event");
     ctx->corners.resize((size_t)D * 2);
     PDQ_CUDA(cudaMemcpyAsync(ctx->corners.data(), ctx->d_corners.p, sizeof(Corner) * 2 * D, cudaMemcpyDeviceToHost, ctx->stream), "D2H corners");
     PDQ_CUDA(cudaStreamSynchronize(ctx->stream), "sync after P1");
     long long off = 0;
+    ctx->chunks.clear();
     for (size_t i = 0; i < ctx->corners.size(); ++i) {
         Corner& c = ctx->corners[i];
         if (c.status != 0) {
@@ -433,13 +460,16 @@ int build_tables(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxes, const double
             return BOD_ERR_INVALID;
         }
         c.off = off;
-        const long long rh = c.y2 - c.y1 + 1, rw = c.x2 - c.x1 + 1;
-        off += (rh * rw + rh + rw + 3) & ~3LL;
+        const long long rh = c.y2 - c.y1 + 1, rw = c.x2 - c.x1 + 1, entries = rh * rw + rh + rw + 1;
+        off += (entries + 3) & ~3LL;
+        for (long long first = 0; first < entries; first += kChunk) ctx->chunks.push_back(Chunk{(int32_t)i, (int32_t)first});
     }
     ctx->table_floats = off;
     PDQ_CUDA(ctx->pool.reserve((size_t)std::max<long long>(off, 4)), "alloc table pool");
     PDQ_CUDA(cudaMemcpyAsync(ctx->d_corners.p, ctx->corners.data(), sizeof(Corner) * 2 * D, cudaMemcpyHostToDevice, ctx->stream), "H2D corners");
-    pdq_table_kernel<<<dim3(kTableCtas, 2 * D), kThreads, 0, ctx->stream>>>(ctx->d_corners.p, ctx->pool.p);
+    PDQ_CUDA(ctx->d_chunks.reserve(ctx->chunks.size()), "alloc chunks");
+    PDQ_CUDA(cudaMemcpyAsync(ctx->d_chunks.p, ctx->chunks.data(), sizeof(Chunk) * ctx->chunks.size(), cudaMemcpyHostToDevice, ctx->stream), "H2D chunks");
+    pdq_table_kernel<<<(unsigned)ctx->chunks.size(), kThreads, 0, ctx->stream>>>(ctx->d_corners.p, ctx->d_quads.p, ctx->d_chunks.p, ctx->pool.p);
     PDQ_CUDA(cudaGetLastError(), "pdq_table_kernel");
     PDQ_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream), "event");
     ctx->launches += 2;
@@ -482,7 +512,7 @@ extern "C" void bod_pdq_destroy(bod_pdq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ctx->d_boxes.release(); ctx->d_covs.release(); ctx->d_partials.release(); ctx->d_probe.release();
-    ctx->d_corners.release(); ctx->d_items.release(); ctx->pool.release(); ctx->d_maps.release();
+    ctx->d_corners.release(); ctx->d_quads.release(); ctx->d_chunks.release(); ctx->d_items.release(); ctx->pool.release(); ctx->d_maps.release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -512,8 +542,12 @@ extern "C" int bod_pdq_heatmaps(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxe
         PDQ_CUDA(ctx->d_maps.reserve(hw * D), "alloc dense maps");
         dst = ctx->d_maps.p;
     }
-    pdq_heatmap_kernel<<<dim3((unsigned)((hw + 4 * kThreads - 1) / (4 * kThreads)), D), kThreads, 0, ctx->stream>>>(
-        ctx->d_corners.p, ctx->pool.p, ctx->H, ctx->W, dst);
+    if (ctx->W % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
+        pdq_heatmap_kernel<<<dim3((unsigned)((ctx->H + kMapRows - 1) / kMapRows), D), kThreads, 0, ctx->stream>>>(
+            ctx->d_corners.p, ctx->pool.p, ctx->H, ctx->W, dst);
+    else
+        pdq_heatmap_scalar_kernel<<<dim3((unsigned)((hw + kThreads - 1) / kThreads), D), kThreads, 0, ctx->stream>>>(
+            ctx->d_corners.p, ctx->pool.p, ctx->H, ctx->W, dst);
     PDQ_CUDA(cudaGetLastError(), "pdq_heatmap_kernel");
     ctx->launches += 1;
     rc = finish_timing(ctx);

@@ -57,6 +57,28 @@ class PBoxDet:
         self.covs = covs
 
 
+_CORNER_TRANSFORM = np.array([[0, 1, 0, -0.5], [1, 0, -0.5, 0], [0, 1, 0, 0.5], [1, 0, 0.5, 0]])     # compute_pdq.py:98-101
+
+
+def det_instances_from_arrays(means_vuhw, covs_vuhw, cat_params, min_score=0.5445, cov_scale=70.0):
+    """The detection list of one image as ``bdd/compute_pdq.py:93-124`` builds it from the saved ``mean`` /
+    ``cov`` / ``cat_param`` arrays (``[D,4]``, ``[D,4,4]``, ``[D,K]``): corner covariances ``T.Sigma.T^T * cov_scale``,
+    corners of ``vuhw_to_vuvu_np`` truncated to int32, detections whose best class score is below ``min_score``
+    dropped.  ``kitti/compute_pdq.py:119-148`` is the same with ``min_score=0.5`` (its x70 is applied when loading)."""
+    means = np.asarray(means_vuhw)
+    if np.asarray(covs_vuhw).size == 0:
+        return []
+    means = means.reshape(-1, 4)
+    cov_t = np.matmul(np.matmul(_CORNER_TRANSFORM, np.asarray(covs_vuhw)), _CORNER_TRANSFORM.T) * cov_scale
+    v, u, h, w = means[:, 0], means[:, 1], means[:, 2], means[:, 3]
+    vuvu = np.stack((v - h / 2.0, u - w / 2.0, v + h / 2.0, u + w / 2.0), axis=1)            # box_utils.py:70-88
+    dets = []
+    for cat, b, cv in zip(np.asarray(cat_params), vuvu, cov_t):
+        if np.max(cat) >= min_score:
+            dets.append(PBoxDet(cat, np.array([b[1], b[0], b[3], b[2]]).astype(np.int32), [cv[0:2, 0:2], cv[2:4, 2:4]]))
+    return dets
+
+
 def _num_pixels(gt, img_size) -> int:
     mask = getattr(gt, "segmentation_mask", None)
     if mask is None:

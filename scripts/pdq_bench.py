@@ -38,18 +38,19 @@ def scene(rng, D, G):
 
 
 def main():
-    n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    D = int(sys.argv[2]) if len(sys.argv) > 2 else 60
-    G = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    n_img = int(args[0]) if len(args) > 0 else 64
+    D = int(args[1]) if len(args) > 1 else 60
+    G = int(args[2]) if len(args) > 2 else 20
+    reps = int(os.environ.get('PDQ_REPS', '10'))
     rng = np.random.default_rng(0)
     scenes = [scene(rng, D, G) for _ in range(n_img)]
     do = np.arange(n_img + 1) * D
     go = np.arange(n_img + 1) * G
     boxes = np.concatenate([s[0] for s in scenes]); covs = np.concatenate([s[1] for s in scenes]); gts = np.concatenate([s[2] for s in scenes])
     eng = ppdq.PdqEngine((H, W))
-    for _ in range(3):
+    for _ in range(min(3, reps)):
         eng.losses(do, boxes, covs, go, gts)
-    reps = 10
     t = time.perf_counter()
     dev = []
     for _ in range(reps):
@@ -64,7 +65,7 @@ def main():
     import torch
     nd = min(len(boxes), 256)
     buf = torch.empty((nd, H, W), device="cuda")
-    for _ in range(3):
+    for _ in range(min(3, reps)):
         eng.heatmaps(boxes[:nd], covs[:nd], out=buf)
     dm = []
     for _ in range(reps):

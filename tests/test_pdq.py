@@ -108,6 +108,18 @@ def test_host_qualities_from_golden_losses():
         assert [res["TP"], res["FP"], res["FN"]] == g["res_counts"].tolist()
 
 
+def test_det_instances_from_arrays_follow_compute_pdq():
+    """compute_pdq.py:93-124 on the golden's saved arrays gives the boxes / corner covariances the golden was minted with."""
+    from bayes_od_rc_b200 import pdq as ppdq
+    for name in CASES:
+        g = load(name)
+        dets = ppdq.det_instances_from_arrays(g["means_vuhw"], g["covs_vuhw"], g["cat_param"], min_score=0.0)
+        assert np.array_equal(np.array([d.box for d in dets]), g["boxes"])
+        np.testing.assert_allclose(np.array([np.stack(d.covs) for d in dets]), g["covs"], rtol=1e-12)
+        assert len(ppdq.det_instances_from_arrays(g["means_vuhw"], g["covs_vuhw"], g["cat_param"], min_score=2.0)) == 0
+    assert ppdq.det_instances_from_arrays(np.zeros((0, 4, 1)), np.zeros((0, 4, 1)), np.zeros((0, 4, 1))) == []
+
+
 # ------------------------------------------------------------------------------------------------ GPU: the product
 @pytest.fixture(scope="module")
 def engines():
@@ -240,6 +252,20 @@ def test_gpu_heatmaps_into_device_tensor(engines):
     out = torch.full(g["heatmaps"].shape, -1.0, device="cuda")
     eng.heatmaps(g["boxes"], g["covs"], out=out)
     assert np.array_equal(out.cpu().numpy(), eng.heatmaps(g["boxes"], g["covs"]))
+
+
+@pytest.mark.gpu
+def test_gpu_odd_width_uses_the_scalar_map_kernel(engines):
+    rng = np.random.default_rng(11)
+    H, W = 50, 70                                  # W % 4 != 0
+    b, c, g = _random_scene(rng, H, W, 5, 3, (0.5, 20))
+    hm = engines((H, W)).heatmaps(b, c)
+    ohm = opdq.heatmaps((H, W), b, c)
+    assert np.array_equal(hm > 0, ohm > 0) and np.abs(hm - ohm).max() <= HM_ATOL
+    fgs, bgs, tot = engines((H, W)).losses([0, 5], b, c, [0, 3], g)
+    ofg, obg, otot = opdq.losses(ohm, g)
+    np.testing.assert_allclose(fgs[0], ofg, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(bgs[0], obg, rtol=1e-6, atol=1e-6)
 
 
 @pytest.mark.gpu
