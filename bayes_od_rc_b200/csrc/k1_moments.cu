@@ -52,6 +52,32 @@ BOD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 BOD_DEVINL void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The same on 32-bit shared-window addresses: the consumers of the pipeline kernel convert their pointers once,
+// outside the sample loop (inside it the generic->shared conversion costs ~14 instructions per iteration).
+BOD_DEVINL void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+BOD_DEVINL void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+template <int OFF> BOD_DEVINL float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int K, int I = 0> struct LoadRow {
+    static BOD_DEVINL void run(uint32_t addr, float (&x)[K]) { x[I] = lds_f32<4 * I>(addr); LoadRow<K, I + 1>::run(addr, x); }
+};
+template <int K> struct LoadRow<K, K> { static BOD_DEVINL void run(uint32_t, float (&)[K]) {} };
+
 BOD_DEVINL void consumer_barrier() {   // named barrier 1: the kTileAnchors consumer threads only
     asm volatile("bar.sync 1, %0;" ::"n"(kTileAnchors) : "memory");
 }
@@ -352,7 +378,9 @@ template <int K>
 __global__ void __launch_bounds__(kTileAnchors + 32, BOD_K1_MINBLOCKS)
 k1_moments_pipe_kernel(K1Args a, int NS) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+    __shared__ uint64_t bars[2 * kMaxStages];         // one array: empty_bar = full_bar + a compile-time offset
+    uint64_t* const full_bar = bars;
+    uint64_t* const empty_bar = bars + kMaxStages;
     __shared__ int stage_tile[kMaxStages];            // tile whose first slab sits in the stage (-1: no more work)
     __shared__ int warp_count[2][kConsumerWarps];
 
@@ -400,9 +428,16 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
     }
 
     // ---- consumers: one thread per anchor of the tile ----
+    uint32_t full0 = smem_u32(&full_bar[0]);
+    constexpr uint32_t empty_minus_full = kMaxStages * 8;
+    uint32_t row0 = smem_u32(ring) + (uint32_t)tid * (uint32_t)(K * 4);
+    // opaque to the optimiser: otherwise it rematerialises the conversions (S2R SR_CgaCtaId + LEA) in every iteration
+    asm volatile("" : "+r"(full0), "+r"(row0));
+    constexpr uint32_t kSlabBytes = (uint32_t)(slab_stride * 4);
+    uint32_t row_addr = row0, bar_off = 0;                   // this thread's row in the current stage; the stage's barrier offset
     int stage = 0, phase = 0;
     for (int tcount = 0;; ++tcount) {
-        mbar_wait(&full_bar[stage], (uint32_t)phase);        // first slab of the next tile, or the end marker
+        mbar_wait_a(full0 + bar_off, (uint32_t)phase);       // first slab of the next tile, or the end marker
         const int t = stage_tile[stage];
         if (t < 0) break;
         const int b = t / tiles, tile = t - b * tiles;
@@ -426,12 +461,10 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
 #pragma unroll
         for (int k = 0; k < K; ++k) p[k] = 0.0f;
         for (int n = 0; n < N; ++n) {
-            if (n > 0) mbar_wait(&full_bar[stage], (uint32_t)phase);
+            if (n > 0) mbar_wait_a(full0 + bar_off, (uint32_t)phase);
             if (valid && a.debug < 2) {
-                const float* row = ring + stage * slab_stride + tid * K;
                 float x[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) x[k] = row[k];
+                LoadRow<K>::run(row_addr, x);
                 float m = x[0];
 #pragma unroll
                 for (int k = 1; k < K; ++k) m = fmaxf(m, x[k]);
@@ -444,8 +477,9 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
                 for (int k = 0; k < K; ++k) p[k] = __fmaf_rn(x[k], inv, p[k]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);   // this warp is done with the stage
-            if (++stage == NS) { stage = 0; phase ^= 1; }
+            if (lane == 0) mbar_arrive_a(full0 + empty_minus_full + bar_off);  // this warp is done with the stage
+            row_addr += kSlabBytes; bar_off += 8;
+            if (++stage == NS) { stage = 0; phase ^= 1; row_addr = row0; bar_off = 0; }
         }
         if (valid) {
             const float invN = 1.0f / (float)N;

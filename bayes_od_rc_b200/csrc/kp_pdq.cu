@@ -82,6 +82,7 @@ struct Quad {
     double scale;                    // asin(r) / (4 pi)
     double r;
     int n;                           // 0: r == 0 or the high-correlation branch
+    int pad;
 };
 
 // One node per calling thread (t in [0, 20)); thread 0 also writes the scalars.
@@ -89,13 +90,15 @@ __device__ void quad_init_node(Quad& q, double r, int t) {
     const bool mid = fabs(r) < 0.925 && fabs(r) > 0;
     const int ng = fabs(r) < 0.3 ? 0 : fabs(r) < 0.75 ? 1 : 2;
     const int n = mid ? 2 * cGLN[ng] : 0;
-    if (t == 0) { q.r = r; q.n = n; q.scale = mid ? asin(r) / (4 * 3.14159265358979323846) : 0.0; }
+    if (t == 0) { q.r = r; q.n = n; q.pad = 0; q.scale = mid ? asin(r) / (4 * 3.14159265358979323846) : 0.0; }
     if (t < n) {
         const int i = t >> 1, is = (t & 1) ? 1 : -1;                     // same node order as the serial loops of the oracle
         const double sn = sin(asin(r) * (is * cGLX[ng][i] + 1) / 2);
         q.sn[t] = sn;
         q.inv[t] = 1.0 / (1 - sn * sn);
         q.w[t] = cGLW[ng][i];
+    } else if (t < 20) {                                                 // unused slots: P2 copies the whole struct
+        q.sn[t] = 0.0; q.inv[t] = 0.0; q.w[t] = 0.0;
     }
 }
 
