@@ -19,3 +19,7 @@ dump 'k3_softnms_kernel' k3_softnms_kernel
 dump 'k4_fusion_kernelILi11' k4_fusion_kernel_K11
 dump 'prefilter_select_kernel' prefilter_select_kernel
 dump 'val_filter_kernelILi11' val_filter_kernel_K11
+dump 'pdq_table_kernel' pdq_table_kernel
+dump 'pdq_sum_kernel' pdq_sum_kernel
+dump 'pdq_heatmap_kernelE' pdq_heatmap_kernel
+dump 'pdq_roi_kernel' pdq_roi_kernel

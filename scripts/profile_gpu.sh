@@ -8,6 +8,13 @@ set -u
 R=${1:-r1}
 ONLY=${2:-all}
 mkdir -p gpurun_out
+if [ "$ONLY" = "pdq" ] || [ "$ONLY" = "all" ]; then
+  # PDQ kernels (csrc/kp_pdq.cu): one --set full capture of the first launches of scripts/pdq_bench.py
+  PDQ_REPS=1 ncu --set full --import-source on --clock-control none -k regex:pdq_ -c 8 -o gpurun_out/prof_pdq_${R} -f \
+      python scripts/pdq_bench.py 16 60 20 --no-cpu > gpurun_out/ncu_pdq_${R}.log 2>&1
+  tail -1 gpurun_out/ncu_pdq_${R}.log
+  [ "$ONLY" = "pdq" ] && exit 0
+fi
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k1_moments|k3_softnms|k4_fusion|k2_posterior|scan_tiles" \
     -c 400 --csv --log-file gpurun_out/launches_${R}.csv \
     python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch_${R}.log 2>&1

@@ -31,7 +31,37 @@ def raw_page(rep):
     return hdr, units, rows[2:]
 
 
+def pdq_summary():
+    """profiles/ncu_pdq_summary_<round>.txt from gpurun_out/prof_pdq_<round>.ncu-rep (scripts/profile_gpu.sh <round> pdq)."""
+    rep = os.path.join(GO, f"prof_pdq_{R}.ncu-rep")
+    if not os.path.exists(rep):
+        return
+    hdr, units, rows = raw_page(rep)
+    name_i = hdr.index("Kernel Name")
+    lines = [f"# ncu --set full --clock-control none, round {R[1:]}, B200: PDQ kernels (csrc/kp_pdq.cu), workload of scripts/pdq_bench.py",
+             "# 16 images of 720x1280, 60 detections + 20 ground-truth boxes each; dense maps: 256 detections; first launch of each kernel",
+             ""]
+    seen = set()
+    for r in rows:
+        k = r[name_i].split("(")[0]
+        if k in seen:
+            continue
+        seen.add(k)
+        lines.append(f"## {r[name_i]}")
+        for m in METRICS:
+            if m in hdr:
+                i = hdr.index(m)
+                lines.append(f"{m:80s} {r[i]:>16s} {units[i]}")
+        lines.append("")
+    with open(os.path.join(OUT, f"ncu_pdq_summary_{R}.txt"), "w") as f:
+        f.write("\n".join(lines))
+    print("\n".join(l for l in lines if l.startswith("##") or "time_duration" in l))
+
+
 def main():
+    pdq_summary()
+    if len(sys.argv) > 2 and sys.argv[2] == "pdq":
+        return
     rep = os.path.join(GO, f"prof_all_{R}.ncu-rep")
     hdr, units, rows = raw_page(rep)
     name_i = hdr.index("Kernel Name")
