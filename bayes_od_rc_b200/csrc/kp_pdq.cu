@@ -42,7 +42,8 @@ constexpr float kHeatThresh = 0.0027f;      // pdq_data_holders.py:8
 constexpr double kMahThresh = 3.439;        // pdq_data_holders.py:9
 constexpr double kSmall = 1e-14;            // pdq_data_holders.py:10, pdq.py:8
 constexpr int kThreads = 256;
-constexpr int kSplit = 8;                   // CTAs per work item of P3
+constexpr int kSplit = 8;                   // at most this many CTAs per work item of P3
+constexpr int kSumPixelsPerCta = 8192;      // P3: an item gets one CTA per this many pixels
 
 struct Corner {
     double mean[2];          // (y, x) in the corner's own frame
@@ -57,8 +58,10 @@ struct Corner {
 struct Item {                // P3 work item: iterate rows [y_lo, y_hi] x columns [x_lo, x_hi] of detection `det`
     int32_t det, x_lo, x_hi, y_lo, y_hi;
     int32_t fx_end, fy_end;  // a pixel is foreground iff x < fx_end && y < fy_end (INT_MIN: no foreground)
-    int32_t pad;
+    int32_t nsplit;          // CTAs that share the item's rows (1..kSplit, by its pixel count)
 };
+
+struct SumCta { int32_t item, split; };   // P3 launches one CTA per entry
 
 __device__ __forceinline__ double phi(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
 
@@ -293,47 +296,86 @@ __device__ __forceinline__ float heat_value(const Corner& c1, const Corner& c2, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// P3: loss sums of one work item, rows interleaved over kSplit CTAs.  partials[(item * kSplit + split) * 2 + {fg, bg}]
+// P3: loss sums of one work item.  Rows are interleaved over (the item's 1..kSplit CTAs) x (8 warps); a warp walks one row with
+// everything that depends on the row only (table row, border term, "below the ROI" flag of both corners) hoisted.
+// partials[(item * kSplit + split) * 2 + {fg, bg}]
 // ---------------------------------------------------------------------------------------------------------------
+struct RowView {                 // one row of gen_single_heatmap's map, in the corner's own frame
+    const float* row;            // table row (clamped to the ROI's last row)
+    const float* outy;           // border vector over columns (used when y1 == 0)
+    float outx;                  // border term of this row (0 unless x1 == 0)
+    bool below, zero;            // row below the ROI; row above the ROI (all zeros)
+};
+
+__device__ __forceinline__ RowView row_view(const Corner& c, const float* __restrict__ pool, int y) {
+    RowView r;
+    const int rh = c.y2 - c.y1 + 1, rw = c.x2 - c.x1 + 1;
+    const int ry = min(y, c.y2) - c.y1;
+    const float* tab = pool + c.off;
+    r.zero = y < c.y1;
+    r.below = y > c.y2;
+    r.row = tab + (long long)max(ry, 0) * rw;
+    r.outy = tab + (long long)rh * rw + rh;
+    r.outx = (c.x1 == 0 && !r.zero) ? __ldg(tab + (long long)rh * rw + ry) : 0.f;
+    return r;
+}
+
+__device__ __forceinline__ float row_value(const Corner& c, const RowView& r, int x) {   // == corner_value(c, pool, y, x)
+    if (x < c.x1) return 0.f;
+    const int rx = min(x, c.x2) - c.x1;
+    float v = (r.below && x > c.x2) ? 1.0f : __ldg(r.row + rx);
+    v -= r.outx;
+    if (c.y1 == 0) v -= __ldg(r.outy + rx);
+    if (c.x1 == 0 && c.y1 == 0) v = (float)((double)v + c.c00);
+    return v < kHeatThresh ? 0.f : v;
+}
+
 __global__ void __launch_bounds__(kThreads) pdq_sum_kernel(const Corner* __restrict__ corners, const float* __restrict__ pool,
-                                                           const Item* __restrict__ items, int H, int W,
-                                                           double* __restrict__ partials) {
+                                                           const Item* __restrict__ items, const SumCta* __restrict__ ctas,
+                                                           int H, int W, double* __restrict__ partials) {
     __shared__ Corner c1, c2;
     __shared__ Item it;
     __shared__ double red[2][kThreads / 32];
+    const SumCta me = ctas[blockIdx.x];
     if (threadIdx.x == 0) {
-        it = items[blockIdx.y];
+        it = items[me.item];
         c1 = corners[2 * it.det];
         c2 = corners[2 * it.det + 1];
     }
     __syncthreads();
     const float eps = (float)kSmall;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double fg = 0, bg = 0;
-    const int w = it.x_hi - it.x_lo + 1, rows = it.y_hi - it.y_lo + 1;
-    if (w > 0 && rows > 0) {
-        const int my_rows = (rows - (int)blockIdx.x + kSplit - 1) / kSplit;     // rows y_lo + split + j * kSplit
-        const int total = my_rows * w;                                           // <= H * W
-        for (int i = threadIdx.x; i < total; i += kThreads) {
-            const int j = i / w, x = it.x_lo + (i - j * w), y = it.y_lo + (int)blockIdx.x + j * kSplit;
-            const float h = heat_value(c1, c2, pool, H, W, y, x);
-            if (x < it.fx_end && y < it.fy_end) fg += (double)logf(h + eps);     // pdq.py:222-225
-            if (h > 0.f) bg += (double)logf((1.f - h) + eps);                    // pdq.py:207-210
+    for (int y = it.y_lo + me.split + warp * it.nsplit; y <= it.y_hi; y += it.nsplit * (kThreads / 32)) {
+        const RowView r1 = row_view(c1, pool, y), r2 = row_view(c2, pool, H - 1 - y);
+        const bool fg_row = y < it.fy_end;
+        if (r1.zero || r2.zero) {                                            // the whole row of the product is zero
+            if (fg_row && lane == 0) fg += (double)max(min(it.x_hi, it.fx_end - 1) - it.x_lo + 1, 0) * (double)logf(eps);
+            continue;
+        }
+        for (int x = it.x_lo + lane; x <= it.x_hi; x += 32) {
+            float h = row_value(c1, r1, x) * row_value(c2, r2, W - 1 - x);   // :106-109
+            h = h > 1.f ? 1.f : h;                                           // :113
+            h = h < kHeatThresh ? 0.f : h;                                   // :115
+            if (fg_row && x < it.fx_end) fg += (double)logf(h + eps);        // pdq.py:222-225
+            if (h > 0.f) bg += (double)logf((1.f - h) + eps);                // pdq.py:207-210
         }
     }
     for (int o = 16; o; o >>= 1) { fg += __shfl_xor_sync(0xffffffffu, fg, o); bg += __shfl_xor_sync(0xffffffffu, bg, o); }
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = fg; red[1][threadIdx.x >> 5] = bg; }
+    if (lane == 0) { red[0][warp] = fg; red[1][warp] = bg; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double f = 0, b = 0;
         for (int i = 0; i < kThreads / 32; ++i) { f += red[0][i]; b += red[1][i]; }
-        partials[((size_t)blockIdx.y * kSplit + blockIdx.x) * 2 + 0] = f;
-        partials[((size_t)blockIdx.y * kSplit + blockIdx.x) * 2 + 1] = b;
+        partials[((size_t)me.item * kSplit + me.split) * 2 + 0] = f;
+        partials[((size_t)me.item * kSplit + me.split) * 2 + 1] = b;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // P5: dense heat maps [D, H, W]: HBM-write bound (4*H*W bytes per detection, most of them zeros).
-// grid (ceil(H / kMapRows), D): a CTA owns kMapRows full rows, one float4 (four pixels of one row) per thread and
+// grid (ceil(H / kMapRows), D) — row tiles fastest, so that concurrently running CTAs write neighbouring rows of one
+// map (5.7 -> 6.1 TB/s against the transposed grid); at most 65535 detections per launch.  A CTA owns kMapRows full rows, one float4 (four pixels of one row) per thread and
 // step, streaming stores; rows outside the support rectangle are written without touching the tables.
 // Needs W % 4 == 0; pdq_heatmap_scalar_kernel below covers other widths.
 // ---------------------------------------------------------------------------------------------------------------
@@ -365,12 +407,13 @@ __global__ void __launch_bounds__(kThreads) pdq_heatmap_scalar_kernel(const Corn
                                                                       const float* __restrict__ pool, int H, int W,
                                                                       float* __restrict__ out) {
     __shared__ Corner c1, c2;
-    if (threadIdx.x == 0) { c1 = corners[2 * blockIdx.y]; c2 = corners[2 * blockIdx.y + 1]; }
+    if (threadIdx.x == 0) { c1 = corners[2 * blockIdx.x]; c2 = corners[2 * blockIdx.x + 1]; }
     __syncthreads();
-    const long long hw = (long long)H * W, p = (long long)blockIdx.x * kThreads + threadIdx.x;
-    if (p >= hw) return;
-    const int y = (int)(p / W), x = (int)(p - (long long)y * W);
-    out[(size_t)blockIdx.y * hw + p] = heat_value(c1, c2, pool, H, W, y, x);
+    const long long hw = (long long)H * W;
+    for (long long p = (long long)blockIdx.y * kThreads + threadIdx.x; p < hw; p += (long long)gridDim.y * kThreads) {
+        const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+        out[(size_t)blockIdx.x * hw + p] = heat_value(c1, c2, pool, H, W, y, x);
+    }
 }
 
 __global__ void pdq_bvn_probe_kernel(int n, const double* __restrict__ h, const double* __restrict__ k, const double* __restrict__ r,
@@ -410,6 +453,8 @@ struct bod_pdq_ctx {
     DevBuf<Chunk> d_chunks;
     std::vector<Chunk> chunks;
     DevBuf<Item> d_items;
+    DevBuf<SumCta> d_sum_ctas;
+    std::vector<SumCta> sum_ctas;
     DevBuf<float> pool, d_maps;
     std::vector<Corner> corners;
     std::vector<Item> items;
@@ -489,7 +534,10 @@ int finish_timing(bod_pdq_ctx* ctx) {
 }  // namespace
 
 extern "C" int bod_pdq_create(bod_pdq_ctx** out, int device, int32_t im_h, int32_t im_w) {
-    if (!out || im_h < 1 || im_w < 1) { snprintf(g_create_err, sizeof g_create_err, "bod_pdq_create: bad argument"); return BOD_ERR_INVALID; }
+    if (!out || im_h < 1 || im_w < 1 || (long long)im_h * im_w > (1LL << 30)) {       // pixel indices are 32-bit
+        snprintf(g_create_err, sizeof g_create_err, "bod_pdq_create: bad argument (image size must be 1 .. 2^30 pixels)");
+        return BOD_ERR_INVALID;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || device < 0 || device >= n) {
@@ -515,7 +563,7 @@ extern "C" void bod_pdq_destroy(bod_pdq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ctx->d_boxes.release(); ctx->d_covs.release(); ctx->d_partials.release(); ctx->d_probe.release();
-    ctx->d_corners.release(); ctx->d_quads.release(); ctx->d_chunks.release(); ctx->d_items.release(); ctx->pool.release(); ctx->d_maps.release();
+    ctx->d_corners.release(); ctx->d_quads.release(); ctx->d_chunks.release(); ctx->d_items.release(); ctx->d_sum_ctas.release(); ctx->pool.release(); ctx->d_maps.release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -546,10 +594,11 @@ extern "C" int bod_pdq_heatmaps(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxe
         dst = ctx->d_maps.p;
     }
     if (ctx->W % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
-        pdq_heatmap_kernel<<<dim3((unsigned)((ctx->H + kMapRows - 1) / kMapRows), D), kThreads, 0, ctx->stream>>>(
-            ctx->d_corners.p, ctx->pool.p, ctx->H, ctx->W, dst);
+        for (int32_t d0 = 0; d0 < D; d0 += 65535)
+            pdq_heatmap_kernel<<<dim3((unsigned)((ctx->H + kMapRows - 1) / kMapRows), (unsigned)std::min(D - d0, 65535)), kThreads, 0,
+                                 ctx->stream>>>(ctx->d_corners.p + 2 * (size_t)d0, ctx->pool.p, ctx->H, ctx->W, dst + (size_t)d0 * hw);
     else
-        pdq_heatmap_scalar_kernel<<<dim3((unsigned)((hw + kThreads - 1) / kThreads), D), kThreads, 0, ctx->stream>>>(
+        pdq_heatmap_scalar_kernel<<<dim3(D, (unsigned)std::min<size_t>((hw + kThreads - 1) / kThreads, 65535)), kThreads, 0, ctx->stream>>>(
             ctx->d_corners.p, ctx->pool.p, ctx->H, ctx->W, dst);
     PDQ_CUDA(cudaGetLastError(), "pdq_heatmap_kernel");
     ctx->launches += 1;
@@ -588,7 +637,7 @@ extern "C" int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t*
             const Corner& c1 = ctx->corners[2 * (size_t)(d0 + d)];
             const Corner& c2 = ctx->corners[2 * (size_t)(d0 + d) + 1];
             const int sx1 = c1.x1, sy1 = c1.y1, sx2 = W - 1 - c2.x1, sy2 = H - 1 - c2.y1;      // support of the product
-            ctx->items.push_back(Item{d0 + d, sx1, sx2, sy1, sy2, INT32_MIN, INT32_MIN, 0});
+            ctx->items.push_back(Item{d0 + d, sx1, sx2, sy1, sy2, INT32_MIN, INT32_MIN, 1});
             slots.push_back(Slot{~(long long)(d0 + d), (int)ctx->items.size() - 1});
             for (int g = 0; g < ng; ++g) {
                 const int32_t* gb = gt_boxes + 4 * (size_t)(g0 + g);
@@ -604,7 +653,7 @@ extern "C" int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t*
                 fg_loss[o] = (double)(n_fg - ((x_lo <= x_hi && y_lo <= y_hi) ? n_in : 0)) * (double)log_eps;
                 bg_loss[o] = 0.0;
                 if (x_lo <= x_hi && y_lo <= y_hi) {
-                    ctx->items.push_back(Item{d0 + d, x_lo, x_hi, y_lo, y_hi, gx2, gy2, 0});
+                    ctx->items.push_back(Item{d0 + d, x_lo, x_hi, y_lo, y_hi, gx2, gy2, 1});
                     slots.push_back(Slot{o, (int)ctx->items.size() - 1});
                 }
             }
@@ -612,16 +661,22 @@ extern "C" int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t*
         pair_base += (size_t)ng * nd;
     }
     const size_t ni = ctx->items.size();
+    ctx->sum_ctas.clear();
+    for (size_t i = 0; i < ni; ++i) {
+        Item& it = ctx->items[i];
+        const long long px = (long long)std::max(it.x_hi - it.x_lo + 1, 0) * std::max(it.y_hi - it.y_lo + 1, 0);
+        it.nsplit = (int32_t)std::min<long long>(kSplit, std::max<long long>(1, (px + kSumPixelsPerCta - 1) / kSumPixelsPerCta));
+        for (int32_t sp = 0; sp < it.nsplit; ++sp) ctx->sum_ctas.push_back(SumCta{(int32_t)i, sp});
+    }
+    PDQ_CUDA(ctx->d_sum_ctas.reserve(ctx->sum_ctas.size()), "alloc CTA list");
+    PDQ_CUDA(cudaMemcpyAsync(ctx->d_sum_ctas.p, ctx->sum_ctas.data(), sizeof(SumCta) * ctx->sum_ctas.size(), cudaMemcpyHostToDevice, ctx->stream), "H2D CTA list");
     PDQ_CUDA(ctx->d_items.reserve(ni), "alloc items");
     PDQ_CUDA(ctx->d_partials.reserve(ni * kSplit * 2), "alloc partials");
     PDQ_CUDA(cudaMemcpyAsync(ctx->d_items.p, ctx->items.data(), sizeof(Item) * ni, cudaMemcpyHostToDevice, ctx->stream), "H2D items");
-    for (size_t first = 0; first < ni; first += 65535) {       // gridDim.y limit
-        const unsigned n = (unsigned)std::min<size_t>(65535, ni - first);
-        pdq_sum_kernel<<<dim3(kSplit, n), kThreads, 0, ctx->stream>>>(ctx->d_corners.p, ctx->pool.p, ctx->d_items.p + first, H, W,
-                                                                     ctx->d_partials.p + first * kSplit * 2);
-        PDQ_CUDA(cudaGetLastError(), "pdq_sum_kernel");
-        ctx->launches += 1;
-    }
+    pdq_sum_kernel<<<(unsigned)ctx->sum_ctas.size(), kThreads, 0, ctx->stream>>>(ctx->d_corners.p, ctx->pool.p, ctx->d_items.p,
+                                                                                 ctx->d_sum_ctas.p, H, W, ctx->d_partials.p);
+    PDQ_CUDA(cudaGetLastError(), "pdq_sum_kernel");
+    ctx->launches += 1;
     ctx->partials.resize(ni * kSplit * 2);
     PDQ_CUDA(cudaMemcpyAsync(ctx->partials.data(), ctx->d_partials.p, sizeof(double) * ni * kSplit * 2, cudaMemcpyDeviceToHost, ctx->stream), "D2H partials");
     rc = finish_timing(ctx);
@@ -630,7 +685,7 @@ extern "C" int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t*
     std::vector<double> fg_item(ni), bg_item(ni);
     for (size_t i = 0; i < ni; ++i) {
         double f = 0, b = 0;
-        for (int s = 0; s < kSplit; ++s) { f += ctx->partials[(i * kSplit + s) * 2]; b += ctx->partials[(i * kSplit + s) * 2 + 1]; }
+        for (int s = 0; s < ctx->items[i].nsplit; ++s) { f += ctx->partials[(i * kSplit + s) * 2]; b += ctx->partials[(i * kSplit + s) * 2 + 1]; }
         fg_item[i] = f; bg_item[i] = b;
     }
     for (const Slot& s : slots)
