@@ -20,3 +20,8 @@ for tool in memcheck racecheck initcheck synccheck; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_pdq.py > gpurun_out/sanitize_${tool}_pdq.log 2>&1
   echo "$tool pdq: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|pdq ok' gpurun_out/sanitize_${tool}_pdq.log | tr '\n' ' ')"
 done
+# optional: memcheck over the whole GPU test suite (slow: ~10 min).  bash scripts/sanitize_gpu.sh suite
+if [ "${1:-}" = "suite" ]; then
+  timeout 1500 compute-sanitizer --tool memcheck --print-limit 30 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/sanitize_memcheck_suite.log 2>&1
+  echo "memcheck suite: $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/sanitize_memcheck_suite.log | tr '\n' ' ')"
+fi

@@ -108,6 +108,33 @@ def test_host_qualities_from_golden_losses():
         assert [res["TP"], res["FP"], res["FN"]] == g["res_counts"].tolist()
 
 
+def test_host_rejects_non_box_ground_truth_and_handles_empty_images():
+    """The evaluator's host half: masks that are not their box are refused (no silent approximation); images without
+    objects or without detections never reach the GPU and follow pdq.py:351-368."""
+    from bayes_od_rc_b200 import pdq as ppdq
+    H, W = 64, 96
+    gt = ppdq.GroundTruthBox([10, 12, 40, 50], 1, (H, W))
+    gt.segmentation_mask = np.zeros((H, W), bool)
+    gt.segmentation_mask[12:50, 10:40] = True
+    assert ppdq._num_pixels(gt, (H, W)) == 30 * 38 == gt.num_pixels
+    gt.segmentation_mask[0, 0] = True                      # a pixel outside the box
+    with pytest.raises(ValueError):
+        ppdq._num_pixels(gt, (H, W))
+    gt.segmentation_mask[0, 0] = False
+    gt.segmentation_mask[20, 20] = False                   # a hole
+    with pytest.raises(ValueError):
+        ppdq._num_pixels(gt, (H, W))
+    big = ppdq.GroundTruthBox([0, 0, 50, 50], 0, (H, W))
+    tiny = ppdq.GroundTruthBox([0, 0, 5, 50], 0, (H, W))     # too narrow to count (pdq.py:455-471)
+    det = ppdq.PBoxDet(np.array([0.9, 0.1]), [1, 1, 20, 20], [np.eye(2), np.eye(2)])
+    res, tables = ppdq._qual_img([big, tiny], [], [big.num_pixels, tiny.num_pixels], None, None, None)
+    assert tables is None and res == {'overall': 0.0, 'spatial': 0.0, 'label': 0.0, 'TP': 0, 'FP': 0, 'FN': 1}
+    res, _ = ppdq._qual_img([], [det, det], [], None, None, None)
+    assert (res['TP'], res['FP'], res['FN']) == (0, 2, 0)
+    clipped = ppdq.GroundTruthBox([80, 50, 120, 90], 0, (H, W))      # box reaching past the image: mask slicing clips it
+    assert clipped.num_pixels == (96 - 80) * (64 - 50)
+
+
 def test_det_instances_from_arrays_follow_compute_pdq():
     """compute_pdq.py:93-124 on the golden's saved arrays gives the boxes / corner covariances the golden was minted with."""
     from bayes_od_rc_b200 import pdq as ppdq
@@ -242,6 +269,29 @@ def test_gpu_full_size_batch_against_oracle(engines):
         np.testing.assert_allclose(tot[do[i]:do[i + 1]], otot, rtol=1e-6, atol=1e-6)
         f1, b1, t1 = eng.losses([0, len(b)], b, c, [0, len(g)], g)
         assert np.array_equal(f1[0], fgs[i]) and np.array_equal(b1[0], bgs[i]) and np.array_equal(t1, tot[do[i]:do[i + 1]])
+
+
+@pytest.mark.gpu
+def test_gpu_evaluator_mixed_batch(engines):
+    """PDQ.score over a batch mixing ordinary images with images that have no detections / no objects: same totals
+    as scoring the images one at a time (add_img_eval), batch size irrelevant."""
+    from bayes_od_rc_b200 import pdq as ppdq
+    g = load("pdq_small")
+    H, W = (int(v) for v in g["img_size"])
+    gts = [ppdq.GroundTruthBox(b, l, (H, W)) for b, l in zip(g["gt_boxes"], g["gt_labels"])]
+    dets = [ppdq.PBoxDet(c, b, cv) for c, b, cv in zip(g["cat_param"], g["boxes"], g["covs"])]
+    matches = [(gts, dets), (gts, []), ([], dets), ([], []), (gts[:2], dets[1:4])]
+    a = ppdq.PDQ((H, W), images_per_call=2)
+    b = ppdq.PDQ((H, W), images_per_call=64)
+    c = ppdq.PDQ((H, W))
+    sa, sb = a.score(matches), b.score(matches)
+    for m in matches:
+        c.add_img_eval(*m)
+    assert sa == sb == c.get_pdq_score()
+    assert a.get_assignment_counts() == b.get_assignment_counts() == c.get_assignment_counts()
+    tp, fp, fn = a.get_assignment_counts()
+    assert fp >= len(dets) and fn >= sum(1 for x in gts if ppdq._is_gt_included(x, x.num_pixels))
+    assert 0 < a.get_avg_spatial_score() <= 1 and 0 < a.get_avg_label_score() <= 1 and 0 < a.get_avg_overall_quality_score() <= 1
 
 
 @pytest.mark.gpu
