@@ -298,7 +298,7 @@ __device__ __forceinline__ float heat_value(const Corner& c1, const Corner& c2, 
 // ---------------------------------------------------------------------------------------------------------------
 // P3: loss sums of one work item.  Rows are interleaved over (the item's 1..kSplit CTAs) x (8 warps); a warp walks one row with
 // everything that depends on the row only (table row, border term, "below the ROI" flag of both corners) hoisted.
-// partials[(item * kSplit + split) * 2 + {fg, bg}]
+// partials[cta * 2 + {fg, bg}]: the CTAs of an item are consecutive, the host adds them in order
 // ---------------------------------------------------------------------------------------------------------------
 struct RowView {                 // one row of gen_single_heatmap's map, in the corner's own frame
     const float* row;            // table row (clamped to the ROI's last row)
@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(kThreads) pdq_sum_kernel(const Corner* __restr
     if (threadIdx.x == 0) {
         double f = 0, b = 0;
         for (int i = 0; i < kThreads / 32; ++i) { f += red[0][i]; b += red[1][i]; }
-        partials[((size_t)me.item * kSplit + me.split) * 2 + 0] = f;
-        partials[((size_t)me.item * kSplit + me.split) * 2 + 1] = b;
+        partials[(size_t)blockIdx.x * 2 + 0] = f;
+        partials[(size_t)blockIdx.x * 2 + 1] = b;
     }
 }
 
@@ -671,21 +671,22 @@ extern "C" int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t*
     PDQ_CUDA(ctx->d_sum_ctas.reserve(ctx->sum_ctas.size()), "alloc CTA list");
     PDQ_CUDA(cudaMemcpyAsync(ctx->d_sum_ctas.p, ctx->sum_ctas.data(), sizeof(SumCta) * ctx->sum_ctas.size(), cudaMemcpyHostToDevice, ctx->stream), "H2D CTA list");
     PDQ_CUDA(ctx->d_items.reserve(ni), "alloc items");
-    PDQ_CUDA(ctx->d_partials.reserve(ni * kSplit * 2), "alloc partials");
+    const size_t nc = ctx->sum_ctas.size();
+    PDQ_CUDA(ctx->d_partials.reserve(nc * 2), "alloc partials");
     PDQ_CUDA(cudaMemcpyAsync(ctx->d_items.p, ctx->items.data(), sizeof(Item) * ni, cudaMemcpyHostToDevice, ctx->stream), "H2D items");
     pdq_sum_kernel<<<(unsigned)ctx->sum_ctas.size(), kThreads, 0, ctx->stream>>>(ctx->d_corners.p, ctx->pool.p, ctx->d_items.p,
                                                                                  ctx->d_sum_ctas.p, H, W, ctx->d_partials.p);
     PDQ_CUDA(cudaGetLastError(), "pdq_sum_kernel");
     ctx->launches += 1;
-    ctx->partials.resize(ni * kSplit * 2);
-    PDQ_CUDA(cudaMemcpyAsync(ctx->partials.data(), ctx->d_partials.p, sizeof(double) * ni * kSplit * 2, cudaMemcpyDeviceToHost, ctx->stream), "D2H partials");
+    ctx->partials.resize(nc * 2);
+    PDQ_CUDA(cudaMemcpyAsync(ctx->partials.data(), ctx->d_partials.p, sizeof(double) * nc * 2, cudaMemcpyDeviceToHost, ctx->stream), "D2H partials");
     rc = finish_timing(ctx);
     if (rc != BOD_OK) return rc;
     // fixed-order reduction of the kSplit partial sums
     std::vector<double> fg_item(ni), bg_item(ni);
-    for (size_t i = 0; i < ni; ++i) {
+    for (size_t i = 0, c = 0; i < ni; ++i) {
         double f = 0, b = 0;
-        for (int s = 0; s < ctx->items[i].nsplit; ++s) { f += ctx->partials[(i * kSplit + s) * 2]; b += ctx->partials[(i * kSplit + s) * 2 + 1]; }
+        for (int s = 0; s < ctx->items[i].nsplit; ++s, ++c) { f += ctx->partials[c * 2]; b += ctx->partials[c * 2 + 1]; }
         fg_item[i] = f; bg_item[i] = b;
     }
     for (const Slot& s : slots)
