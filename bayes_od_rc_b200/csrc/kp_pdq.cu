@@ -12,9 +12,10 @@
 // G dense boolean masks.  Here nothing dense exists unless asked for (bod_pdq_heatmaps):
 //   P1 pdq_roi_kernel     one CTA per Gaussian corner: the Mahalanobis window scan of find_roi, block-reduced to the ROI
 //   P2 pdq_table_kernel   the CDF of every ROI pixel (binary64 Genz BVND; the Gauss-Legendre nodes depend on the
-//                         corner only: P1 computes them once, P2 keeps them in shared memory) + the two "outside
-//                         the image" border vectors, as one compact float32 table per corner, 1024 entries per CTA;
-//                         every other pixel of a corner's map is a replica of a table entry
+//                         corner only: P1 computes them once, P2 keeps them in shared memory; along a table row the
+//                         quadrature terms follow a two-multiplication recurrence instead of one exp each) + the two
+//                         "outside the image" border vectors, as one compact float32 table per corner; every other
+//                         pixel of a corner's map is a replica of a table entry
 //   P3 pdq_sum_kernel     one work item per (detection, overlapping ground-truth box) and one per detection for the
 //                         whole-image term: heat-map pixels are rebuilt from the two tables on the fly, log terms in
 //                         binary32 like numpy's, sums in binary64, split over kSplit CTAs with a fixed reduction order
@@ -32,6 +33,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <exception>
+#include <new>
 #include <vector>
 
 #include "../../include/bayesod.h"
@@ -239,39 +242,80 @@ __global__ void __launch_bounds__(kThreads) pdq_roi_kernel(const int32_t* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// P2: CDF tables.  One CTA per chunk of kChunk table entries (the host lays the chunks out after reading the ROIs
-// back).  Entries of a corner: P [rh*rw] | outx [rh] | outy [rw] | c00.
+// P2: CDF tables.  Entries of a corner: P [rh*rw] | outx [rh] | outy [rw] | c00.
+// Work unit = one thread: a run of kRun consecutive columns of one table row, or one border entry; one CTA per chunk
+// of kThreads units (the host lays the chunks out after reading the ROIs back).
+// Along a row only k = (x - mean_x) / sigma_x changes, in equal steps dk, and every quadrature term of the
+// |r| < 0.925 branch is exp(f(k)) with f quadratic in k:  f(k) = inv_i (sn_i h k - h^2/2 - k^2/2).  So a run needs two
+// exp per node (the term E and its step ratio Q at the first column) and then two multiplications per node and column:
+//   E(k + dk) = E(k) Q(k),   Q(k + dk) = Q(k) G,   G = exp(-inv_i dk^2)  (per corner and node)
+// instead of one exp per node and column (5x fewer FP64 instructions; the relative error grows by ~2e-16 per step,
+// far below the float32 rounding of the table).  Runs whose arguments leave the range where E cannot underflow, steps
+// larger than 2 sigma, and the high-correlation branch evaluate every column directly.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kChunk = 4 * kThreads;
+constexpr int kRun = 16;
 
-struct Chunk { int32_t corner, first; };
+struct Chunk { int32_t corner, first; };    // first work unit of the chunk
+
+__host__ __device__ inline int runs_per_row(int rw) { return (rw + kRun - 1) / kRun; }
 
 __global__ void __launch_bounds__(kThreads) pdq_table_kernel(Corner* __restrict__ corners, const Quad* __restrict__ quads,
                                                              const Chunk* __restrict__ chunks, float* __restrict__ pool) {
     __shared__ Corner c;
     __shared__ Quad q;
+    __shared__ double sG[20];
     const Chunk ch = chunks[blockIdx.x];
     if (threadIdx.x == 0) c = corners[ch.corner];
     for (int i = threadIdx.x; i < (int)(sizeof(Quad) / sizeof(double)); i += kThreads)
         reinterpret_cast<double*>(&q)[i] = reinterpret_cast<const double*>(quads + ch.corner)[i];
     __syncthreads();
-    const double sy = sqrt(c.cov[0]), sx = sqrt(c.cov[3]);
-    const int rh = c.y2 - c.y1 + 1, rw = c.x2 - c.x1 + 1;
-    const int np = rh * rw, total = np + rh + rw + 1, last = min(total, ch.first + kChunk);
+    const double sy = sqrt(c.cov[0]), sx = sqrt(c.cov[3]), dk = 1.0 / sx;
+    if (threadIdx.x < 20) sG[threadIdx.x] = threadIdx.x < q.n ? exp(-q.inv[threadIdx.x] * dk * dk) : 0.0;
+    __syncthreads();
+    const int rh = c.y2 - c.y1 + 1, rw = c.x2 - c.x1 + 1, rpr = runs_per_row(rw);
+    const int np = rh * rw, nruns = rh * rpr, total = nruns + rh + rw + 1;
+    const int u = ch.first + (int)threadIdx.x;
+    if (u >= total) return;
     float* tab = pool + c.off;
-    for (int e = ch.first + threadIdx.x; e < last; e += kThreads) {
-        if (e < np) {                                                        // :199-207
-            const int ry = e / rw, rx = e - ry * rw;
-            tab[e] = (float)corner_cdf(c, q, sy, sx, (double)(c.y1 + ry + 1) - kSmall, (double)(c.x1 + rx + 1) - kSmall);
-        } else if (e < np + rh) {                                            // :217-223 (used when x1 == 0)
-            const int ry = e - np;
-            tab[e] = c.x1 == 0 ? (float)corner_cdf(c, q, sy, sx, (double)(c.y1 + ry + 1) - kSmall, 0.0 - kSmall) : 0.f;
-        } else if (e < np + rh + rw) {                                       // :230-235 (used when y1 == 0)
-            const int rx = e - np - rh;
-            tab[e] = c.y1 == 0 ? (float)corner_cdf(c, q, sy, sx, 0.0 - kSmall, (double)(c.x1 + rx + 1) - kSmall) : 0.f;
-        } else {                                                             // :240-241
-            corners[ch.corner].c00 = (c.x1 == 0 && c.y1 == 0) ? corner_cdf(c, q, sy, sx, 0.0 - kSmall, 0.0 - kSmall) : 0.0;
+    if (u < nruns) {                                                         // :199-207
+        const int ry = u / rpr, x0 = (u - ry * rpr) * kRun, n = min(kRun, rw - x0);
+        const double h = (((double)(c.y1 + ry + 1) - kSmall) - c.mean[0]) / sy;
+        const double k0 = (((double)(c.x1 + x0 + 1) - kSmall) - c.mean[1]) / sx;
+        const double k1 = (((double)(c.x1 + x0 + n) - kSmall) - c.mean[1]) / sx;
+        float* out = tab + (long long)ry * rw + x0;
+        const bool stepped = q.n > 0 && dk <= 2.0 && fabs(h) <= 7.0 && fabs(k0) <= 7.0 && fabs(k1) <= 7.0;
+        if (stepped) {
+            double acc[kRun];
+#pragma unroll
+            for (int j = 0; j < kRun; ++j) acc[j] = 0.0;
+            const double hh = h * h;
+            for (int i = 0; i < q.n; ++i) {
+                const double inv = q.inv[i], a = q.sn[i] * h, w = q.w[i], G = sG[i];
+                double E = exp((a * k0 - (hh + k0 * k0) / 2) * inv);         // the term of the direct evaluation at k0
+                double Q = exp(((a - k0) * dk - dk * dk / 2) * inv);
+#pragma unroll
+                for (int j = 0; j < kRun; ++j) { acc[j] += w * E; E *= Q; Q *= G; }
+            }
+            const double ph = phi(h);
+#pragma unroll
+            for (int j = 0; j < kRun; ++j)
+                if (j < n) {
+                    const double k = (((double)(c.x1 + x0 + j + 1) - kSmall) - c.mean[1]) / sx;
+                    const double v = acc[j] * q.scale + ph * phi(k);
+                    out[j] = (float)(v < 0 ? 0 : v > 1 ? 1 : v);
+                }
+        } else {
+            for (int j = 0; j < n; ++j)
+                out[j] = (float)bvn_cdf(q, h, (((double)(c.x1 + x0 + j + 1) - kSmall) - c.mean[1]) / sx);
         }
+    } else if (u < nruns + rh) {                                             // :217-223 (used when x1 == 0)
+        const int ry = u - nruns;
+        tab[np + ry] = c.x1 == 0 ? (float)corner_cdf(c, q, sy, sx, (double)(c.y1 + ry + 1) - kSmall, 0.0 - kSmall) : 0.f;
+    } else if (u < nruns + rh + rw) {                                        // :230-235 (used when y1 == 0)
+        const int rx = u - nruns - rh;
+        tab[np + rh + rx] = c.y1 == 0 ? (float)corner_cdf(c, q, sy, sx, 0.0 - kSmall, (double)(c.x1 + rx + 1) - kSmall) : 0.f;
+    } else {                                                                 // :240-241
+        corners[ch.corner].c00 = (c.x1 == 0 && c.y1 == 0) ? corner_cdf(c, q, sy, sx, 0.0 - kSmall, 0.0 - kSmall) : 0.0;
     }
 }
 
@@ -425,6 +469,23 @@ __global__ void pdq_bvn_probe_kernel(int n, const double* __restrict__ h, const 
     out[i] = bvn_cdf(q, h[i], k[i]);
 }
 
+// std::vector storage in page-locked host memory: the small per-call lists (ROIs, work lists, partial sums) cross
+// PCIe with real asynchronous copies instead of staged ones; capacity persists across calls.
+template <class T> struct PinnedAlloc {
+    using value_type = T;
+    PinnedAlloc() = default;
+    template <class U> PinnedAlloc(const PinnedAlloc<U>&) {}
+    T* allocate(size_t n) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocDefault) != cudaSuccess) throw std::bad_alloc();
+        return static_cast<T*>(p);
+    }
+    void deallocate(T* p, size_t) { cudaFreeHost(p); }
+    template <class U> bool operator==(const PinnedAlloc<U>&) const { return true; }
+    template <class U> bool operator!=(const PinnedAlloc<U>&) const { return false; }
+};
+template <class T> using PinnedVec = std::vector<T, PinnedAlloc<T>>;
+
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
@@ -451,14 +512,14 @@ struct bod_pdq_ctx {
     DevBuf<Corner> d_corners;
     DevBuf<Quad> d_quads;
     DevBuf<Chunk> d_chunks;
-    std::vector<Chunk> chunks;
+    PinnedVec<Chunk> chunks;
     DevBuf<Item> d_items;
     DevBuf<SumCta> d_sum_ctas;
-    std::vector<SumCta> sum_ctas;
+    PinnedVec<SumCta> sum_ctas;
     DevBuf<float> pool, d_maps;
-    std::vector<Corner> corners;
-    std::vector<Item> items;
-    std::vector<double> partials;
+    PinnedVec<Corner> corners;
+    PinnedVec<Item> items;
+    PinnedVec<double> partials;
     float ms[3] = {0, 0, 0};
     int64_t table_floats = 0, launches = 0;
     char err[256] = {0};
@@ -510,7 +571,8 @@ int build_tables(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxes, const double
         c.off = off;
         const long long rh = c.y2 - c.y1 + 1, rw = c.x2 - c.x1 + 1, entries = rh * rw + rh + rw + 1;
         off += (entries + 3) & ~3LL;
-        for (long long first = 0; first < entries; first += kChunk) ctx->chunks.push_back(Chunk{(int32_t)i, (int32_t)first});
+        const long long units = rh * runs_per_row((int)rw) + rh + rw + 1;
+        for (long long first = 0; first < units; first += kThreads) ctx->chunks.push_back(Chunk{(int32_t)i, (int32_t)first});
     }
     ctx->table_floats = off;
     PDQ_CUDA(ctx->pool.reserve((size_t)std::max<long long>(off, 4)), "alloc table pool");
@@ -579,9 +641,7 @@ extern "C" int bod_pdq_last_ms(const bod_pdq_ctx* ctx, float ms[3], int64_t* tab
     return BOD_OK;
 }
 
-extern "C" int bod_pdq_heatmaps(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxes, const double* covs, float* out,
-                                int32_t out_on_device) {
-    if (!ctx) return BOD_ERR_INVALID;
+static int heatmaps_impl(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxes, const double* covs, float* out, int32_t out_on_device) {
     if (D < 0 || (D && (!boxes || !covs || !out))) return fail(ctx, BOD_ERR_INVALID, "bod_pdq_heatmaps: bad argument");
     ctx->launches = 0;
     if (D == 0) return BOD_OK;
@@ -608,10 +668,20 @@ extern "C" int bod_pdq_heatmaps(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxe
     return BOD_OK;
 }
 
-extern "C" int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t* det_offsets, const int32_t* boxes,
-                              const double* covs, const int32_t* gt_offsets, const int32_t* gt_boxes, double* fg_loss,
-                              double* bg_loss, double* bg_total) {
+// No C++ exception may cross the C ABI: host-side allocation failures (pinned or pageable) become BOD_ERR_NOMEM.
+extern "C" int bod_pdq_heatmaps(bod_pdq_ctx* ctx, int32_t D, const int32_t* boxes, const double* covs, float* out,
+                                int32_t out_on_device) {
     if (!ctx) return BOD_ERR_INVALID;
+    try {
+        return heatmaps_impl(ctx, D, boxes, covs, out, out_on_device);
+    } catch (const std::exception&) {
+        cudaStreamSynchronize(ctx->stream);
+        return fail(ctx, BOD_ERR_NOMEM, "bod_pdq_heatmaps: host allocation failed");
+    }
+}
+
+static int losses_impl(bod_pdq_ctx* ctx, int32_t n_images, const int32_t* det_offsets, const int32_t* boxes, const double* covs,
+                       const int32_t* gt_offsets, const int32_t* gt_boxes, double* fg_loss, double* bg_loss, double* bg_total) {
     if (n_images < 0 || (n_images && (!det_offsets || !gt_offsets))) return fail(ctx, BOD_ERR_INVALID, "bod_pdq_losses: bad argument");
     ctx->launches = 0;
     if (n_images == 0) return BOD_OK;
@@ -702,6 +772,18 @@ extern "C" int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t*
         pair_base += (size_t)ng * nd;
     }
     return BOD_OK;
+}
+
+extern "C" int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t* det_offsets, const int32_t* boxes,
+                              const double* covs, const int32_t* gt_offsets, const int32_t* gt_boxes, double* fg_loss,
+                              double* bg_loss, double* bg_total) {
+    if (!ctx) return BOD_ERR_INVALID;
+    try {
+        return losses_impl(ctx, n_images, det_offsets, boxes, covs, gt_offsets, gt_boxes, fg_loss, bg_loss, bg_total);
+    } catch (const std::exception&) {
+        cudaStreamSynchronize(ctx->stream);
+        return fail(ctx, BOD_ERR_NOMEM, "bod_pdq_losses: host allocation failed");
+    }
 }
 
 extern "C" int bod_pdq_bvn_cdf(bod_pdq_ctx* ctx, int32_t n, const double* h, const double* k, const double* r, double* out) {
