@@ -259,7 +259,7 @@ struct Chunk { int32_t corner, first; };    // first work unit of the chunk
 
 __host__ __device__ inline int runs_per_row(int rw) { return (rw + kRun - 1) / kRun; }
 
-__global__ void __launch_bounds__(kThreads) pdq_table_kernel(Corner* __restrict__ corners, const Quad* __restrict__ quads,
+__global__ void __launch_bounds__(kThreads, 3) pdq_table_kernel(Corner* __restrict__ corners, const Quad* __restrict__ quads,
                                                              const Chunk* __restrict__ chunks, float* __restrict__ pool) {
     __shared__ Corner c;
     __shared__ Quad q;
