@@ -297,6 +297,17 @@ def test_generated_anchors_bit_exact():
         assert lib.bod_generate_anchors(h, w, buf.data_ptr(), None) == A
         torch.cuda.synchronize()
         assert_bit_equal(buf.cpu().numpy(), oracle.generate_anchors(h, w), f"anchors {h}x{w}")
+    # and against the digests of the reference generator's own output (tests/golden/make_anchor_digests.py)
+    import hashlib
+    import json
+    import os
+    digests = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "anchor_digests.json")))
+    for key, want in digests.items():
+        h, w = (int(v) for v in key.split("x"))
+        buf = torch.empty(want["A"], 4, device="cuda")
+        assert lib.bod_generate_anchors(h, w, buf.data_ptr(), None) == want["A"]
+        torch.cuda.synchronize()
+        assert hashlib.sha256(buf.cpu().numpy().tobytes()).hexdigest() == want["sha256"], key
 
 
 def test_anchor_generate_mode_equals_tensor_mode():

@@ -26,6 +26,25 @@ def test_anchors_bit_exact(name):
     assert np.array_equal(mine.view(np.uint32), g["anchors"].view(np.uint32))
 
 
+def test_anchors_full_size_digests():
+    """Oracle and the host mirror (bayes_od_rc_b200/anchors.py) against SHA-256 digests of the reference generator's output
+    for the image shapes of BASELINE.json's configs and some odd ones (tests/golden/make_anchor_digests.py)."""
+    import hashlib
+    import json
+    import os
+    from helpers import GOLDEN_DIR
+    from bayes_od_rc_b200 import anchors as host_anchors
+    digests = json.load(open(os.path.join(GOLDEN_DIR, "anchor_digests.json")))
+    assert len(digests) >= 7
+    for key, want in digests.items():
+        h, w = (int(v) for v in key.split("x"))
+        for name, arr in (("oracle", oracle.generate_anchors(h, w)), ("host mirror", host_anchors.generate_anchors(h, w))):
+            arr = np.ascontiguousarray(arr, np.float32)
+            assert arr.shape == (want["A"], 4), (key, name)
+            assert hashlib.sha256(arr.tobytes()).hexdigest() == want["sha256"], (key, name)
+        assert host_anchors.num_anchors(h, w) == want["A"]
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_inference_half(name):
     """bayes_od_inference outputs (inference_utils.py:217)."""
