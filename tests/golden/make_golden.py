@@ -69,7 +69,7 @@ def ids_from_counts(counts: np.ndarray, T: int) -> np.ndarray:
     return ids
 
 
-def run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical):
+def run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical, store_inputs=True):
     spec = synthetic.SceneSpec(**spec_kw)
     # anchors from the REFERENCE's generator (fpn_anchor_generator.py:21-59), P3->P7
     gen = ag.FpnAnchorGenerator(dict(aspect_ratios=[[1.0, 1.0], [1.0, 2.0], [2.0, 1.0]], scales=[1.0, 1.26, 1.59]))
@@ -118,11 +118,31 @@ def run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical):
     meta = dict(case=name, spec=spec_kw, cfg=cfg, dataset_name=dataset_name, orig_size=list(orig),
                 image_shape=[spec.im_h, spec.im_w], has_cov=not ov.get("drop_cov", False),
                 numpy=np.__version__, generator="tests/golden/make_golden.py over tf_numpy_shim; reference sources executed verbatim")
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), anchors=anchors,
-                        cls=cls16, box=box16, cov=cov16, counts=counts.astype(np.uint8), **res)
+    if store_inputs:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), anchors=anchors,
+                            cls=cls16, box=box16, cov=cov16, counts=counts.astype(np.uint8), **res)
+    else:
+        import hashlib
+        hsh = hashlib.sha256()
+        for arr in (anchors, cls16, box16, cov16, counts.astype(np.uint8)):
+            hsh.update(np.ascontiguousarray(arr).tobytes())
+        meta["input_sha256"] = hsh.hexdigest()
+        meta["inputs"] = "regenerate: synthetic.make_image(SceneSpec(**spec), 0, anchors, 'cpu', with_counts=True), float16-rounded"
+        res.pop("iou_cols")                                     # [S, D] float32: replaced by the membership bits below
+        res["members"] = np.packbits(iou_mat[:, nms_idx] > cfg["nms_config"]["iou_threshold"], axis=0)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), **res)
     S, D = len(cnt_post), len(nms_idx)
     members = (iou_mat[:, nms_idx] > 0.5).sum(0) if S else []
     print(f"{name:16s} A={len(anchors)} S={S} D={D} members(min/max)={min(members, default=0)}/{max(members, default=0)}")
+
+
+# Full-size images (BASELINE.json shapes).  Inputs are NOT stored (hundreds of MB): the fixture keeps the generator
+# arguments and a SHA-256 of the exact input bytes; tests regenerate them with the same seeded generator
+# (bayes_od_rc_b200/synthetic.py on the CPU) and skip if the digest differs (another torch RNG).
+FULL_CASES = {
+    "full_bdd_covar_k8": (dict(im_h=720, im_w=1280, N=10, K=8, config_id=31), {}),
+    "full_kitti_k4_n20": (dict(im_h=375, im_w=1242, N=20, K=4, config_id=32), dict(dataset_name='kitti', orig_size=(375, 1242))),
+}
 
 
 VAL_CASES = {
@@ -162,10 +182,13 @@ def run_val_case(name, spec_kw, ov, vu, ag, cs):
 
 def main():
     iu, bu, ag, cs, Categorical = shim.load_reference()
-    only_val = "--val-only" in sys.argv
+    only_val = "--val-only" in sys.argv or "--full" in sys.argv
     if not only_val:
         for name, (spec_kw, ov) in CASES.items():
             run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical)
+    if not only_val or "--full" in sys.argv:
+        for name, (spec_kw, ov) in FULL_CASES.items():
+            run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical, store_inputs=False)
     import importlib
     vu = importlib.import_module("src.retina_net.experiments.validation_utils")
     for name, (spec_kw, ov) in VAL_CASES.items():
