@@ -36,6 +36,7 @@ CASES = {
     "pdq_borders": (80, 120, 2, 3, 6, (0.05, 1.0), True),
     "pdq_tight":   (64, 96, 3, 2, 4, (0.001, 0.01), False),
     "pdq_wide":    (120, 200, 4, 5, 5, (0.5, 3.0), True),
+    "pdq_full":    (720, 1280, 5, 3, 4, (0.05, 0.6), False),      # the size bdd/compute_pdq.py evaluates
 }
 
 
