@@ -142,6 +142,8 @@ def run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical, store_inputs=True):
 FULL_CASES = {
     "full_bdd_covar_k8": (dict(im_h=720, im_w=1280, N=10, K=8, config_id=31), {}),
     "full_kitti_k4_n20": (dict(im_h=375, im_w=1242, N=20, K=4, config_id=32), dict(dataset_name='kitti', orig_size=(375, 1242))),
+    "full_bdd_kendall_k11": (dict(im_h=720, im_w=1280, N=10, K=11, config_id=33), dict(use_full_covar=False)),
+    "full_bdd_entropy_k8": (dict(im_h=720, im_w=1280, N=6, K=8, config_id=34), dict(ranking='joint_entropy')),
 }
 
 

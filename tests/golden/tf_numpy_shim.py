@@ -177,6 +177,25 @@ def fill_triangular(x):
     return _t(np.tril(full))
 
 
+def _reduce_sum(x, axis=None, keepdims=False):
+    """tf.reduce_sum.  The order in which TensorFlow adds the terms is internal to its (Eigen / GPU) reduction kernels and
+    differs between devices and versions; for binary32 it matters as soon as the terms are inexact, e.g. the Dirichlet
+    counts + 1/K at inference_utils.py:96-97 with K = 11, whose row sums feed the ranking score and through it the order of
+    soft-NMS selections among candidates one ulp apart.  This build fixes the order the way its arithmetic contract does
+    (reductions sequential in index order), and the shim follows it for reductions over one axis of a float
+    array, so that the fixtures pin everything else; numpy's own pairwise order would be just as arbitrary a stand-in."""
+    a = _raw(x)
+    if axis is None or not np.issubdtype(a.dtype, np.floating) or isinstance(axis, (tuple, list)):
+        return _t(np.sum(a, axis=axis, keepdims=keepdims))
+    m = np.moveaxis(a, axis, 0)
+    acc = m[0].copy()
+    for k in range(1, m.shape[0]):
+        acc = acc + m[k]                      # one correctly rounded addition per term, in index order
+    if keepdims:
+        acc = np.expand_dims(acc, axis)
+    return _t(acc)
+
+
 def install():
     """Put fake `tensorflow` / `tensorflow_probability` modules in sys.modules."""
     tf = types.ModuleType("tensorflow")
@@ -193,7 +212,7 @@ def install():
     tf.less_equal = lambda a, b: _t(np.less_equal(_raw(a), _raw(b)))
     tf.argmax = lambda x, axis=None, name=None: _t(np.argmax(_raw(x), axis=axis).astype(np.int64))
     tf.reduce_mean = lambda x, axis=None, keepdims=False: _t(np.mean(_raw(x), axis=axis, keepdims=keepdims, dtype=_raw(x).dtype))
-    tf.reduce_sum = lambda x, axis=None, keepdims=False: _t(np.sum(_raw(x), axis=axis, keepdims=keepdims))
+    tf.reduce_sum = _reduce_sum
     tf.reduce_max = lambda x, axis=None, keepdims=False: _t(np.max(_raw(x), axis=axis, keepdims=keepdims))
     tf.reduce_min = lambda x, axis=None, keepdims=False: _t(np.min(_raw(x), axis=axis, keepdims=keepdims))
     tf.reduce_any = lambda x, axis=None: _t(np.any(_raw(x), axis=axis))

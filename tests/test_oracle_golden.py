@@ -106,7 +106,10 @@ def test_stage_isolated_nms_and_clustering(name):
     corners = np.stack([mu[:, 0] - mu[:, 2] / np.float32(2), mu[:, 1] - mu[:, 3] / np.float32(2),
                         mu[:, 0] + mu[:, 2] / np.float32(2), mu[:, 1] + mu[:, 3] / np.float32(2)], 1).astype(np.float32)
     if cfg.ranking_method == "score":
-        p = g["cnt_post"] / g["cnt_post"].sum(1, keepdims=True)
+        tot = g["cnt_post"][:, 0].copy()                      # row sums in index order (numpy's pairwise
+        for k in range(1, g["cnt_post"].shape[1]):            # order differs by an ulp when 1/K is inexact, e.g. K = 11)
+            tot = tot + g["cnt_post"][:, k]
+        p = g["cnt_post"] / tot[:, None]
         score = p.max(1).astype(np.float32)
         sel, _ = oracle.nms_v5(corners, score, cfg.max_output_size, cfg.iou_threshold, -np.inf, cfg.soft_nms_sigma)
         assert np.array_equal(sel, g["nms_indices"])
