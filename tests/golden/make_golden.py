@@ -153,6 +153,10 @@ VAL_CASES = {
     "val_kitti_k4": (dict(im_h=64, im_w=128, N=2, K=4, g_min=3, g_max=5, box_hi=60., config_id=22),
                      dict(dataset_name='kitti', orig_size=(47, 94))),
     "val_none_k8":  (dict(im_h=64, im_w=96, N=2, K=8, g_min=3, g_max=4, box_hi=60., config_id=23), dict(all_background=True)),
+    # full size: outputs + input digest only (see FULL_CASES)
+    "val_full_bdd_k8": (dict(im_h=720, im_w=1280, N=2, K=8, config_id=24), dict(digest_only=True)),
+    "val_full_kitti_k4": (dict(im_h=375, im_w=1242, N=2, K=4, config_id=25),
+                          dict(dataset_name='kitti', orig_size=(370, 1224), digest_only=True)),
 }
 
 
@@ -177,8 +181,19 @@ def run_val_case(name, spec_kw, ov, vu, ag, cs):
     meta = dict(case=name, spec=spec_kw, dataset_name=dataset_name, orig_size=list(orig), image_shape=[spec.im_h, spec.im_w],
                 numpy=np.__version__, generator="tests/golden/make_golden.py over tf_numpy_shim; "
                 "validation_utils.post_process_predictions executed verbatim")
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), anchors=anchors, cls=cls16, box=box16,
-                        classes_out=classes_out.reshape(-1, spec.K), corners_out=corners_out.reshape(-1, 4))
+    if ov.get("digest_only"):
+        import hashlib
+        hsh = hashlib.sha256()
+        for arr in (anchors, cls16, box16):
+            hsh.update(np.ascontiguousarray(arr).tobytes())
+        meta["input_sha256"] = hsh.hexdigest()
+        meta["kind"] = "val"
+        meta["inputs"] = "regenerate: synthetic.make_image(SceneSpec(**spec), 0, anchors, 'cpu', with_counts=False), sample 0, float16-rounded"
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta),
+                            classes_out=classes_out.reshape(-1, spec.K), corners_out=corners_out.reshape(-1, 4))
+    else:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), anchors=anchors, cls=cls16, box=box16,
+                            classes_out=classes_out.reshape(-1, spec.K), corners_out=corners_out.reshape(-1, 4))
     print(f"{name:16s} A={len(anchors)} D={len(classes_out)}")
 
 

@@ -54,6 +54,16 @@ def _regenerate_full_inputs(g):
     meta = g["meta"]
     spec = synthetic.SceneSpec(**meta["spec"])
     anchors = oracle.generate_anchors(spec.im_h, spec.im_w)          # bit-identical to the reference's (anchor_digests.json)
+    if meta.get("kind") == "val":                                    # validation fixtures: one sample, no counts / covariances
+        img = synthetic.make_image(spec, 0, torch.from_numpy(anchors), "cpu", with_counts=False)
+        cls16, box16 = img["cls"][0].numpy().astype(np.float16), img["box"][0].numpy().astype(np.float16)
+        h = hashlib.sha256()
+        for arr in (anchors, cls16, box16):
+            h.update(np.ascontiguousarray(arr).tobytes())
+        if h.hexdigest() != meta["input_sha256"]:
+            pytest.skip(f"{meta['case']}: the seeded generator produced different bytes here (torch {torch.__version__})")
+        g.update(anchors=anchors, cls=cls16, box=box16)
+        return
     img = synthetic.make_image(spec, 0, torch.from_numpy(anchors), "cpu", with_counts=True)
     cls16, box16, cov16 = (img[k].numpy().astype(np.float16) for k in ("cls", "box", "cov"))
     counts = img["counts"].numpy().astype(np.uint8)
