@@ -210,31 +210,29 @@ def _qual_img(gts, dets, num_fg, fg, bg, bg_total):
     tables['label'][:G, :D] -= label_qual
     row_idxs, col_idxs = linear_sum_assignment(tables['overall'])                           # :377
     overall_q, spatial_q, label_q = (1 - tables[k] for k in ('overall', 'spatial', 'label'))
-    tp = fp = fn = 0
-    fp_cols = []
-    for row_id, col_id in zip(row_idxs, col_idxs):                                          # :390-406
-        included = row_id < G and _is_gt_included(gts[row_id], num_fg[row_id])
-        if overall_q[row_id, col_id] > 0:
-            if included:
-                tp += 1
-            else:
-                overall_q[row_id, col_id] = 0.0
-        else:
-            if included:
-                fn += 1
-            if col_id < D:
-                fp += 1
-                fp_cols.append(col_id)
+    # :390-406, vectorised over the assignment: a pair with positive quality is a TP if its object counts (else its
+    # quality is zeroed); a zero-quality pair is an FN if its row is a counted object and an FP if its column is a detection
+    included = np.zeros(n_pairs, bool)
+    included[:G] = [_is_gt_included(g, n) for g, n in zip(gts, num_fg)]
+    pos = overall_q[row_idxs, col_idxs] > 0
+    inc = included[row_idxs]
+    tp = int(np.count_nonzero(pos & inc))
+    overall_q[row_idxs[pos & ~inc], col_idxs[pos & ~inc]] = 0.0
+    fn = int(np.count_nonzero(~pos & inc))
+    fp_cols = col_idxs[~pos & (col_idxs < D)]
+    fp = int(fp_cols.size)
     tot_tp_overall = np.sum(overall_q[row_idxs, col_idxs])
     spatial_q[overall_q == 0] = 0.0
     label_q[overall_q == 0] = 0.0
     tot_tp_spatial = np.sum(spatial_q[row_idxs, col_idxs])
     tot_tp_label = np.sum(label_q[row_idxs, col_idxs])
-    fp_label = np.array([1.0 - np.max(label_prob[i]) for i in fp_cols])                     # :417-419
+    fp_cols = np.asarray(fp_cols, dtype=np.int64)
+    fp_label = 1.0 - label_prob[fp_cols].max(axis=1) if fp_cols.size else np.zeros(0)       # :417-419
     if fp_label.size:                                                                       # :421-432
-        area = np.array([(dets[i].box[3] - dets[i].box[1]) * (dets[i].box[2] - dets[i].box[0]) for i in fp_cols])
+        boxes = np.stack([np.asarray(d.box) for d in dets])[fp_cols]
+        area = (boxes[:, 3] - boxes[:, 1]) * (boxes[:, 2] - boxes[:, 0])                     # _compute_bb_area, :449-452
         with np.errstate(divide='ignore', invalid='ignore'):
-            fp_spatial = np.exp(np.asarray([bg_total[i] for i in fp_cols], np.float32) / area)
+            fp_spatial = np.exp(np.asarray(bg_total, np.float64)[fp_cols].astype(np.float32) / area)
         tot_fp_spatial = np.sum(fp_spatial)
         tot_fp_overall = np.sum(_gmean2(fp_spatial, fp_label))
     else:
