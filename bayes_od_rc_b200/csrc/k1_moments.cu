@@ -73,10 +73,24 @@ template <int OFF> BOD_DEVINL float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
     return v;
 }
-template <int K, int I = 0> struct LoadRow {
-    static BOD_DEVINL void run(uint32_t addr, float (&x)[K]) { x[I] = lds_f32<4 * I>(addr); LoadRow<K, I + 1>::run(addr, x); }
+template <int OFF> BOD_DEVINL void lds_v4(uint32_t addr, float& a, float& b, float& c, float& d) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr), "n"(OFF));
+}
+// One anchor's K logits of the current stage.  Rows are K floats apart (the slab is a verbatim copy of the [tile, K]
+// span of `cls`), so 32-bit loads are conflict-free only for odd K: K = 8 puts the 32 lanes on 4 banks (8-way
+// conflict, 64 wavefronts per row — the LSU pipe, not HBM, then bounds the kernel) and K = 4 on 8 banks.  For
+// K % 4 == 0 the row is read with 128-bit loads instead (K = 4: conflict-free, K = 8: 16 wavefronts per row).
+template <int K, int I = 0, bool V4 = (K % 4 == 0)> struct LoadRow {
+    static BOD_DEVINL void run(uint32_t addr, float (&x)[K]) { x[I] = lds_f32<4 * I>(addr); LoadRow<K, I + 1, V4>::run(addr, x); }
 };
-template <int K> struct LoadRow<K, K> { static BOD_DEVINL void run(uint32_t, float (&)[K]) {} };
+template <int K, int I> struct LoadRow<K, I, true> {
+    static BOD_DEVINL void run(uint32_t addr, float (&x)[K]) {
+        lds_v4<4 * I>(addr, x[I], x[I + 1], x[I + 2], x[I + 3]);
+        LoadRow<K, I + 4, true>::run(addr, x);
+    }
+};
+template <int K> struct LoadRow<K, K, false> { static BOD_DEVINL void run(uint32_t, float (&)[K]) {} };
+template <int K> struct LoadRow<K, K, true> { static BOD_DEVINL void run(uint32_t, float (&)[K]) {} };
 
 BOD_DEVINL void consumer_barrier() {   // named barrier 1: the kTileAnchors consumer threads only
     asm volatile("bar.sync 1, %0;" ::"n"(kTileAnchors) : "memory");
