@@ -342,7 +342,8 @@ __device__ __forceinline__ float heat_value(const Corner& c1, const Corner& c2, 
 // ---------------------------------------------------------------------------------------------------------------
 // P3: loss sums of one work item.  Rows are interleaved over (the item's 1..kSplit CTAs) x (8 warps); a warp walks one row with
 // everything that depends on the row only (table row, border term, "below the ROI" flag of both corners) hoisted;
-// the stretch of a row between the two corners' ROI columns is one value and is added as count x term.
+// the stretch of a row between the two corners' ROI columns is one value and is added as count x term, and the rows
+// between the two corners' ROI rows are all equal: one is summed, weighted by their number.
 // partials[cta * 2 + {fg, bg}]: the CTAs of an item are consecutive, the host adds them in order
 // ---------------------------------------------------------------------------------------------------------------
 struct RowView {                 // one row of gen_single_heatmap's map, in the corner's own frame
@@ -391,34 +392,45 @@ __global__ void __launch_bounds__(kThreads) pdq_sum_kernel(const Corner* __restr
     const float eps = (float)kSmall;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double fg = 0, bg = 0;
+    // Rows below the first corner's ROI and above the second corner's (mirrored) ROI see both corner maps in their
+    // row-replicated regime: every row of the band [ya, yb] is the same function of x.  Its first row is summed once and
+    // weighted by the number of band rows (foreground: those above fy_end); the other band rows are skipped.
+    const int ya = max(it.y_lo, c1.y2 + 1), yb = min(it.y_hi, H - 2 - c2.y2);
+    const double log_eps = (double)logf(eps);
     for (int y = it.y_lo + me.split + warp * it.nsplit; y <= it.y_hi; y += it.nsplit * (kThreads / 32)) {
+        const bool band = y >= ya && y <= yb;
+        if (band && y != ya) continue;
+        const int w_bg = band ? yb - ya + 1 : 1;
+        const int w_fg = band ? max(min(yb, it.fy_end - 1) - ya + 1, 0) : (y < it.fy_end ? 1 : 0);
         const RowView r1 = row_view(c1, pool, y), r2 = row_view(c2, pool, H - 1 - y);
-        const bool fg_row = y < it.fy_end;
         if (r1.zero || r2.zero) {                                            // the whole row of the product is zero
-            if (fg_row && lane == 0) fg += (double)max(min(it.x_hi, it.fx_end - 1) - it.x_lo + 1, 0) * (double)logf(eps);
+            if (w_fg && lane == 0) fg += (double)w_fg * (double)max(min(it.x_hi, it.fx_end - 1) - it.x_lo + 1, 0) * log_eps;
             continue;
         }
         // Columns right of the first corner's ROI and left of the second corner's (mirrored) ROI see both corner maps
-        // in their replicated regime: the product is one value for the whole segment [xa, xb] of this row.
+        // in their column-replicated regime: the product is one value for the whole segment [xa, xb] of this row.
         const int xa = max(it.x_lo, c1.x2 + 1), xb = min(it.x_hi, W - 2 - c2.x2);
         const bool mid = xa <= xb;
         const int n_left = mid ? xa - it.x_lo : it.x_hi - it.x_lo + 1, n_rest = mid ? n_left + (it.x_hi - xb) : n_left;
+        double rf = 0, rb = 0;                                               // this lane's share of the row sums
         for (int t = lane; t < n_rest; t += 32) {
             const int x = t < n_left ? it.x_lo + t : xb + 1 + (t - n_left);
             float h = row_value(c1, r1, x) * row_value(c2, r2, W - 1 - x);   // :106-109
             h = h > 1.f ? 1.f : h;                                           // :113
             h = h < kHeatThresh ? 0.f : h;                                   // :115
-            if (fg_row && x < it.fx_end) fg += (double)logf(h + eps);        // pdq.py:222-225
-            if (h > 0.f) bg += (double)logf((1.f - h) + eps);                // pdq.py:207-210
+            if (w_fg && x < it.fx_end) rf += (double)logf(h + eps);          // pdq.py:222-225
+            if (h > 0.f) rb += (double)logf((1.f - h) + eps);                // pdq.py:207-210
         }
         if (mid && lane == 0) {
             float h = row_value(c1, r1, xa) * row_value(c2, r2, W - 1 - xa);
             h = h > 1.f ? 1.f : h;
             h = h < kHeatThresh ? 0.f : h;
-            const int n_mid = xb - xa + 1, n_fg = fg_row ? max(min(xb, it.fx_end - 1) - xa + 1, 0) : 0;
-            fg += (double)n_fg * (double)logf(h + eps);
-            if (h > 0.f) bg += (double)n_mid * (double)logf((1.f - h) + eps);
+            const int n_mid = xb - xa + 1, n_fg = max(min(xb, it.fx_end - 1) - xa + 1, 0);
+            if (w_fg) rf += (double)n_fg * (double)logf(h + eps);
+            if (h > 0.f) rb += (double)n_mid * (double)logf((1.f - h) + eps);
         }
+        fg += (double)w_fg * rf;
+        bg += (double)w_bg * rb;
     }
     for (int o = 16; o; o >>= 1) { fg += __shfl_xor_sync(0xffffffffu, fg, o); bg += __shfl_xor_sync(0xffffffffu, bg, o); }
     if (lane == 0) { red[0][warp] = fg; red[1][warp] = bg; }
