@@ -10,7 +10,9 @@
 //   pdq.py:423-424                sum of the background loss over the whole image (false-positive spatial quality)
 // The reference materialises D dense [H,W] float32 maps per image (3.7 MB each at 720x1280) and contracts them with
 // G dense boolean masks.  Here nothing dense exists unless asked for (bod_pdq_heatmaps):
-//   P1 pdq_roi_kernel     one CTA per Gaussian corner: the Mahalanobis window scan of find_roi, block-reduced to the ROI
+//   P1 pdq_roi_kernel     one CTA per Gaussian corner: the Mahalanobis window scan of find_roi, one thread per window
+//                         row (the passing pixels of a row form one run: its ends come from the quadratic and are
+//                         settled with the reference's own predicate), block-reduced to the ROI
 //   P2 pdq_table_kernel   the CDF of every ROI pixel (binary64 Genz BVND; the Gauss-Legendre nodes depend on the
 //                         corner only: P1 computes them once, P2 keeps them in shared memory; along a table row the
 //                         quadrature terms follow a two-multiplication recurrence instead of one exp each) + the two
@@ -216,14 +218,47 @@ __global__ void __launch_bounds__(kThreads) pdq_roi_kernel(const int32_t* __rest
         const double det = c.cov[0] * c.cov[3] - c.cov[1] * c.cov[2];
         const double v0 = c.cov[3] / det, v1 = -c.cov[1] / det, v2 = -c.cov[2] / det, v3 = c.cov[0] / det;
         int bx1 = nx, by1 = ny, bx2 = -1, by2 = -1;
-        const int total = nx * ny;                                                    // <= H * W
-        for (int i = threadIdx.x; i < total; i += kThreads) {
-            const int y = i / nx, x = i - y * nx;
+        // the reference's predicate for window pixel (y, x), evaluated exactly as its dense scan does
+        auto inside = [&](int y, int x) {
             const int sy = (shy && y < dmy) ? y + 1 : y, sx = (shx && x < dmx) ? x + 1 : x;
             const double dy = (double)(sy + miny) - c.mean[0], dx = (double)(sx + minx) - c.mean[1];
             const double m = sqrt(dy * (v0 * dy + v1 * dx) + dx * (v2 * dy + v3 * dx));
-            if (m <= kMahThresh || (y == dmy && x == dmx)) {
-                bx1 = min(bx1, x); bx2 = max(bx2, x); by1 = min(by1, y); by2 = max(by2, y);
+            return m <= kMahThresh || (y == dmy && x == dmx);
+        };
+        if (det > 0 && v3 > 0) {
+            // Positive definite: the pixels of a row that pass form one run (the ellipse is convex and the column shift is
+            // monotone), so a row costs a handful of predicate evaluations: the ends of the run are estimated from the
+            // quadratic in dx and settled by the exact predicate on the columns next to them; one thread per row.
+            for (int y = threadIdx.x; y < ny; y += kThreads) {
+                const int sy = (shy && y < dmy) ? y + 1 : y;
+                const double dy = (double)(sy + miny) - c.mean[0];
+                const double bq = (v1 + v2) * dy, cq = v0 * dy * dy - kMahThresh * kMahThresh;
+                const double disc = bq * bq - 4 * v3 * cq, sq = disc > 0 ? sqrt(disc) : 0.0;
+                const double off = c.mean[1] - (double)minx;                       // evaluation point s = dx + off
+                const double lo = fmin(fmax((-bq - sq) / (2 * v3) + off, -4.0), (double)nx + 4.0);
+                const double hi = fmin(fmax((-bq + sq) / (2 * v3) + off, -4.0), (double)nx + 4.0);
+                const int s_lo = (int)ceil(lo), s_hi = (int)floor(hi);
+                // column whose evaluation point is s: columns x < dmx evaluate x + 1 when the shift applies
+                const int e_lo = min(max((shx && s_lo <= dmx) ? s_lo - 1 : s_lo, 0), nx - 1);    // clipped to the window: a run
+                const int e_hi = min(max((shx && s_hi < dmx) ? s_hi - 1 : s_hi, 0), nx - 1);     // that leaves it ends at its edge
+                int rmin = -1, rmax = -1;
+                for (int x = max(e_lo - 2, 0); x <= min(e_lo + 2, nx - 1); ++x) if (inside(y, x)) { rmin = x; break; }
+                for (int x = min(e_hi + 2, nx - 1); x >= max(e_hi - 2, 0); --x) if (inside(y, x)) { rmax = x; break; }
+                if (y == dmy) {                                                    // the forced pixel joins the run's extent
+                    rmin = rmin < 0 ? dmx : min(rmin, dmx);
+                    rmax = max(rmax, dmx);
+                }
+                if (rmin >= 0 || rmax >= 0) {
+                    if (rmin < 0) rmin = rmax;
+                    if (rmax < 0) rmax = rmin;
+                    bx1 = min(bx1, rmin); bx2 = max(bx2, rmax); by1 = min(by1, y); by2 = max(by2, y);
+                }
+            }
+        } else {
+            const int total = nx * ny;                                                // <= H * W
+            for (int i = threadIdx.x; i < total; i += kThreads) {
+                const int y = i / nx, x = i - y * nx;
+                if (inside(y, x)) { bx1 = min(bx1, x); bx2 = max(bx2, x); by1 = min(by1, y); by2 = max(by2, y); }
             }
         }
         if (bx2 >= 0) { atomicMin(&s_box[0], bx1); atomicMin(&s_box[1], by1); atomicMax(&s_box[2], bx2); atomicMax(&s_box[3], by2); }

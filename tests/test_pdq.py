@@ -305,6 +305,41 @@ def test_gpu_heatmaps_into_device_tensor(engines):
 
 
 @pytest.mark.gpu
+def test_gpu_roi_row_scan_matches_dense_scan(engines):
+    """The ROI kernel settles the ends of each window row from the quadratic + the reference's predicate instead of scanning
+    the whole 5-sigma window like find_roi (and the oracle) do: random corners with strong correlation, sub-pixel and
+    image-sized sigmas and windows clipped by the image must give the same maps (a different ROI moves the replicated rows /
+    columns of a corner map, so it cannot hide)."""
+    rng = np.random.default_rng(123)
+    H, W = 97, 143
+    eng = engines((H, W))
+    checked = 0
+    for _ in range(25):
+        boxes, covs = [], []
+        for _ in range(8):
+            x1, y1 = rng.integers(0, W - 12), rng.integers(0, H - 12)
+            x2, y2 = rng.integers(x1 + 4, W), rng.integers(y1 + 4, H)
+            cs = []
+            for _ in range(2):
+                s1, s2 = np.exp(rng.uniform(np.log(0.3), np.log(40), 2))
+                r = rng.uniform(-0.97, 0.97)
+                cs.append(np.array([[s1 * s1, r * s1 * s2], [r * s1 * s2, s2 * s2]]))
+            boxes.append([x1, y1, x2, y2]); covs.append(cs)
+        boxes, covs = np.array(boxes, np.int32), np.array(covs)
+        try:
+            ohm = opdq.heatmaps((H, W), boxes, covs)
+        except ValueError:                      # a corner for which the reference raises: the product must refuse it too
+            from bayes_od_rc_b200._cabi import BodError
+            with pytest.raises(BodError):
+                eng.heatmaps(boxes, covs)
+            continue
+        hm = eng.heatmaps(boxes, covs)
+        assert np.array_equal(hm > 0, ohm > 0) and np.abs(hm - ohm).max() <= HM_ATOL
+        checked += len(boxes)
+    assert checked >= 100
+
+
+@pytest.mark.gpu
 def test_gpu_odd_width_uses_the_scalar_map_kernel(engines):
     rng = np.random.default_rng(11)
     H, W = 50, 70                                  # W % 4 != 0
