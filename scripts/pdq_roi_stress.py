@@ -1,5 +1,5 @@
-# ROI parity stress: GPU find_roi (through the dense-map path's corner tables is indirect) -> compare dense maps with the oracle
-# on many random corners incl. window-clipped, tiny and huge covariances, strong correlation
+"""ROI parity stress on the GPU box: dense PDQ maps of random corners (strong correlation, sub-pixel to image-sized sigmas,
+clipped windows) against oracle/pdq_oracle.c.  Usage: python scripts/pdq_roi_stress.py"""
 import sys, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from bayes_od_rc_b200 import pdq
