@@ -359,15 +359,26 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
         slot_anchor = pf.out_anchor; slot_counts = pf.out_counts;
         launches += 4;
     }
-    CU(c, launch_scan(sc, hs));
-    if (record) CU(c, cudaEventRecord(c->ev[2], hs));
-
     // K2 overwrites what the previous tail on this lane (two runs ago) reads
     cudaStream_t k2s = hs;
+    // Short moments kernels (small batches: < 0.8 GB of logits per run, ~0.12 ms) leave the head stream idle for a
+    // noticeable share of the step while the scan runs between two of them; there the scan (per-lane outputs, read by K2
+    // onwards) rides with the tail and the head stream carries K1 back to back (B = 8, K = 8: 69.0 -> 73.8 k images/s).
+    // Long ones lose ~1 % that way (the soft-NMS CTAs then find no free SM at the kernel boundary), so they keep the scan.
+    static const int scan_tail_env = getenv("BOD_SCAN_TAIL") ? atoi(getenv("BOD_SCAN_TAIL")) : -1;     // experiments
+    const bool scan_tail = k2_tail && (scan_tail_env >= 0 ? scan_tail_env != 0 : 4.0 * nb * g.N * A * K < 0.8e9);
+    if (!scan_tail) {
+        CU(c, launch_scan(sc, hs));
+        if (record) CU(c, cudaEventRecord(c->ev[2], hs));
+    }
     if (k2_tail) {
         CU(c, cudaEventRecord(L.head_done, hs));
         CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));
         k2s = ts;
+        if (scan_tail) {
+            CU(c, launch_scan(sc, ts, true));
+            if (record) CU(c, cudaEventRecord(c->ev[2], ts));
+        }
     } else if (hs != ts && L.tail_pending) {
         CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
     }

@@ -54,7 +54,7 @@ struct ScanArgs {
     int32_t* status;            // [1] sticky error flags
     int B, tiles, capacity;
 };
-cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st);
+cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st, bool beside_k1 = false);
 
 // ---- K1c: pre-NMS filter on the slot lists (extension knobs score_threshold / pre_nms_top_k) --
 struct PrefilterArgs {

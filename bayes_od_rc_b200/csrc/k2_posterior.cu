@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(ScanArgs a) {
     int32_t* off = a.tile_off + (size_t)b * (a.tiles + 1);
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < a.tiles; base += 1024) {
+    for (int base = 0; base < a.tiles; base += (int)blockDim.x) {
         const int t = base + tid;
         const int v = (t < a.tiles) ? cnt[t] : 0;
         int x = v;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(ScanArgs a) {
         if (lane == 31) warp_tot[warp] = x;
         __syncthreads();
         if (warp == 0) {
-            int w = warp_tot[lane];
+            int w = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
             warp_tot[lane] = w;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(ScanArgs a) {
         const int incl = x + (warp > 0 ? warp_tot[warp - 1] : 0) + carry;
         if (t < a.tiles) off[t] = incl - v;
         __syncthreads();
-        if (tid == 1023) carry_s = incl;
+        if (tid == (int)blockDim.x - 1) carry_s = incl;
         __syncthreads();
     }
     if (tid == 0) {
@@ -62,8 +62,10 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(ScanArgs a) {
     }
 }
 
-cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st) {
-    scan_tiles_kernel<<<a.B, 1024, 0, st>>>(a);
+// beside_k1: 256 threads (8 k registers), so that a scan CTA fits beside the resident moments-kernel CTAs of a pipelined
+// context when the scan of run i rides on the tail stream while the head stream already streams the logits of run i+1.
+cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st, bool beside_k1) {
+    scan_tiles_kernel<<<a.B, beside_k1 ? 256 : 1024, 0, st>>>(a);
     return cudaGetLastError();
 }
 
