@@ -366,6 +366,22 @@ def test_gpu_errors(engines):
     assert eng.heatmaps([[10, 10, 40, 40]], [ok]).max() > 0.5    # the context survives an error
 
 
+def test_pdq_create_validates_before_touching_the_device():
+    import ctypes as C
+    from bayes_od_rc_b200 import _cabi
+    lib = _cabi.load()
+    h = C.c_void_p()
+    for hh, ww in [(0, 10), (10, 0), (-1, 5), (40000, 40000)]:            # > 2^30 pixels: indices are 32-bit
+        assert lib.bod_pdq_create(C.byref(h), 0, hh, ww) == -1
+        assert b"bad argument" in lib.bod_pdq_last_error(None)
+    assert lib.bod_pdq_create(None, 0, 8, 8) == -1
+    # NULL contexts are refused, not dereferenced
+    assert lib.bod_pdq_heatmaps(None, 0, None, None, None, 0) == -1
+    assert lib.bod_pdq_losses(None, 0, None, None, None, None, None, None, None, None) == -1
+    assert lib.bod_pdq_last_ms(None, None, None, None) == -1
+    lib.bod_pdq_destroy(None)
+
+
 def test_pdq_has_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
