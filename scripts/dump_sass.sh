@@ -23,3 +23,4 @@ dump 'pdq_table_kernel' pdq_table_kernel
 dump 'pdq_sum_kernel' pdq_sum_kernel
 dump 'pdq_heatmap_kernelE' pdq_heatmap_kernel
 dump 'pdq_roi_kernel' pdq_roi_kernel
+dump 'k1_moments_pipe_kernelILi8E' k1_moments_pipe_kernel_K8
