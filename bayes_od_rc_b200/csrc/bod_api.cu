@@ -58,7 +58,7 @@ struct bod_ctx {
     uint32_t* ticket = nullptr;       // K1's dynamic tile scheduler: monotonically increasing ticket counter
     uint32_t ticket_next = 0;         // its value once every launch issued so far has finished
     float* probs = nullptr; float* sampled = nullptr;
-    int fastS = 0, pstride = 0, pw_rows = 0, k3_smem_S = 0, k3_rows = 0;
+    int pstride = 0, pw_rows = 0, k3_rows = 0, k3_threads = 512, k3_force_big = 0;
     // device staging of host inputs (bod_run_host), allocated on first use
     float* in_cls = nullptr; float* in_box = nullptr; float* in_cov = nullptr; float* in_anchors = nullptr; float* in_counts = nullptr;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
@@ -76,11 +76,13 @@ struct bod_ctx {
     int launches = 0;
     int64_t h2d_copied = 0, h2d_mapped_rows = 0, d2h_copied = 0;   // traffic of the last bod_run_host
     bool host_copy_all = false;       // BOD_HOST_COPY_ALL: never read box/cov in place from pinned host memory
-    int k1_debug = 0;                 // BOD_K1_DEBUG (diagnostics)
-    int skip_mask = 0;                // BOD_DEBUG_SKIP (diagnostics, results invalid): 1 = no K2, 2 = no soft-NMS, 4 = no K4
-    long long* k3_dbg = nullptr;      // BOD_K3_DEBUG (diagnostics): [B][8] cycle counters
+#ifdef BOD_DIAGNOSTICS
+    int k1_debug = 0;                 // BOD_K1_DEBUG (diagnostic builds only)
+    int skip_mask = 0;                // BOD_DEBUG_SKIP (diagnostic builds only, results invalid): 1 = no K2, 2 = no soft-NMS, 4 = no K4
+    long long* k3_dbg = nullptr;      // BOD_K3_DEBUG (diagnostic builds only): [B][32][12] cycle counters
+#endif
     bool k2_on_tail = true;           // pipelined contexts: K2 rides with the tail (see run_range); BOD_K2_TAIL=0 keeps it on the head
-    int k3_seg_cap = -1, k3_psm_max = -1;   // BOD_K3_SEGCAP / BOD_K3_PSM_MAX (tests: reach the overflow paths on small inputs)
+    int k3_psm_max = -1, k3_seg_cap = -1;   // BOD_K3_PSM_MAX / BOD_K3_SEGCAP (tests: reach the spill rows / the piecewise pass B on small inputs)
 };
 
 static int fail(bod_ctx* c, int code, const char* fmt, ...) {
@@ -178,15 +180,14 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
 
     // carve the slab
     c->nlanes = cfg->pipeline_depth < 1 ? 1 : (cfg->pipeline_depth > bod_ctx::kMaxLanes ? bod_ctx::kMaxLanes : cfg->pipeline_depth);
-    c->fastS = k3_fast_capacity(c->capacity);
     c->pstride = (c->Dmax + 3) & ~3;
     c->pw_rows = c->capacity < 65535 ? c->capacity : 65535;
-    int k3_smem_S = c->fastS, k3_rows = c->pw_rows;       // BOD_K3_MODE (tests): force the soft-NMS variants
-    if (const char* md = getenv("BOD_K3_MODE")) {
-        if (!strcmp(md, "big")) k3_smem_S = 0;                              // per-candidate state in global memory
-        else if (!strcmp(md, "generic")) { k3_smem_S = 0; k3_rows = 0; }    // the literal round-per-selection kernel
+    c->k3_rows = c->pw_rows;
+    if (const char* md = getenv("BOD_K3_MODE")) {          // tests: force the soft-NMS variants on small inputs
+        if (!strcmp(md, "big")) c->k3_force_big = 1;                        // per-candidate state in global memory
+        else if (!strcmp(md, "generic")) c->k3_rows = 0;                    // the literal round-per-selection kernel
     }
-    c->k3_smem_S = k3_smem_S; c->k3_rows = k3_rows;
+    if (const char* t = getenv("BOD_K3_THREADS")) { const int v = atoi(t); if (v == 256 || v == 512 || v == 1024) c->k3_threads = v; }
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     struct Piece { void** p; size_t o; };
@@ -255,13 +256,15 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     for (auto& set : c->evring) for (auto& ev : set) cudaEventCreate(&ev);
     for (auto& ev : c->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
+#ifdef BOD_DIAGNOSTICS
     if (const char* d = getenv("BOD_K1_DEBUG")) c->k1_debug = atoi(d);
     if (const char* d = getenv("BOD_DEBUG_SKIP")) c->skip_mask = atoi(d);
+    if (getenv("BOD_K3_DEBUG")) { cudaMalloc(&c->k3_dbg, ((size_t)B * 384 + 8) * sizeof(long long)); cudaMemset(c->k3_dbg, 0, ((size_t)B * 384 + 8) * sizeof(long long)); }
+#endif
     c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
     if (const char* d = getenv("BOD_K2_TAIL")) c->k2_on_tail = atoi(d) != 0;
-    if (const char* d = getenv("BOD_K3_SEGCAP")) { int v = atoi(d); if (v >= 0) c->k3_seg_cap = v; }
     if (const char* d = getenv("BOD_K3_PSM_MAX")) c->k3_psm_max = atoi(d);
-    if (getenv("BOD_K3_DEBUG")) { cudaMalloc(&c->k3_dbg, (size_t)B * 8 * sizeof(long long)); cudaMemset(c->k3_dbg, 0, (size_t)B * 8 * sizeof(long long)); }
+    if (const char* d = getenv("BOD_K3_SEGCAP")) c->k3_seg_cap = atoi(d);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { snprintf(create_err, sizeof create_err, "init: %s", cudaGetErrorString(e)); bod_destroy(c); return BOD_ERR_CUDA; }
     *out = c;
@@ -315,7 +318,11 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     // K2 with the tail: the head stream then carries K1 + scan only, so the next run's K1 starts as soon as
     // this one's logits are consumed (not with the pre-NMS filter: its scratch is shared between lanes)
     const bool k2_tail = (hs != ts) && c->k2_on_tail && !c->prefilter;
-    if (k2_tail && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));   // the lane's slot lists are still being read
+    // The tail issued on this lane nlanes runs ago may still be reading the lane's state (slot lists by K2,
+    // num_survivors / tile_off by the soft-NMS and fusion kernels): nothing of this run may overwrite it before
+    // that tail is done -- also when K2 stays on the head stream (pre-NMS filter), where the scans would otherwise
+    // rewrite num_survivors under a running tail.
+    if (hs != ts && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
     if (record) CU(c, cudaEventRecord(c->ev[0], hs));
     K1Args k1{};
     k1.lv = lv; k1.counts_in = counts;
@@ -325,7 +332,9 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     k1.tile_count = L.tile_count + (size_t)b0 * c->tiles;
     k1.B = nb; k1.N = g.N; k1.A = g.A; k1.K = g.K; k1.tiles = c->tiles;
     k1.num_draws = g.num_draws; k1.seed = g.seed; k1.image_id_base = g.image_id_base + (uint32_t)b0;
+#ifdef BOD_DIAGNOSTICS
     k1.debug = c->k1_debug;
+#endif
     k1.leave_room = (hs != ts) ? 1 : 0;
     k1.ticket = c->ticket; k1.ticket_base = c->ticket_next;
     c->ticket_next += k1_tickets_per_launch(k1);           // K1 launches of a context never overlap each other
@@ -379,8 +388,6 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
             CU(c, launch_scan(sc, ts, true));
             if (record) CU(c, cudaEventRecord(c->ev[2], ts));
         }
-    } else if (hs != ts && L.tail_pending) {
-        CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
     }
     K2Args k2{};
     k2.lv = lv; k2.anchors = anchors;
@@ -398,7 +405,10 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
                          g.dirichlet_prior != BOD_PRIOR_NONE) ? 1 : 0;
     k2.isotropic_variance = g.isotropic_variance; k2.scale_v = g.scale_v; k2.scale_u = g.scale_u;
     k2.anchor_mode = g.anchor_mode; k2.im_h = g.im_h; k2.im_w = g.im_w;
-    if (!(c->skip_mask & 1)) CU(c, launch_k2(k2, k2s));
+#ifdef BOD_DIAGNOSTICS
+    if (!(c->skip_mask & 1))
+#endif
+    CU(c, launch_k2(k2, k2s));
     if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, k2s)); ++launches; }
     if (record) CU(c, cudaEventRecord(c->ev[3], k2s));
     if (hs != ts && !k2_tail) {
@@ -412,27 +422,34 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     k3.stale = L.stale + b0 * cap; k3.cur = L.cur + b0 * cap; k3.begin = L.begin + b0 * cap;
     k3.pend = L.pend + b0 * cap * kPendStride;
     k3.pw = L.pw + (size_t)b0 * c->pw_rows * c->pstride; k3.pw_rows = c->pw_rows; k3.max_rows = c->k3_rows;
-    k3.fastS = c->k3_smem_S; k3.pstride = c->pstride;
+    k3.pstride = c->pstride;
     k3.nms_idx = L.nms_idx + b0 * D; k3.nms_score = L.nms_score + b0 * D; k3.centre_anchor = L.centre_anchor + b0 * D;
-    k3.num_dets = L.num_dets + b0; k3.member = L.member + b0 * D * c->words;
-    k3.B = nb; k3.capacity = c->capacity; k3.Dmax = c->Dmax; k3.words = c->words;
+    k3.num_dets = L.num_dets + b0;
+    k3.B = nb; k3.capacity = c->capacity; k3.Dmax = c->Dmax;
     k3.iou_threshold = g.iou_threshold; k3.soft_nms_sigma = g.soft_nms_sigma;
-    k3.dbg = c->k3_dbg ? c->k3_dbg + (size_t)b0 * 8 : nullptr;
-    k3.seg_cap = c->k3_seg_cap; k3.psm_max = c->k3_psm_max;
-    if (!(c->skip_mask & 2)) CU(c, launch_k3(k3, ts));
+    k3.threads = c->k3_threads; k3.force_big = c->k3_force_big; k3.psm_max = c->k3_psm_max; k3.seg_cap = c->k3_seg_cap;
+#ifdef BOD_DIAGNOSTICS
+    k3.dbg = c->k3_dbg ? c->k3_dbg + (size_t)b0 * 384 : nullptr;
+    if (!(c->skip_mask & 2))
+#endif
+    CU(c, launch_k3(k3, ts));
     if (record) CU(c, cudaEventRecord(c->ev[4], ts));
 
     K4Args k4{};
     k4.cnt_post = k2.cnt_post; k4.mu_post = k2.mu_post; k4.sig_post = k2.sig_post; k4.num_survivors = sc.num_survivors;
-    k4.nms_idx = k3.nms_idx; k4.num_dets = k3.num_dets; k4.member = k3.member;
+    k4.nms_idx = k3.nms_idx; k4.num_dets = k3.num_dets;
+    k4.corners = k2.corners; k4.member = L.member + b0 * D * c->words;
     k4.out_means = L.out_means + b0 * D * 4; k4.out_covs = L.out_covs + b0 * D * 16;
     k4.out_param = L.out_param + b0 * D * K; k4.out_count = L.out_count + b0 * D * K;
     k4.B = nb; k4.K = g.K; k4.capacity = c->capacity; k4.Dmax = c->Dmax; k4.words = c->words;
-    k4.calibration = g.cov_calibration;
-    if (!(c->skip_mask & 4)) CU(c, launch_k4(k4, ts));
+    k4.calibration = g.cov_calibration; k4.iou_threshold = g.iou_threshold;
+#ifdef BOD_DIAGNOSTICS
+    if (!(c->skip_mask & 4))
+#endif
+    CU(c, launch_k4(k4, ts));
     if (record) CU(c, cudaEventRecord(c->ev[5], ts));
     if (hs != ts) { CU(c, cudaEventRecord(L.tail_done, ts)); L.tail_pending = true; }
-    c->launches += launches + 2;   // + soft-NMS (with the membership bits), K4
+    c->launches += launches + 2;   // + soft-NMS, K4 (membership + fusion)
     return BOD_OK;
 }
 
@@ -556,12 +573,12 @@ extern "C" int bod_validate_run(bod_ctx* c, const float* cls, const float* box, 
     k3.corners = L.corners; k3.score = L.score; k3.num_survivors = L.num_survivors; k3.surv_anchor = L.surv_anchor;
     k3.stale = L.stale; k3.cur = L.cur; k3.begin = L.begin; k3.pend = L.pend;
     k3.pw = L.pw; k3.pw_rows = c->pw_rows; k3.max_rows = c->k3_rows;
-    k3.fastS = c->k3_smem_S; k3.pstride = c->pstride;
+    k3.pstride = c->pstride;
     k3.nms_idx = L.nms_idx; k3.nms_score = L.nms_score; k3.centre_anchor = L.centre_anchor;
-    k3.num_dets = L.num_dets; k3.member = L.member;
-    k3.B = g.B; k3.capacity = c->capacity; k3.Dmax = c->Dmax; k3.words = c->words;
+    k3.num_dets = L.num_dets;
+    k3.B = g.B; k3.capacity = c->capacity; k3.Dmax = c->Dmax;
     k3.iou_threshold = g.iou_threshold; k3.soft_nms_sigma = g.soft_nms_sigma;
-    k3.dbg = nullptr; k3.seg_cap = c->k3_seg_cap; k3.psm_max = c->k3_psm_max;
+    k3.threads = c->k3_threads; k3.force_big = c->k3_force_big; k3.psm_max = c->k3_psm_max; k3.seg_cap = c->k3_seg_cap;
     CU(c, launch_k3(k3, st));
     CU(c, launch_val_gather(v, st));
     c->launches = 5;
@@ -678,14 +695,16 @@ extern "C" int bod_fetch_sampled_counts(bod_ctx* c, int32_t b, float* counts) {
     return BOD_OK;
 }
 
-// diagnostics (not part of the public header): per-image soft-NMS phase cycle counters
+#ifdef BOD_DIAGNOSTICS
+// diagnostic builds only (not part of the public header): per-image, per-warp soft-NMS phase cycle counters
 extern "C" int bod_debug_k3_counters(bod_ctx* c, long long* out) {
     if (!c || !out || !c->k3_dbg) return BOD_ERR_STATE;
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaDeviceSynchronize());
-    CU(c, cudaMemcpy(out, c->k3_dbg, (size_t)c->cfg.B * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(out, c->k3_dbg, ((size_t)c->cfg.B * 384 + 8) * sizeof(long long), cudaMemcpyDeviceToHost));
     return BOD_OK;
 }
+#endif
 
 extern "C" int bod_synchronize(bod_ctx* c) {
     if (!c) return BOD_ERR_INVALID;
@@ -881,10 +900,10 @@ extern "C" int bod_cluster_host(bod_ctx* c, int32_t S, const float* counts, cons
     CU(c, cudaStreamSynchronize(st));          // `mask`, S, D are stack/heap temporaries
     K4Args k4{};
     k4.cnt_post = L.cnt_post; k4.mu_post = L.mu_post; k4.sig_post = L.sig_post; k4.num_survivors = L.num_survivors;
-    k4.nms_idx = L.nms_idx; k4.num_dets = L.num_dets; k4.member = L.member;
+    k4.nms_idx = L.nms_idx; k4.num_dets = L.num_dets; k4.corners = nullptr; k4.member = L.member;
     k4.out_means = L.out_means; k4.out_covs = L.out_covs; k4.out_param = L.out_param; k4.out_count = L.out_count;
     k4.B = 1; k4.K = (int)K; k4.capacity = c->capacity; k4.Dmax = (int)Dm; k4.words = c->words;
-    k4.calibration = c->cfg.cov_calibration;
+    k4.calibration = c->cfg.cov_calibration; k4.iou_threshold = c->cfg.iou_threshold;
     CU(c, launch_k4(k4, st));
     c->launches = 1;
     c->last_stream = st; c->ran = true;

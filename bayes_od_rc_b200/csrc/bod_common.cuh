@@ -155,6 +155,17 @@ BOD_DEVINL float repo_iou(const float4 b1, const float4 b2) {
     return inter / (uni + 0.00001f);
 }
 
+// bbox_iou_vuvu(survivor, centre) > threshold (strict; inference_utils.py:316), skipping the division when
+// the boxes cannot overlap even with the +1 pixel convention ((hi - lo) + 1 > 0 <=> hi - lo > -1 in binary32;
+// then inter = 0 and the quotient is +-0 or NaN, never > a threshold >= 0)
+BOD_DEVINL bool is_member(const float4 bs, const float4 bx, float thr) {
+    const float dx = fminf(bs.w, bx.w) - fmaxf(bs.y, bx.y);
+    const float dy = fminf(bs.z, bx.z) - fmaxf(bs.x, bx.x);
+    const bool wellformed = (bx.x <= bx.z) && (bx.y <= bx.w) && (bs.x <= bs.z) && (bs.y <= bs.w);
+    if (!wellformed || (dx > -1.0f && dy > -1.0f)) return repo_iou(bs, bx) > thr;
+    return false;
+}
+
 // order-preserving float -> uint32 key (larger float <=> larger key; -inf > 0)
 BOD_DEVINL uint32_t float_key(float f) {
     const uint32_t u = __float_as_uint(f);

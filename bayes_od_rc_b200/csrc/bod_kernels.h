@@ -36,7 +36,8 @@ struct K1Args {
     int num_draws;
     uint64_t seed;
     uint32_t image_id_base;
-    int debug;               // diagnostics only: 1 = skip sampler/compaction, 2 = also skip the softmax
+    int debug;               // BOD_DIAGNOSTICS builds only: 1 = skip sampler/compaction, 2 = also skip the softmax
+    int ratio_slot;          // filled by launch_k1: slot of the binomial ratio table for num_draws (-1: divide)
     int leave_room;          // pipelined context: size the ring so that other stages' CTAs fit beside K1's
     uint32_t* ticket;        // dynamic tile scheduler: global ticket counter (never reset) ...
     uint32_t ticket_base;    // ... and its value when this launch starts
@@ -99,7 +100,7 @@ cudaError_t launch_k2(const K2Args& a, cudaStream_t st);
 // joint_entropy ranking: normalise the information gains over each image's survivors
 cudaError_t launch_rank_normalise(const K2Args& a, cudaStream_t st);
 
-// ---- K3: soft-NMS centre selection + membership masks -----------------------
+// ---- K3: soft-NMS centre selection ------------------------------------------
 struct K3Args {
     const float4* corners;        // [B,cap]
     const float* score;           // [B,cap]
@@ -108,28 +109,28 @@ struct K3Args {
     // scratch per candidate, [B,cap]
     float* stale;     // score as of the candidate's last queue update
     float* cur;       // up-to-date score
-    int32_t* begin;   // suppress_begin_index
+    int32_t* begin;   // suppress_begin_index (generic kernel) / pending-entry counts (round kernel, state in global memory)
     uint32_t* pend;   // [B,cap,kPendStride] pending-selection bitmask (generic kernel)
-    float* pw;        // [B,pw_rows,pstride] spill rows of the pending soft-NMS weights (fast kernel)
+    float* pw;        // [B,pw_rows,pstride] spill rows of the pending soft-NMS weights (round kernel)
     int pw_rows;      // rows per image in pw: min(capacity, 65535)
-    int max_rows;     // survivors the fast kernel takes (<= pw_rows: its list entries hold 16-bit indices); more: literal kernel
-    int fastS, pstride;
+    int max_rows;     // survivors the round kernel takes (<= pw_rows); more: the literal kernel
+    int pstride;
     // outputs
     int32_t* nms_idx;           // [B,Dmax]
     float* nms_score;           // [B,Dmax]
     int32_t* centre_anchor;     // [B,Dmax]
     int32_t* num_dets;          // [B]
-    uint32_t* member;           // [B,Dmax,words]
-    int B, capacity, Dmax, words;
+    int B, capacity, Dmax;
     float iou_threshold, soft_nms_sigma;
-    long long* dbg;             // diagnostics: [B][8] cycle counters per phase, or nullptr
-    int seg_cap;                // pair-list entries per warp and round (-1: the kernel's own; tests shrink it to reach the in-place path)
+    int threads;                // CTA size: 256, 512 (default) or 1024
+    int force_big;              // tests: per-candidate state in global memory whatever the survivor count
     int psm_max;                // cap on the pending weights kept in shared memory per candidate (-1: none; tests)
+    int seg_cap;                // pairs per warp list segment (-1: the kernel's own; tests shrink it, >= 32, to reach the piecewise path)
+    long long* dbg;             // BOD_DIAGNOSTICS builds only: [B][32 warps][12] phase cycle counters, or nullptr
 };
 cudaError_t launch_k3(const K3Args& a, cudaStream_t st);
-int k3_fast_capacity(int capacity);   // candidates the shared-memory soft-NMS kernel holds for this capacity
 
-// ---- K4: per-cluster Bayesian fusion ----------------------------------------
+// ---- K4: cluster membership + per-cluster Bayesian fusion -------------------
 struct K4Args {
     const float* cnt_post;   // [B,cap,K]
     const float* mu_post;    // [B,cap,4]
@@ -137,13 +138,15 @@ struct K4Args {
     const int32_t* num_survivors;
     const int32_t* nms_idx;  // [B,Dmax]
     const int32_t* num_dets; // [B]
-    const uint32_t* member;  // [B,Dmax,words]
+    const float4* corners;   // [B,cap] survivor corners: membership rows are computed here (and written to `member`);
+                             // nullptr: `member` is an input (bod_cluster_host: the caller's affinity matrix)
+    uint32_t* member;        // [B,Dmax,words] bit s of row d <=> bbox_iou_vuvu(s, centre d) > iou_threshold
     float* out_means;        // [B,Dmax,4]
     float* out_covs;         // [B,Dmax,16]
     float* out_param;        // [B,Dmax,K]
     float* out_count;        // [B,Dmax,K]
     int B, K, capacity, Dmax, words;
-    float calibration;
+    float calibration, iou_threshold;
 };
 cudaError_t launch_k4(const K4Args& a, cudaStream_t st);
 

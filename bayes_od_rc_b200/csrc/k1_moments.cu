@@ -12,13 +12,15 @@
 // [B,N,A,K] logits tensor exactly once (4*N*A*K bytes per image), so it IS the
 // HBM roofline of the path.  Data movement: the unit of work is a tile of
 // kTileAnchors consecutive anchors of one image; for every MC sample the tile's
-// [tile,K] slab is a contiguous span of global memory.  Persistent CTAs (two per
-// SM) walk the tiles; one producer thread per CTA bulk-copies slab after slab
-// into a ring of shared-memory stages with the TMA engine (cp.async.bulk +
-// full/empty mbarriers), running up to NSTAGE slabs ahead of the eight consumer
-// warps, so ~200 KB per SM are always in flight, no thread issues a global load
+// [tile,K] slab is a contiguous span of global memory.  Persistent CTAs (six per
+// SM, 160 threads each) take tiles from a global ticket counter; one producer
+// thread per CTA bulk-copies slab after slab into a ring of shared-memory stages
+// with the TMA engine (cp.async.bulk + full/empty mbarriers), running up to NS
+// slabs ahead of the CTA's four consumer warps (one thread per anchor of the
+// tile), so ~170-210 KB per SM are always in flight, no thread issues a global load
 // and rows of any K (8, 11, 4, ...) are consumed conflict-free from shared memory.
 #include <cstdlib>
+#include <mutex>
 #include "bod_common.cuh"
 #include "bod_kernels.h"
 
@@ -112,9 +114,12 @@ BOD_DEVINL void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, u
 // (p_m^T < 1e-30) fall back to T plain inverse-cdf draws.  Every operation is an
 // explicitly rounded binary32 intrinsic so the CPU restatement is bit-identical.
 // ---------------------------------------------------------------------------
-// (T - j) / (j + 1) for j < kRatioTab, filled by the launcher for the configured number of draws T
+// (T - j) / (j + 1) for j < kRatioTab, one slot per number of draws T seen on the device.  A slot is
+// written once (before the first launch that uses it) and never rewritten, so contexts with different T
+// share the table safely; when the slots run out the kernel divides instead (same bits, slower).
 constexpr int kRatioTab = 64;
-__constant__ float c_binom_ratio[kRatioTab];
+constexpr int kRatioSlots = 8;
+__constant__ float c_binom_ratio[kRatioSlots * kRatioTab];
 
 struct PhiloxStream {
     uint4 w;
@@ -144,7 +149,7 @@ struct PhiloxStream {
 // anchor is dropped; its counts are never read again.  Otherwise cnt[] holds the
 // full multinomial counts.
 template <int K>
-BOD_DEVINL bool philox_counts(const float (&p)[K], uint32_t anchor, uint32_t image, uint2 key, int T,
+BOD_DEVINL bool philox_counts(const float (&p)[K], uint32_t anchor, uint32_t image, uint2 key, int T, int rslot,
                               bool need_counts, float (&cnt)[K]) {
     float cdf[K];
     float s = 0.0f, pm = p[0];
@@ -165,7 +170,8 @@ BOD_DEVINL bool philox_counts(const float (&p)[K], uint32_t anchor, uint32_t ima
         int j = 0;
         float cd = pw, f = pw;
         while (u >= cd && j < T) {
-            const float ratio = (j < kRatioTab) ? c_binom_ratio[j] : __fdiv_rn((float)(T - j), (float)(j + 1));
+            const float ratio = (j < kRatioTab && rslot >= 0) ? c_binom_ratio[rslot * kRatioTab + j]
+                                                              : __fdiv_rn((float)(T - j), (float)(j + 1));
             f = __fmul_rn(__fmul_rn(f, ratio), odds);
             ++j;
             cd = __fadd_rn(cd, f);
@@ -335,7 +341,7 @@ k1_moments_kernel(K1Args a, int NC) {
     bool maybe_fg = true;
     if (a.counts_in == nullptr && valid) {
         maybe_fg = philox_counts<K>(p, (uint32_t)anchor, a.image_id_base + (uint32_t)b,
-                                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws,
+                                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws, a.ratio_slot,
                                         a.sampled_out != nullptr, cnt);
         if (a.sampled_out != nullptr) {
             float* o = a.sampled_out + ((size_t)b * a.A + anchor) * K;
@@ -476,7 +482,11 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
         for (int k = 0; k < K; ++k) p[k] = 0.0f;
         for (int n = 0; n < N; ++n) {
             if (n > 0) mbar_wait_a(full0 + bar_off, (uint32_t)phase);
+#ifdef BOD_DIAGNOSTICS
             if (valid && a.debug < 2) {
+#else
+            if (valid) {
+#endif
                 float x[K];
                 LoadRow<K>::run(row_addr, x);
                 float m = x[0];
@@ -506,16 +516,18 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
             }
         }
 
-        if (a.debug >= 1) {                                  // diagnostics: data movement (+ softmax) only
+#ifdef BOD_DIAGNOSTICS
+        if (a.debug >= 1) {                                  // diagnostic builds: data movement (+ softmax) only
             if (valid && p[0] == 12345.0f) a.slot_anchor[0] = 1;
             continue;
         }
+#endif
 
         // H3: categorical draw counts
         bool maybe_fg = true;
         if (a.counts_in == nullptr && valid) {
             maybe_fg = philox_counts<K>(p, (uint32_t)anchor, a.image_id_base + (uint32_t)b,
-                                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws,
+                                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.num_draws, a.ratio_slot,
                                         a.sampled_out != nullptr, cnt);
             if (a.sampled_out != nullptr) {
                 float* o = a.sampled_out + ((size_t)b * a.A + anchor) * K;
@@ -619,22 +631,37 @@ static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-static int g_ratio_T[64] = {0};
-
-cudaError_t launch_k1(const K1Args& a, cudaStream_t st) {
+// slot of the ratio table for T draws on the current device (-1: none left, the kernel divides)
+static int ratio_slot_for(int T, cudaError_t* err) {
+    static std::mutex mu;
+    static int slot_T[64][kRatioSlots];
+    static int slot_n[64] = {0};
+    *err = cudaSuccess;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && g_ratio_T[dev] != a.num_draws) {
-        float tab[kRatioTab];
-        for (int j = 0; j < kRatioTab; ++j) {
-            volatile float num = (float)(a.num_draws - j), den = (float)(j + 1);
-            tab[j] = num / den;
-        }
-        cudaError_t e0 = cudaMemcpyToSymbolAsync(c_binom_ratio, tab, sizeof tab, 0, cudaMemcpyHostToDevice, st);
-        if (e0 != cudaSuccess) return e0;
-        cudaStreamSynchronize(st);              // `tab` is a stack temporary; happens once per device / T
-        g_ratio_T[dev] = a.num_draws;
+    if (dev < 0 || dev >= 64) return -1;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < slot_n[dev]; ++i) if (slot_T[dev][i] == T) return i;
+    if (slot_n[dev] == kRatioSlots) return -1;
+    float tab[kRatioTab];
+    for (int j = 0; j < kRatioTab; ++j) {
+        volatile float num = (float)(T - j), den = (float)(j + 1);
+        tab[j] = num / den;
     }
+    const int slot = slot_n[dev];
+    // synchronous copy into a slot no kernel has been told about yet
+    *err = cudaMemcpyToSymbol(c_binom_ratio, tab, sizeof tab, (size_t)slot * sizeof tab, cudaMemcpyHostToDevice);
+    if (*err != cudaSuccess) return -1;
+    slot_T[dev][slot] = T;
+    slot_n[dev] = slot + 1;
+    return slot;
+}
+
+cudaError_t launch_k1(const K1Args& a0, cudaStream_t st) {
+    K1Args a = a0;
+    cudaError_t e0;
+    a.ratio_slot = ratio_slot_for(a.num_draws, &e0);
+    if (e0 != cudaSuccess) return e0;
     switch (a.K) {
 #define BOD_CASE(KK) case KK: return launch_k<KK>(a, st);
         BOD_CASE(2) BOD_CASE(3) BOD_CASE(4) BOD_CASE(5) BOD_CASE(6) BOD_CASE(7) BOD_CASE(8) BOD_CASE(9)

@@ -1,15 +1,12 @@
-// k3_softnms.cu — stage K3: exact emulation of TF's soft-NMS centre selection
-// plus the cluster-membership bitmasks.  Compiled with -fmad=false.
+// k3_softnms.cu — stage K3: exact emulation of TF's soft-NMS centre selection.
+// Compiled with -fmad=false.
 //
 // Reference lines replaced:
 //   inference_utils.py:207-212  tf.image.non_max_suppression_with_scores(boxes, scores,
 //                               max_output_size, iou_threshold, soft_nms_sigma)
 //                               = TF's NonMaxSuppressionV5 CPU kernel (a device->host->device
 //                               round trip in the reference graph)
-//   inference_utils.py:214-215  box_utils.bbox_iou_vuvu(corners, corners)  [S,S]
-//   inference_utils.py:316      affinity_matrix[:, centre] > threshold
-// Only the D centre columns of the S x S matrix are ever read by the reference
-// (:316), so only those are evaluated here and only as bits.
+// (The cluster-membership test of :214-215 / :316 lives in K4, one warp per centre.)
 //
 // How the sequential priority-queue loop of the TF kernel is reproduced exactly.
 // TF pops the best candidate, multiplies its score by exp(scale*iou^2) for every
@@ -21,20 +18,20 @@
 // x = argmax_i (u_i, -i); on the way TF pops, updates and re-pushes exactly the
 // candidates whose stale key (t_i, -i) exceeds (u_x, -x).  Weights equal to exactly
 // 1.0f (IoU 0, the overwhelmingly common case) leave a score bit-identical, so
-// boxes that do not overlap a new centre need no arithmetic at all.
+// boxes that do not overlap a new centre need no arithmetic at all.  On the bench
+// scenes TF performs 2 000 - 3 000 pops and ~140 000 IoU evaluations per image; the
+// formulation below needs ~14 rounds of (one lean overlap test per candidate and
+// new centre) + (exact arithmetic for the few hundred pairs that do overlap).
 //
-// Three kernels-in-one, chosen per image by its survivor count S:
-//   S <= shared-memory pool (~7.4 k): the fast path below, every per-candidate array in shared memory;
-//   S <= 65 535: the same code with the per-candidate arrays in (L2-resident) global scratch rows;
-//   beyond: k3_generic, the literal one-round-per-selection formulation (list entries hold 16-bit indices).
-// One CTA per image (images are independent); B CTAs run concurrently.
+// One CTA per image (images are independent); B CTAs run concurrently.  Chosen per
+// image by its survivor count S:
+//   the per-candidate state fits the shared-memory pool: everything a round touches is on chip;
+//   S <= max_rows (65 535): the same code with the per-candidate arrays in (L2-resident) global scratch;
+//   beyond: k3_generic, the literal one-round-per-selection formulation.
 #include "bod_common.cuh"
 #include "bod_kernels.h"
 
 namespace bod {
-
-constexpr int kK3Threads = 1024;
-constexpr int kFastS = 7424;          // candidates the shared-memory kernel holds
 
 BOD_DEVINL unsigned long long make_key(float score, int idx) {
     return ((unsigned long long)float_key(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
@@ -72,7 +69,6 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
     float* cur = a.cur + (size_t)b * a.capacity;
     int32_t* begin = a.begin + (size_t)b * a.capacity;
     uint32_t* pend = a.pend + (size_t)b * a.capacity * kPendStride;
-    uint32_t* member = a.member + (size_t)b * Dmax * a.words;
     const bool is_soft = a.soft_nms_sigma > 0.0f;
     const float scale = is_soft ? -0.5f / a.soft_nms_sigma : 0.0f;
     const float thr = a.iou_threshold;
@@ -108,45 +104,37 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
         __syncthreads();
 
         best = 0ull;
-        const int S32 = (S + 31) & ~31;
-        for (int s = tid; s < S32; s += blockDim.x) {
-            bool mem = false;
-            if (s < S) {
-                const float4 bs = corners[s];
-                float u = cur[s];
-                const bool in_queue = (u > -INFINITY) && (s != x);
-                if (s == x) cur[s] = -INFINITY;
-                const float xI1 = fmaxf(bs.y, bx.y), yI1 = fmaxf(bs.x, bx.x);
-                const float xI2 = fminf(bs.w, bx.w), yI2 = fminf(bs.z, bx.z);
-                const bool wellformed = (bs.x <= bs.z) && (bs.y <= bs.w) && (bx.x <= bx.z) && (bx.y <= bx.w);
-                const bool maybe = !wellformed || (((xI2 - xI1) + 1.0f > 0.0f) && ((yI2 - yI1) + 1.0f > 0.0f));
-                if (maybe) mem = repo_iou(bs, bx) > thr;                         // :316, strict >
-                if (in_queue) {
-                    float t = stale[s];
-                    if (u != t && make_key(t, s) > kx) { t = u; stale[s] = t; begin[s] = r; }   // popped before x
-                    if (maybe) {
-                        const float sim = tf_iou(bs, bx);
-                        const float w = nms_weight(sim, scale, is_soft, thr);
-                        if (w != 1.0f) {
-                            uint32_t* pm = pend + (size_t)s * kPendStride;
-                            pm[r >> 5] |= 1u << (r & 31);
-                            const int bg = begin[s];
-                            float v = t;
-                            for (int j = r; j >= bg; --j) {     // pending selections, newest first
-                                if (!((pm[j >> 5] >> (j & 31)) & 1u)) continue;
-                                const float sj = (j == r) ? sim : tf_iou(bs, sel_box[j]);
-                                v = v * nms_weight(sj, scale, is_soft, thr);
-                            }
-                            u = v;
-                            if (!is_soft && w == 0.0f) u = -INFINITY;   // hard-NMS: removed for good
-                            cur[s] = u;
-                        }
+        for (int s = tid; s < S; s += blockDim.x) {
+            const float4 bs = corners[s];
+            float u = cur[s];
+            const bool in_queue = (u > -INFINITY) && (s != x);
+            if (s == x) cur[s] = -INFINITY;
+            if (!in_queue) continue;
+            const float xI1 = fmaxf(bs.y, bx.y), yI1 = fmaxf(bs.x, bx.x);
+            const float xI2 = fminf(bs.w, bx.w), yI2 = fminf(bs.z, bx.z);
+            const bool wellformed = (bs.x <= bs.z) && (bs.y <= bs.w) && (bx.x <= bx.z) && (bx.y <= bx.w);
+            const bool maybe = !wellformed || (((xI2 - xI1) + 1.0f > 0.0f) && ((yI2 - yI1) + 1.0f > 0.0f));
+            float t = stale[s];
+            if (u != t && make_key(t, s) > kx) { t = u; stale[s] = t; begin[s] = r; }   // popped before x
+            if (maybe) {
+                const float sim = tf_iou(bs, bx);
+                const float w = nms_weight(sim, scale, is_soft, thr);
+                if (w != 1.0f) {
+                    uint32_t* pm = pend + (size_t)s * kPendStride;
+                    pm[r >> 5] |= 1u << (r & 31);
+                    const int bg = begin[s];
+                    float v = t;
+                    for (int j = r; j >= bg; --j) {     // pending selections, newest first
+                        if (!((pm[j >> 5] >> (j & 31)) & 1u)) continue;
+                        const float sj = (j == r) ? sim : tf_iou(bs, sel_box[j]);
+                        v = v * nms_weight(sj, scale, is_soft, thr);
                     }
-                    if (u > -INFINITY) { const unsigned long long k = make_key(u, s); best = k > best ? k : best; }
+                    u = v;
+                    if (!is_soft && w == 0.0f) u = -INFINITY;   // hard-NMS: removed for good
+                    cur[s] = u;
                 }
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, mem);
-            if (lane == 0) member[(size_t)r * a.words + (s >> 5)] = bal;
+            if (u > -INFINITY) { const unsigned long long k = make_key(u, s); best = k > best ? k : best; }
         }
     }
     if (tid == 0) a.num_dets[b] = r;
@@ -158,7 +146,7 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
 }
 
 // ---------------------------------------------------------------------------
-// fast kernel: everything a round touches lives in shared memory.
+// round kernel.
 //
 // (1) Selections are BATCHED.  With every score up to date, walk the candidates in
 // key order y_1 > y_2 > ...  y_1 is the next centre.  A later y_q whose weight
@@ -177,33 +165,36 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
 // <= kBatch selections of the batch in order; pops that happened in rounds that
 // did not touch it fold the same (whole) pending list and are caught by the
 // first comparison of its next walk.
-// (3) The block-wide top-kTop of the NEXT round is folded into the same passes:
+// (3) The block-wide top list of the NEXT round is folded into the same passes:
 // every thread tracks the best two keys it has seen (untouched candidates in
 // pass A, updated ones in pass B); warps merge by popping heads (REDUX) into a
 // list of kTop1 keys each.  A list is cut where a thread runs out of tracked
 // keys (its third best is unknown), and the acceptance walk stops at the largest
 // such cut -- fewer centres in that round, never a wrong one.
-// (4) The expensive arithmetic runs one (candidate, centre) PAIR per thread.
-// A round is: acceptance (a team of four warps behind a named barrier: rank the
-// 128 listed keys by counting, one pair of examined candidates per thread, then
-// warp 0 walks them) | pass A: one lean overlap test of every survivor against
-// the batch (a superset filter: the centre grown by 2 px), overlapping pairs
-// compacted into the warp's own list segment | pass B1: IoU + exp for every
-// listed pair, and the pair's cluster-membership bit (bbox_iou_vuvu > threshold,
-// inference_utils.py:316) | pass B2: the epoch walk of every listed candidate
-// over its precomputed weights.  A survivor is scanned by the same thread every
-// round, so B1 / B2 work on the warp's own segment without a block barrier: two
-// block barriers per round, no global memory on the critical path: the first
-// psm pending weights of every candidate live in shared memory (psm is chosen
-// per image from its survivor count), the rest spill to global rows.
+// (4) Work layout.  Candidate s belongs to warp s % W, lane (s / W) % 32 (W warps
+// per CTA): neighbouring survivor indices -- which is what the top of a tie group
+// looks like, ties go to the lower index -- land in different warps, so the
+// per-warp lists rarely cut the block-wide top list.  A round is:
+//   acceptance (four warps behind a named barrier: rank the listed keys by
+//   counting, one pair of examined candidates per thread, then warp 0 walks them)
+//   | pass A: every thread tests its own queued candidates against the batch
+//   centres grown by 2 px (a superset filter: four compares per pair, centres
+//   in the outer loop, the thread's candidates in registers), candidates that
+//   may overlap are listed (one entry per candidate: who, and a bit per centre)
+//   in the warp's own segment
+//   | pass B: one listed candidate per lane: IoU + exp for its pairs, then the
+//   epoch walk.  A candidate's state is only ever touched by its own warp, so
+//   pass B needs no block barrier: two block barriers per round.
+// The first psm pending weights of every candidate live in shared memory (psm is
+// what fits for the image's survivor count), the rest spill to global rows.
 // ---------------------------------------------------------------------------
-constexpr int kK3Warps = kK3Threads / 32;
-constexpr int kSegCap = 4096 / kK3Warps; // (candidate, centre) pairs listed per warp and round
-constexpr int kTop1 = 128 / kK3Warps;  // keys every warp lists per round
 constexpr int kTop = 16;              // candidates examined per round
-constexpr int kBatch = 16;            // centres selected per round at most
+constexpr int kBatch = 15;            // centres selected per round at most (pair entries name them in 4 bits; 15 = "no centre")
+constexpr int kTauRank = 31;          // rank (among the listed keys) of the key below which scores are kept as upper bounds
+constexpr int kListed = 64;           // keys listed per round by all warps together
 constexpr int kExpTab = 129;
 constexpr int kTeamWarps = 4;         // warps that share a round's acceptance work
+constexpr int kPairsCta = 4096;       // (candidate, centre) pairs the warps' list segments hold together
 
 BOD_DEVINL void team_barrier() {      // named barrier 1: the acceptance team only
     asm volatile("bar.sync 1, %0;" ::"n"(kTeamWarps * 32) : "memory");
@@ -211,8 +202,8 @@ BOD_DEVINL void team_barrier() {      // named barrier 1: the acceptance team on
 
 struct K3Smem {
     unsigned long long warp_best[2][32];         // generic kernel scratch
-    unsigned long long top_w[kK3Warps][kTop1];   // per-warp top keys (descending, 0 = none)
-    unsigned long long bound_w[kK3Warps];        // every key of the warp that is not in top_w is below this (0: there is none)
+    unsigned long long top_flat[kListed];        // per-warp top keys (descending, 0 = none): warp w at [w * kTop1, (w+1) * kTop1)
+    unsigned long long bound_w[32];              // every key of the warp that is not listed is below this (0: there is none)
     unsigned long long sel_key[kMaxOut];         // key (score, -index) of every selected centre
     float4 sel_box[kMaxOut];
     unsigned long long cand_key[kTop];           // the round's examined candidates ...
@@ -221,27 +212,17 @@ struct K3Smem {
     float wpair[kTop][kTop];                     // ... their pairwise soft-NMS weights [q][i], i < q
     uint32_t rowmask[kTop];                      // bit i of row q: wpair[q][i] != 1
     double exp_tab[kExpTab];                     // exp(-k/64)
+    unsigned long long tau[2];                   // the round's laziness threshold (see k3_walk), by round parity
     int batch_n;                                 // centres selected in this round
     int malformed;
 };
 
 struct K3State {                                  // kernel-lifetime constants (registers)
     const float4* corn; float* ucur; float* stl; uint8_t* npend;
-    float* pws; int S32, psm;                     // pending weights in shared memory: entry i of candidate s at pws[s*psm+i], i < psm (psm % 4 == 0)
-    float* pwg; int pstride;                      // spill rows in global memory: entry i >= psm at pwg[s*pstride+i]
-    uint32_t* member; int words;                  // membership rows of this image
+    float* pws; int psm;                          // pending weights in shared memory: entry i of state row si at pws[si*psm+i], i < psm
+    float* pwg; int pstride;                      // spill rows in global memory: entry i >= psm of survivor s at pwg[s*pstride+i]
     float scale, thr; bool is_soft;
 };
-
-// list entry: candidate | centre-of-batch << 16 | first pair of its candidate << 20 | candidate queued << 21 | pairs of the candidate << 22
-BOD_DEVINL uint32_t ent_make(int s, int q, bool head, bool queued, int c) {
-    return (uint32_t)s | ((uint32_t)q << 16) | ((uint32_t)head << 20) | ((uint32_t)queued << 21) | ((uint32_t)c << 22);
-}
-BOD_DEVINL int ent_s(uint32_t e) { return (int)(e & 0xFFFFu); }
-BOD_DEVINL int ent_q(uint32_t e) { return (int)((e >> 16) & 15u); }
-BOD_DEVINL bool ent_head(uint32_t e) { return (e >> 20) & 1u; }
-BOD_DEVINL bool ent_queued(uint32_t e) { return (e >> 21) & 1u; }
-BOD_DEVINL int ent_pairs(uint32_t e) { return (int)((e >> 22) & 31u); }
 
 // exp(y) rounded to binary32 for the soft-NMS argument range: y = -k/64 + r, table of exp(-k/64) in
 // binary64 and a degree-6 Taylor polynomial in r (|r| <= 1/128, error < 2e-17): the binary64 value is
@@ -268,16 +249,6 @@ BOD_DEVINL float nms_weight_fast(float sim, float scale, bool is_soft, float thr
     return (is_soft || sim <= thr) ? w : 0.0f;
 }
 
-// bbox_iou_vuvu(survivor, centre) > threshold (strict), skipping the division when the boxes cannot
-// overlap even with the +1 pixel convention ((hi - lo) + 1 > 0 <=> hi - lo > -1 in binary32)
-BOD_DEVINL bool is_member(const float4 bs, const float4 bx, float thr) {
-    const float dx = fminf(bs.w, bx.w) - fmaxf(bs.y, bx.y);
-    const float dy = fminf(bs.z, bx.z) - fmaxf(bs.x, bx.x);
-    const bool wellformed = (bx.x <= bx.z) && (bx.y <= bx.w) && (bs.x <= bs.z) && (bs.y <= bs.w);
-    if (!wellformed || (dx > -1.0f && dy > -1.0f)) return repo_iou(bs, bx) > thr;
-    return false;
-}
-
 // best two keys a thread has seen in a round
 struct Top2 {
     unsigned long long a = 0ull, b = 0ull;
@@ -286,104 +257,161 @@ struct Top2 {
     }
 };
 
-BOD_DEVINL void pend_put(const K3State& C, int s, int i, float w) {
-    if (i < C.psm) C.pws[s * C.psm + i] = w; else C.pwg[(size_t)s * C.pstride + i] = w;
+BOD_DEVINL void pend_put(const K3State& C, int si, int s, int i, float w) {
+    if (i < C.psm) C.pws[si * C.psm + i] = w; else C.pwg[(size_t)s * C.pstride + i] = w;
 }
-// st * (pending weights, newest first).  The shared-memory part of the list is a row of the candidate
-// (psm is a multiple of 4): blocks of four weights per LDS.128, the next block in flight while the
-// current one is multiplied in.
-BOD_DEVINL float pend_product(const K3State& C, int s, int n, float st) {
-    float v = st;
-    int i = n - 1;
-    for (; i >= C.psm; --i) v = v * C.pwg[(size_t)s * C.pstride + i];        // spilled entries (rare)
-    if (i < 0) return v;
-    const float4* row = reinterpret_cast<const float4*>(C.pws + s * C.psm);
-    int blk = i >> 2;
-    float4 cur = row[blk];
-    const int top = i & 3;
+// entries 4b .. 4b+3 of a pending list (psm and pstride are multiples of 4: a block never straddles)
+BOD_DEVINL float4 pend_block(const K3State& C, int si, int s, int b) {
+    return (4 * b < C.psm) ? *reinterpret_cast<const float4*>(C.pws + si * C.psm + 4 * b)
+                           : *reinterpret_cast<const float4*>(C.pwg + (size_t)s * C.pstride + 4 * b);
+}
+// v * (entries n-1 .. 0 of the pending list), in that order: four weights per load, the next block in
+// flight while the current one is multiplied in
+BOD_DEVINL float pend_product(const K3State& C, int si, int s, int n, float v) {
+    if (n <= 0) return v;
+    int blk = (n - 1) >> 2;
+    float4 cur = pend_block(C, si, s, blk);
+    const int top = (n - 1) & 3;
     {
-        const float4 nxt = row[blk > 0 ? blk - 1 : 0];
+        const float4 nxt = pend_block(C, si, s, blk > 0 ? blk - 1 : 0);
         if (top >= 3) v = v * cur.w;
         if (top >= 2) v = v * cur.z;
         if (top >= 1) v = v * cur.y;
         v = v * cur.x;
         cur = nxt;
     }
+#pragma unroll 1
     for (--blk; blk >= 0; --blk) {
-        const float4 nxt = row[blk > 0 ? blk - 1 : 0];
+        const float4 nxt = pend_block(C, si, s, blk > 0 ? blk - 1 : 0);
         v = v * cur.w; v = v * cur.z; v = v * cur.y; v = v * cur.x;
         cur = nxt;
     }
     return v;
 }
 
-// Epoch walk of one QUEUED candidate s over the round's batch (selections r0 .. r0+m-1), driven by the
-// candidate's listed pairs in ascending centre order: step(q, w) for every batch centre q it overlaps
-// (w = its soft-NMS weight against that centre), then finish().  TF pops s right before selection j iff
-// it has pending weights and key(stale) > key(selection j); between two of its pairs the pending list
-// does not change and the selection keys decrease, so such a pop exists in (q_prev, q] iff
-// key(stale) > key(selection q), and wherever it happens it folds the same list.
-struct K3Walk {
-    float st;
-    int n, n_in, last_q;
-    bool folded, dead;
-    unsigned long long ks;
-    BOD_DEVINL void begin(const K3State& C, int s) {
-        st = C.stl[s]; n = C.npend[s]; n_in = n; last_q = -1; folded = false; dead = false;
-        ks = make_key(st, s);
-    }
-    BOD_DEVINL void fold(const K3State& C, int s) {        // newest first
-        st = pend_product(C, s, n, st);
-        n = 0; folded = true;
-        ks = make_key(st, s);
-    }
-    BOD_DEVINL void step(const K3State& C, const K3Smem& sm, int r0, int s, int q, float w) {
-        if (dead) return;
-        if (n > 0 && ks > sm.sel_key[r0 + q]) fold(C, s);
-        last_q = q;
-        if (w != 1.0f) {
-            if (!C.is_soft && w == 0.0f) { dead = true; return; }           // hard-NMS: removed for good
-            pend_put(C, s, n, w);
-            ++n;
+// list entry of one (candidate, centre) pair: row of the block | owner lane << 3 | centre of the batch << 8 |
+// first pair of its candidate << 12 | pairs of the candidate << 13
+BOD_DEVINL uint32_t ent_make(int j, int ln, int q, bool head, int c) {
+    return (uint32_t)j | ((uint32_t)ln << 3) | ((uint32_t)q << 8) | ((uint32_t)head << 12) | ((uint32_t)c << 13);
+}
+BOD_DEVINL int ent_row(uint32_t e) { return (int)(e & 7u); }
+BOD_DEVINL int ent_lane(uint32_t e) { return (int)((e >> 3) & 31u); }
+BOD_DEVINL int ent_q(uint32_t e) { return (int)((e >> 8) & 15u); }
+BOD_DEVINL int ent_pairs(uint32_t e) { return (int)((e >> 13) & 31u); }
+
+// Epoch walk of one QUEUED candidate (survivor s, state row si) over a batch of selections whose keys are
+// sel_key[0 .. qlast] (the caller passes the batch's slice of sm.sel_key), driven by the candidate's listed
+// pairs in ascending centre order: ents[i] names the centre, ws[i] is the exact soft-NMS weight, i < c.
+// TF pops s right before selection j iff it has pending weights and key(stale) > key(selection j), and then
+// folds every pending weight into the stale score, newest first.  Between two of the candidate's pairs the
+// pending list does not change and the selection keys decrease, so such a pop exists in (q_prev, q] iff
+// key(stale) > key(selection q), and wherever it happens it folds the same list; pops hidden behind centres
+// the candidate does not overlap (weight exactly 1) are caught by the next comparison the same way.
+// The pending list is (old entries, in memory) ++ (this batch's non-unit weights, in ws): a product over it,
+// newest first, walks ws backwards (unit weights multiply exactly) and then the old entries.
+//
+// Lazy scores.  A candidate far below the top of the queue needs no score, only a bound that keeps it out of
+// the examined candidates: TF itself never looks at it until the queue's front reaches it.  When no pop can be
+// due in this batch (key(stale) <= key(last selection); the selection keys decrease) the walk would only append
+// the new weights, so that is all that is done, and the score is replaced by an UPPER BOUND (previous score or
+// bound x new weights x a rounding allowance), stored negated.  Bounds at or above `tau` (a key well below the
+// examined ones) are not allowed: such a candidate takes the exact path -- which never reads the old score --
+// and owners list their bounded candidates for it (with no centre at all) once tau has come down to them.
+// The pending list, the stale score and the epoch logic are the same on both paths; only how often the
+// O(list) product is evaluated differs (without this, candidates TF never pops accumulate lists of dozens of
+// weights that are re-multiplied on every touch).
+// One loop with one product site (steps 0..c-1: the pairs, c: pops behind the batch's last selections,
+// c+1: the up-to-date score): the kernel's round loop has to stay small for the instruction cache.
+// Returns the new score (>= 0), the negated bound, or -inf (removed by hard-NMS).
+#ifdef BOD_DIAGNOSTICS
+__device__ unsigned long long g_k3_cnt[8];     // 0 walks, 1 bounded (lazy) walks, 2 untouched, 3 products, 4 product entries, 5 folds, 6 woken
+#define K3_CNT(i, v) atomicAdd(&g_k3_cnt[i], (unsigned long long)(v))
+#else
+#define K3_CNT(i, v)
+#endif
+BOD_DEVINL float k3_walk(const K3State& C, const unsigned long long* sel_key, int qlast, unsigned long long tau,
+                         int si, int s, const uint32_t* ents, const float* ws, int c) {
+    K3_CNT(0, 1);
+    float st = C.stl[si];
+    int n_old = C.npend[si];              // old entries still pending (0 once folded)
+    unsigned long long ks = make_key(st, s);
+    const float uprev = C.ucur[si];
+    if (!(uprev > -INFINITY)) return -INFINITY;    // removed by an earlier piece of this batch (hard-NMS, piecewise pass B)
+    const bool was_exact = __float_as_int(uprev) >= 0;
+    if (qlast >= 0 && !(ks > sel_key[qlast])) {
+        float ub = fabsf(uprev);
+        if (was_exact) ub = ub * 1.00005f;                          // the same factors in another order: <= 2n+2 roundings apart, n <= 255
+        int nn = 0;
+        bool dead = false;
+#pragma unroll 1
+        for (int i = 0; i < c; ++i) {
+            const float w = ws[i];
+            if (w != 1.0f) { ub = ub * w * 1.0000005f; ++nn; dead = dead || (!C.is_soft && w == 0.0f); }
+        }
+        if (dead) { C.ucur[si] = -INFINITY; return -INFINITY; }     // hard-NMS: removed for good
+        if (nn == 0 && was_exact) { K3_CNT(2, 1); return uprev; }   // every weight was exactly 1: untouched
+        if (make_key(ub, s) < tau) {
+            K3_CNT(1, 1);
+            int base = n_old;
+#pragma unroll 1
+            for (int i = 0; i < c; ++i) { const float w = ws[i]; if (w != 1.0f) pend_put(C, si, s, base++, w); }
+            C.npend[si] = (uint8_t)base;
+            const float nb = __int_as_float(__float_as_int(ub) | (int)0x80000000);
+            C.ucur[si] = nb;
+            return nb;
         }
     }
-    // returns the candidate's new up-to-date score (-inf: removed by hard-NMS)
-    BOD_DEVINL float finish(const K3State& C, const K3Smem& sm, int r0, int m, int s) {
-        if (dead) { C.ucur[s] = -INFINITY; return -INFINITY; }
-        if (last_q < m - 1 && n > 0 && ks > sm.sel_key[r0 + m - 1]) fold(C, s);   // popped before a later selection of the batch
-        if (!folded && n == n_in) return C.ucur[s];        // every weight was exactly 1: untouched
-        const float u = pend_product(C, s, n, st);
-        C.ucur[s] = u;
-        C.npend[s] = (uint8_t)n;
-        if (folded) C.stl[s] = st;
-        return u;
+    if (!was_exact) K3_CNT(6, 1);
+    bool folded = false;
+    int nf = 0, nn = 0;                   // ws[nf..) belong to the pending list; nn of them are not 1
+    int last_q = -1;
+    float u = 0.0f;
+#pragma unroll 1
+    for (int i = 0; i <= c + 1; ++i) {
+        bool want;                        // the product over the pending list is needed at this step
+        float w = 1.0f;
+        int q = qlast;
+        if (i < c) {
+            w = ws[i];
+            if (w == 1.0f) continue;                                 // the centre does nothing to this candidate
+            q = ent_q(ents[i]);
+            want = (n_old + nn) > 0 && ks > sel_key[q];              // popped (folded) before selection q
+        } else if (i == c) {
+            want = last_q < qlast && (n_old + nn) > 0 && ks > sel_key[qlast];   // popped before a later selection of the batch
+                                                                                 // (qlast = -1: no selections, nothing to check)
+        } else {
+            if (!folded && nn == 0 && was_exact) return uprev;       // every weight was exactly 1: untouched
+            want = true;
+        }
+        if (want) {
+            const int upto = i < c ? i : c;
+            float v = st;
+#pragma unroll 1
+            for (int k = upto - 1; k >= nf; --k) v = v * ws[k];
+            v = pend_product(C, si, s, n_old, v);
+            K3_CNT(3, 1); K3_CNT(4, n_old + (upto - nf)); if (i <= c) K3_CNT(5, 1);
+            if (i <= c) { st = v; n_old = 0; nf = upto; nn = 0; folded = true; ks = make_key(st, s); }
+            else u = v;
+        }
+        if (i < c) {
+            last_q = q;
+            if (!C.is_soft && w == 0.0f) { C.ucur[si] = -INFINITY; return -INFINITY; }   // hard-NMS: removed for good
+            ++nn;
+        }
     }
-};
-
-// A whole candidate in place (only when a warp's list segment is full): membership bits and, if the
-// candidate is queued, its walk with the weights computed on the fly.
-__device__ __noinline__ float k3_process_inplace(const K3State* Cp, const K3Smem& sm, const int r0, const int m, const uint32_t mask,
-                                                 const int s, const bool queued) {
-    const K3State C = *Cp;                                  // a shared-memory copy: nothing of the caller's is forced to the stack
-    const float4 bs = C.corn[s];
-    for (uint32_t rem = mask; rem; rem &= rem - 1) {
-        const int q = __ffs(rem) - 1;
-        if (is_member(bs, sm.sel_box[r0 + q], C.thr))
-            atomicOr(&C.member[(size_t)(r0 + q) * C.words + (s >> 5)], 1u << (s & 31));
-    }
-    if (!queued) return -INFINITY;
-    K3Walk wk;
-    wk.begin(C, s);
-    for (uint32_t rem = mask; rem; rem &= rem - 1) {
-        const int q = __ffs(rem) - 1;
-        wk.step(C, sm, r0, s, q, nms_weight_fast(tf_iou(bs, sm.sel_box[r0 + q]), C.scale, C.is_soft, C.thr, sm.exp_tab));
-    }
-    return wk.finish(C, sm, r0, m, s);
+    int base = n_old;
+#pragma unroll 1
+    for (int k = nf; k < c; ++k) { const float w = ws[k]; if (w != 1.0f) pend_put(C, si, s, base++, w); }
+    C.npend[si] = (uint8_t)base;
+    C.ucur[si] = u;
+    if (folded) C.stl[si] = st;
+    return u;
 }
 
 // Warp-level merge of the lanes' Top2 pairs: every lane returns with the warp's best keys in out[]
 // (descending, 0 = none), cut after the first key whose lane has nothing tracked behind it; `bound`
 // is that key (0 when the list was not cut and the warp has no further keys).
+template <int kTop1>
 BOD_DEVINL void warp_top_merge2(Top2 t, unsigned long long (&out)[kTop1], unsigned long long& bound) {
     unsigned long long cur = t.a, nxt = t.b;
     bool spent = false;                                     // this lane's second key has been promoted already
@@ -401,32 +429,48 @@ BOD_DEVINL void warp_top_merge2(Top2 t, unsigned long long (&out)[kTop1], unsign
     if (!cut) bound = out[kTop1 - 1];                       // untracked keys are below the last one listed
 }
 
-__global__ void __launch_bounds__(kK3Threads, 1)
-k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
+#ifdef BOD_DIAGNOSTICS
+#define K3_T(var) long long var = clock64()
+#define K3_ACC(slot, t1, t0) if (lane == 0) dbg_acc[slot] += (t1) - (t0)
+#else
+#define K3_T(var)
+#define K3_ACC(slot, t1, t0)
+#endif
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
+k3_softnms_kernel(K3Args a, int pool_bytes) {
+    constexpr int W = NT / 32;                              // warps
+    constexpr int kTop1 = kListed / W;                      // keys every warp lists per round
+    constexpr int kSegCap = kPairsCta / W;                  // pairs per warp segment
+    constexpr int kCH = NT >= 1024 ? 4 : 8;                 // candidates per thread handled per pass-A/B block (registers)
+    static_assert(W >= kTeamWarps && kTop1 >= 2 && kTop1 * W == kListed && kSegCap >= 32, "CTA size");
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ K3Smem sm;
-    __shared__ K3State kc;
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = a.num_survivors[b];
-    // more survivors than the shared-memory pool holds: same algorithm with the per-candidate state in
-    // global memory (L2-resident scratch rows of the workspace); beyond 16-bit list entries: the literal kernel
-    const bool big = S > smem_S;
-    if (big && S > a.max_rows) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
+    if (S > a.max_rows) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
 
-    const int S32 = (S + 31) & ~31;
-    uint32_t* list = reinterpret_cast<uint32_t*>(dyn);                    // [kK3Warps][kSegCap] pair entries (ent_make)
-    float* wl = reinterpret_cast<float*>(list + kK3Warps * kSegCap);      // [kK3Warps][kSegCap] their soft-NMS weights
-    float4* corn = reinterpret_cast<float4*>(wl + kK3Warps * kSegCap);    // [S32] corners
-    float* ucur = reinterpret_cast<float*>(corn + S32);                   // [S32] up-to-date score, -inf = not queued
-    float* stl = ucur + S32;                                              // [S32] score as of the last fold
+    // Candidate rows: thread `tid` owns survivor s = k*NT + lane*W + warp of row k; its state row (shared
+    // memory) is si = k*NT + tid.  More survivors than the pool holds: state in the workspace's global
+    // rows, indexed by s, corners read in place.
+    const int nrows = (S + NT - 1) / NT;
+    const int SP = nrows * NT;
+    uint32_t* list = reinterpret_cast<uint32_t*>(dyn);                    // [W][kSegCap] pair entries (ent_make)
+    float* wl = reinterpret_cast<float*>(list + kPairsCta);               // [W][kSegCap] their soft-NMS weights
+    uint16_t* hl = reinterpret_cast<uint16_t*>(wl + kPairsCta);           // [W][kSegCap] first pair of every listed candidate
+    const bool big = (long long)SP * 25 > (long long)pool_bytes || a.force_big != 0;
+    float4* corn = reinterpret_cast<float4*>(hl + kPairsCta);             // [SP] corners
+    float* ucur = reinterpret_cast<float*>(corn + SP);                    // [SP] up-to-date score, -inf = not queued
+    float* stl = ucur + SP;                                               // [SP] score as of the last fold
     // pending weights per candidate held in shared memory: whatever fits behind the fixed arrays
-    int psm = S32 > 0 ? (pool_bytes - S32 * 25) / (S32 * 4) : 0;
+    int psm = (SP > 0 && !big) ? (pool_bytes - SP * 25) / (SP * 4) : 0;
     psm = psm < 0 ? 0 : (psm > a.pstride ? a.pstride : psm);
-    if (a.psm_max >= 0 && psm > a.psm_max) psm = a.psm_max;              // diagnostics: force the global spill rows
+    if (a.psm_max >= 0 && psm > a.psm_max) psm = a.psm_max;              // tests: force the global spill rows
     psm &= ~3;                                                            // rows are read four weights at a time
-    float* pws = stl + S32;                                               // [S32][psm]
-    uint8_t* npend = reinterpret_cast<uint8_t*>(pws + (size_t)psm * S32); // [S32] pending entries per candidate
+    float* pws = stl + SP;                                                // [SP][psm]
+    uint8_t* npend = reinterpret_cast<uint8_t*>(pws + (size_t)psm * SP);  // [SP] pending entries per candidate
     if (big) {
         corn = const_cast<float4*>(a.corners + (size_t)b * a.capacity);   // read in place, never written
         ucur = a.cur + (size_t)b * a.capacity;
@@ -440,89 +484,95 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
     const float* score = a.score + (size_t)b * a.capacity;
     K3State C;
     C.corn = corn; C.ucur = ucur; C.stl = stl; C.npend = npend;
-    C.pws = pws; C.S32 = S32; C.psm = psm;
+    C.pws = pws; C.psm = psm;
     C.pwg = a.pw + (size_t)b * a.pw_rows * a.pstride; C.pstride = a.pstride;
-    C.member = a.member + (size_t)b * Dmax * a.words; C.words = a.words;
     C.is_soft = a.soft_nms_sigma > 0.0f;
     C.scale = C.is_soft ? -0.5f / a.soft_nms_sigma : 0.0f;
     C.thr = a.iou_threshold;
+    // state row of survivor s (used where a key names the candidate)
+    auto row_of = [&](int s) -> int {
+        if (big) return s;
+        const int r = s & (NT - 1);
+        return (s - r) + (r % W) * 32 + r / W;
+    };
 
-    if (tid == 0) { sm.malformed = 0; kc = C; }
-    for (int k = tid; k < kExpTab; k += kK3Threads) sm.exp_tab[k] = c_exp_tab[k];
-    // membership rows start out empty (only the words K4 / bod_fetch_members read)
-    {
-        const int nw = S32 >> 5;
-        for (int d = warp; d < Dmax; d += kK3Warps)
-            for (int w = lane; w < nw; w += 32) C.member[(size_t)d * a.words + w] = 0u;
-    }
+    if (tid == 0) sm.malformed = 0;
+    for (int k = tid; k < kExpTab; k += NT) sm.exp_tab[k] = c_exp_tab[k];
     __syncthreads();
 
     // ---- load; the first round's top keys come from the initial scores ----
     Top2 t2k;
-    for (int s = tid; s < S; s += kK3Threads) {
+    unsigned long long ixmax = 0ull;                        // largest key(upper bound) this thread has seen in the round
+    for (int k = 0; k < nrows; ++k) {
+        const int s = k * NT + lane * W + warp;
+        if (s >= S) continue;
+        const int si = big ? s : k * NT + tid;
         const float4 c = corners[s];
-        if (!big) corn[s] = c;
+        if (!big) corn[si] = c;
         // corners out of order need the canonicalising IoU path for every pair; so do coordinates so large
         // that the 2 px margin of pass A's lean test is not safely above their rounding
         if (!((c.x <= c.z) && (c.y <= c.w)) || !(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))) < 1.0e5f))
             sm.malformed = 1;
         const float sc = score[s];
         const bool queued = sc > -INFINITY;                              // scores_data[i] > score_threshold (-inf); NaN stays out
-        ucur[s] = queued ? sc : -INFINITY;
-        stl[s] = sc;
-        npend[s] = 0;
+        ucur[si] = queued ? sc : -INFINITY;
+        stl[si] = sc;
+        npend[si] = 0;
         if (queued) t2k.add(make_key(sc, s));
     }
 
-    long long tA = 0, tB = 0, tC = 0, tL = 0, t0 = 0, t1 = 0, t2c = 0, t3 = 0, tm = 0, tw = 0, tM = 0, tW = 0, tx1 = 0, tx2 = 0, tR = 0, tP = 0;
-    int r = 0, rounds = 0;
+#ifdef BOD_DIAGNOSTICS
+    // per warp (lane 0): 0 merge, 1 wait at barrier 1, 2 rank, 3 pairwise, 4 walk, 5 wait at barrier 2, 6 pass A, 7 pass B,
+    // 8 listed candidates, 9 spilled weights read, 10 rounds, 11 psm
+    long long dbg_acc[12] = {0};
+#endif
+    int r = 0, rnd = 0;
     while (r < Dmax) {
-        if (a.dbg && tid == 0) t0 = clock64();
+        K3_T(c0);
         // ---- warp lists of this round's best keys ----
         {
             unsigned long long out[kTop1], bound;
-            warp_top_merge2(t2k, out, bound);
+            warp_top_merge2<kTop1>(t2k, out, bound);
             if (lane < kTop1) {
                 unsigned long long v = out[0];
 #pragma unroll
                 for (int q = 1; q < kTop1; ++q) v = (lane == q) ? out[q] : v;
-                sm.top_w[warp][lane] = v;
+                sm.top_flat[warp * kTop1 + lane] = v;
             }
-            if (lane == 0) sm.bound_w[warp] = bound;
+            // a candidate whose score is only an upper bound is never examined, and nothing below its bound is
+            const unsigned long long ixw = warp_max_u64(ixmax);
+            if (lane == 0) sm.bound_w[warp] = bound > ixw ? bound : ixw;
         }
         if (tid < kTop) { sm.cand_key[tid] = 0ull; sm.rowmask[tid] = 0u; }     // filled by the acceptance team below
-        if (a.dbg && tid == 0) tm = clock64();
+        if (tid == 0) sm.tau[rnd & 1] = 0ull;                                  // fewer than kTauRank+1 listed keys: every score exact
+        K3_T(c1);
         __syncthreads();
-        if (a.dbg && tid == 0) tw = clock64();
+        K3_T(c2);
+        K3_ACC(0, c1, c0); K3_ACC(1, c2, c1);
         if (warp < kTeamWarps) {
             // ---- acceptance, by the first four warps (named barrier 1 among them) ----
-            // (i) the block's top-kTop keys: thread t ranks entry t of the kK3Warps x kTop1 = 128 listed keys
-            // by counting the larger ones; G = the largest cut of any warp's list: below it an untracked key
-            // might outrank a listed one, so such entries are dropped (validity is a prefix of the order)
-            static_assert(kK3Warps * kTop1 == kTeamWarps * 32, "one listed key per thread of the acceptance team");
-            const unsigned long long* flat = &sm.top_w[0][0];
-            {
-                unsigned long long G = (lane < kK3Warps) ? sm.bound_w[lane] : 0ull;
+            // (i) the block's top-kTop keys: thread t < kListed ranks listed key t by counting the larger ones;
+            // G = the largest cut of any warp's list: below it an untracked key might outrank a listed one,
+            // so such entries are dropped (validity is a prefix of the order)
+            if (tid < kListed) {
+                unsigned long long G = (lane < W) ? sm.bound_w[lane] : 0ull;
                 G = warp_max_u64(G);
-                const unsigned long long key = flat[tid];
+                const unsigned long long key = sm.top_flat[tid];
                 if (key != 0ull && key >= G) {
-                    // the listed scores are non-negative floats in practice, so the high words alone decide almost
-                    // every comparison: count on 32-bit words, resolve equal scores (ties) on the index words
-                    const uint32_t khi = (uint32_t)(key >> 32), klo = (uint32_t)key;
-                    const uint4* f4 = reinterpret_cast<const uint4*>(flat);        // (lo, hi, lo, hi) of two keys
-                    int r0 = 0, r1 = 0;
-#pragma unroll 16
-                    for (int j = 0; j < kTeamWarps * 16; ++j) {
-                        const uint4 kk = f4[j];
-                        r0 += (kk.y > khi) || (kk.y == khi && kk.x > klo);
-                        r1 += (kk.w > khi) || (kk.w == khi && kk.z > klo);
+                    const ulonglong2* f2 = reinterpret_cast<const ulonglong2*>(sm.top_flat);
+                    int rank = 0;
+#pragma unroll 4
+                    for (int j = 0; j < kListed / 2; ++j) {
+                        const ulonglong2 kk = f2[j];
+                        rank += (int)(kk.x > key) + (int)(kk.y > key);
                     }
-                    const int rank = r0 + r1;
-                    if (rank < kTop) { sm.cand_key[rank] = key; sm.cand_box[rank] = corn[key_index(key)]; }
+                    if (rank < kTop) { sm.cand_key[rank] = key; sm.cand_box[rank] = corn[row_of(key_index(key))]; }
+                    if (rank == kTauRank) sm.tau[rnd & 1] = key;
                 }
             }
             team_barrier();
-            if (a.dbg && tid == 0) tx1 = clock64();
+            K3_T(c3);
+            K3_ACC(2, c3, c2);
             // (ii) pairwise weights among the examined candidates, one pair (q, i), i < q, per thread.  Most pairs
             // do not intersect at all (weight exactly 1): the division + exp runs only for those that do
             if (tid < kTop * (kTop - 1) / 2) {
@@ -541,8 +591,10 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
                 }
             }
             team_barrier();
-            if (a.dbg && tid == 0) tx2 = clock64();
+            K3_T(c4);
+            K3_ACC(3, c4, c3);
         }
+        K3_T(c5);
         if (warp == 0) {
             // (iii) accept centres in key order (see header); every lane walks, lane p < kTop owns candidate p
             const unsigned long long myk = (lane < kTop) ? sm.cand_key[lane] : 0ull;
@@ -579,117 +631,223 @@ k3_softnms_kernel(K3Args a, int smem_S, int pool_bytes) {
                 sm.sel_box[pos] = cb;
                 sm.batch_ebox[pos - r] = make_float4(cb.x - 2.0f, cb.y - 2.0f, cb.z + 2.0f, cb.w + 2.0f);
                 sm.sel_key[pos] = myk;
-                ucur[x] = -INFINITY;                                     // leaves the queue
+                ucur[row_of(x)] = -INFINITY;                             // leaves the queue
                 a.nms_idx[(size_t)b * Dmax + pos] = x;
                 a.nms_score[(size_t)b * Dmax + pos] = key_score(myk);
             }
-            if (lane == 0) sm.batch_n = m;
+            // nothing examinable although keys exist (every listed key is below some candidate's upper bound):
+            // a refresh round (-1) makes all bounds exact
+            if (lane == 0) {
+                unsigned long long G = 0ull;
+                for (int w = 0; w < W; ++w) G = sm.bound_w[w] > G ? sm.bound_w[w] : G;
+                sm.batch_n = (m == 0 && G != 0ull) ? -1 : m;
+            }
         }
+        K3_T(c6);
         __syncthreads();
-        const int m = sm.batch_n;
-        if (m == 0) break;                                                     // queue empty
-        if (a.dbg && tid == 0) t1 = clock64();
+        K3_T(c7);
+        K3_ACC(4, c6, c5); K3_ACC(5, c7, c6);
+        const bool refresh = sm.batch_n < 0;
+        const int m = refresh ? 0 : sm.batch_n;
+        if (m == 0 && !refresh) break;                                         // queue empty
         const bool all_maybe = sm.malformed != 0;
+        const uint32_t full = (1u << m) - 1u;                                  // m <= kBatch = 15
+        const uint32_t wake = 1u << m;                                         // pseudo-centre: "make this score exact"
+        const unsigned long long tau = refresh ? 0ull : sm.tau[rnd & 1];
 
-        // ---- pass A: geometric overlap of every survivor with the batch centres (queued or not: selected
-        // and removed survivors still belong to clusters) ----
         t2k = Top2();
-        int cnt = 0;                                                           // entries in this warp's segment
+        ixmax = 0ull;
         uint32_t* seg = list + warp * kSegCap;
-        const int seg_cap = (a.seg_cap >= 0 && a.seg_cap < kSegCap) ? a.seg_cap : kSegCap;   // tests shrink it
-        for (int s = tid; s < S32; s += kK3Threads) {
-            uint32_t mask = 0u;
-            bool queued = false;
-            if (s < S) {
-                const float u = ucur[s];
-                queued = u > -INFINITY;
-                const float4 bs = corn[s];
-                // No overlap even with the +1 pixel convention => not a member, and TF's intersection area
-                // max(dy,0)*max(dx,0) is 0 => IoU = 0, weight exactly 1: the centre does nothing to this survivor.
-                // The test here only has to be a superset of "(hi - lo) > -1 in both dimensions" (passes B1 / B2
-                // decide exactly), so it compares against the centre grown by 2 px: four compares per pair.
-                for (int q = 0; q < m; ++q) {
-                    const float4 e = sm.batch_ebox[q];
-                    if ((bs.z > e.x && bs.x < e.z && bs.w > e.y && bs.y < e.w) || all_maybe) mask |= 1u << q;
-                }
-                if (mask == 0u && queued) t2k.add(make_key(u, s));
-            }
-            const int c = __popc(mask);
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total != 0) {
-                if (cnt + total <= seg_cap) {
-                    int pos = cnt + incl - c;
-                    bool head = true;
-                    for (uint32_t rem = mask; rem; rem &= rem - 1) {
-                        seg[pos++] = ent_make(s, __ffs(rem) - 1, head, queued, c);
-                        head = false;
-                    }
-                    cnt += total;
-                } else if (mask) {                                             // segment full: handle in place
-                    const float u = k3_process_inplace(&kc, sm, r, m, mask, s, queued);
-                    if (u > -INFINITY) t2k.add(make_key(u, s));
-                }
-            }
-        }
-        __syncwarp();
-        if (a.dbg && tid == 0) t2c = clock64();
-
-        // Every survivor is scanned by the same thread in every round (s = tid + k * kK3Threads), so a warp's
-        // segment only ever lists survivors whose state this warp owns: passes B1 / B2 run per warp on the
-        // warp's own segment and need no block barrier.
-        // ---- pass B1: one listed pair per lane: soft-NMS weight + membership bit ----
         float* wseg = wl + warp * kSegCap;
-        for (int e = lane; e < cnt; e += 32) {
-            const uint32_t ent = seg[e];
-            const int s = ent_s(ent), q = ent_q(ent);
-            const float4 bs = corn[s], bx = sm.sel_box[r + q];
-            wseg[e] = ent_queued(ent) ? nms_weight_fast(tf_iou(bs, bx), C.scale, C.is_soft, C.thr, sm.exp_tab) : 1.0f;
-            if (is_member(bs, bx, C.thr)) atomicOr(&C.member[(size_t)(r + q) * C.words + (s >> 5)], 1u << (s & 31));
-        }
-        __syncwarp();
-        // ---- pass B2: one listed candidate per lane (its first pair): the epoch walk ----
-        for (int e = lane; e < cnt; e += 32) {
-            const uint32_t ent = seg[e];
-            if (ent_head(ent) && ent_queued(ent)) {
-                const int s = ent_s(ent), c = ent_pairs(ent);
-                K3Walk wk;
-                wk.begin(C, s);
-                for (int j = 0; j < c; ++j) wk.step(C, sm, r, s, ent_q(seg[e + j]), wseg[e + j]);
-                const float u = wk.finish(C, sm, r, m, s);
-                if (u > -INFINITY) t2k.add(make_key(u, s));
+        uint16_t* hseg = hl + warp * kSegCap;
+        const int seg_cap = (a.seg_cap >= 32 && a.seg_cap < kSegCap) ? a.seg_cap : kSegCap;   // tests shrink it
+        for (int k0 = 0; k0 < nrows; k0 += kCH) {
+            // ---- pass A: the thread's queued candidates of this block against the batch centres.
+            // No positive intersection => TF's IoU is 0 and the weight exactly 1: the centre does nothing to the
+            // candidate.  The test here only has to be a superset of "positive intersection" (pass B decides
+            // exactly), so it compares against the centre grown by 2 px: four compares per pair.
+            K3_T(a0);
+            float4 bx[kCH];
+            float uq[kCH];
+            uint32_t mk[kCH];
+#pragma unroll
+            for (int j = 0; j < kCH; ++j) {
+                const int k = k0 + j;
+                const int s = k * NT + lane * W + warp;
+                uq[j] = -INFINITY; mk[j] = 0u;
+                bx[j] = make_float4(NAN, NAN, NAN, NAN);                       // compares false against everything
+                if (k < nrows && s < S) {
+                    const int si = big ? s : k * NT + tid;
+                    uq[j] = ucur[si];
+                    if (uq[j] > -INFINITY) bx[j] = corn[si];
+                }
             }
+            for (int q = 0; q < m; ++q) {
+                const float4 e = sm.batch_ebox[q];
+#pragma unroll
+                for (int j = 0; j < kCH; ++j) {
+                    const bool hit = (bx[j].z > e.x) & (bx[j].x < e.z) & (bx[j].w > e.y) & (bx[j].y < e.w);
+                    mk[j] |= (uint32_t)hit << q;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kCH; ++j) {
+                if (uq[j] > -INFINITY) {
+                    if (all_maybe) mk[j] = full;
+                    const unsigned long long key = make_key(fabsf(uq[j]), (k0 + j) * NT + lane * W + warp);
+                    if (__float_as_int(uq[j]) >= 0) {                          // an exact score
+                        if (mk[j] == 0u) t2k.add(key);
+                    } else if (key >= tau) mk[j] |= wake;                      // a bound the threshold has come down to
+                    else if (mk[j] == 0u) ixmax = key > ixmax ? key : ixmax;
+                }
+            }
+            K3_T(a1);
+            K3_ACC(6, a1, a0);
+
+            // ---- pass B on the pairs with a centre in `qm` and a row in [jlo, jhi): list them in the warp's
+            // segment (pairs of a candidate adjacent, ascending centre), B1: one pair per lane: IoU + exp;
+            // B2: one listed candidate per lane: the epoch walk over its weights.  Returns false (nothing done)
+            // when the pairs do not fit the segment.
+            auto pass_b = [&](const uint32_t qm, const int jlo, const int jhi, const bool add_keys) -> bool {
+                int pc = 0, cc = 0;
+#pragma unroll
+                for (int j = 0; j < kCH; ++j) {
+                    const uint32_t mm = (j >= jlo && j < jhi) ? (mk[j] & qm) : 0u;
+                    pc += __popc(mm); cc += (mm != 0u);
+                }
+                int incl = (pc << 16) | cc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                const int npairs = tot >> 16, ncand = tot & 0xffff;
+                if (npairs == 0) return true;
+                if (npairs > seg_cap) return false;
+                {
+                    int pos = (incl >> 16) - pc, hpos = (incl & 0xffff) - cc;
+#pragma unroll
+                    for (int j = 0; j < kCH; ++j) {
+                        const uint32_t mm = (j >= jlo && j < jhi) ? (mk[j] & qm) : 0u;
+                        if (mm != 0u) {
+                            hseg[hpos++] = (uint16_t)pos;
+                            const int c = __popc(mm);
+                            bool head = true;
+                            for (uint32_t rem = mm; rem; rem &= rem - 1) { seg[pos++] = ent_make(j, lane, __ffs(rem) - 1, head, c); head = false; }
+                        }
+                    }
+                }
+                __syncwarp();
+                for (int e = lane; e < npairs; e += 32) {                      // B1
+                    const uint32_t ent = seg[e];
+                    const int k = k0 + ent_row(ent), ln = ent_lane(ent);
+                    const int si = big ? (k * NT + ln * W + warp) : (k * NT + warp * 32 + ln);
+                    const int q = ent_q(ent);
+                    wseg[e] = (q < m) ? nms_weight_fast(tf_iou(corn[si], sm.sel_box[r + q]), C.scale, C.is_soft, C.thr, sm.exp_tab)
+                                      : 1.0f;                                  // the pseudo-centre of a woken candidate
+                }
+                __syncwarp();
+                const int qlast = 31 - __clz(qm & full);                       // pieces always hold a real centre
+                for (int h = lane; h < ncand; h += 32) {                       // B2
+                    const int e = hseg[h];
+                    const uint32_t ent = seg[e];
+                    const int k = k0 + ent_row(ent), ln = ent_lane(ent);
+                    const int s = k * NT + ln * W + warp;
+                    const int si = big ? s : (k * NT + warp * 32 + ln);
+                    const float u = k3_walk(C, sm.sel_key + r, qlast, tau, si, s, seg + e, wseg + e, ent_pairs(ent));
+                    if (add_keys && u > -INFINITY) {
+                        const unsigned long long key = make_key(fabsf(u), s);
+                        if (__float_as_int(u) >= 0) t2k.add(key); else ixmax = key > ixmax ? key : ixmax;
+                    }
+                }
+                __syncwarp();
+#ifdef BOD_DIAGNOSTICS
+                if (lane == 0) { dbg_acc[8] += ncand; dbg_acc[9] += npairs; }
+#endif
+                return true;
+            };
+            // The whole block at once; when its pairs overflow the segment (rare): a batch may be applied in pieces
+            // -- rounds are only a grouping of consecutive selections -- so centre by centre, and row by row where
+            // one centre alone overflows (<= 32 pairs then); the owners pick the final scores up afterwards.
+            // (One call site: the round loop has to stay small enough for the instruction cache.)
+            {
+                uint32_t qm = full | wake;
+                int q = -1, jlo = 0, jhi = kCH;
+                bool add = true;
+#pragma unroll 1
+                for (;;) {
+                    if (pass_b(qm, jlo, jhi, add)) {
+                        if (q < 0) break;
+                        if (jhi < kCH) { jlo = jhi; jhi = jlo + 1; }           // next row of this centre
+                        else { ++q; jlo = 0; jhi = kCH; if (q >= m) break; qm = 1u << q; }
+                    } else {
+                        add = false;
+                        if (q < 0) { q = 0; qm = 1u; }                         // centre by centre
+                        else { jlo = 0; jhi = 1; }                             // this centre row by row
+                    }
+                }
+                if (!add) {
+#pragma unroll
+                    for (int j = 0; j < kCH; ++j) {
+                        if (mk[j] != 0u) {
+                            const int k = k0 + j;
+                            const int s = k * NT + lane * W + warp;
+                            const float u = ucur[big ? s : k * NT + tid];
+                            if (u > -INFINITY) {
+                                const unsigned long long key = make_key(fabsf(u), s);
+                                if (__float_as_int(u) >= 0) t2k.add(key); else ixmax = key > ixmax ? key : ixmax;
+                            }
+                        }
+                    }
+                }
+            }
+            K3_T(a2);
+            K3_ACC(7, a2, a1);
         }
-        __syncwarp();
-        if (a.dbg && tid == 0) { t3 = clock64(); tC += t1 - tx2; tM += tm - t0; tW += tw - tm; tR += tx1 - tw; tP += tx2 - tx1; tA += t2c - t1; tB += t3 - t2c; tL += cnt; }
         r += m;
-        ++rounds;
-        // no barrier here: the warp lists of the next round go to sm.top_w, which warp 0 finished reading
-        // before the batch barrier; seg_n / list / wl are next written after the top-of-round barrier
+        ++rnd;
+#ifdef BOD_DIAGNOSTICS
+        dbg_acc[10] += 1;
+#endif
+        // no barrier here: the warp lists of the next round go to sm.top_flat, which the team finished
+        // reading before the batch barrier; the segments are warp-private
     }
-    if (a.dbg && tid == 0) {
-        a.dbg[b * 8 + 0] = tA; a.dbg[b * 8 + 1] = tB; a.dbg[b * 8 + 2] = tR; a.dbg[b * 8 + 3] = rounds; a.dbg[b * 8 + 4] = tP; (void)tL;
-        a.dbg[b * 8 + 5] = tC; a.dbg[b * 8 + 6] = tM; a.dbg[b * 8 + 7] = tW;
+#ifdef BOD_DIAGNOSTICS
+    if (a.dbg) {
+        dbg_acc[11] = psm;
+        if (b == 0 && tid == 0) for (int i = 0; i < 8; ++i) a.dbg[(size_t)gridDim.x * 384 + i] = (long long)g_k3_cnt[i];
+        if (lane == 0) for (int i = 0; i < 12; ++i) a.dbg[((size_t)b * 32 + warp) * 12 + i] = dbg_acc[i];
     }
+#endif
     if (tid == 0) a.num_dets[b] = r;
     __syncthreads();                                         // sel_key of the last round
-    for (int d = tid; d < r; d += kK3Threads)               // off the rounds' critical path: one gather at the end
+    for (int d = tid; d < r; d += NT)                       // off the rounds' critical path: one gather at the end
         a.centre_anchor[(size_t)b * Dmax + d] = a.surv_anchor[(size_t)b * a.capacity + key_index(sm.sel_key[d])];
-    for (int d = r + tid; d < Dmax; d += kK3Threads) {       // padding rows
+    for (int d = r + tid; d < Dmax; d += NT) {               // padding rows
         a.nms_idx[(size_t)b * Dmax + d] = -1;
         a.centre_anchor[(size_t)b * Dmax + d] = -1;
         a.nms_score[(size_t)b * Dmax + d] = 0.0f;
     }
 }
 
-int k3_fast_capacity(int capacity) {
-    int s = capacity < kFastS ? capacity : kFastS;
-    return (s + 31) & ~31;
-}
-
 static bool g_exp_tab_ready[64] = {false};
+
+template <int NT>
+static cudaError_t launch_k3_nt(const K3Args& a, cudaStream_t st) {
+    // dynamic shared memory: candidate lists + the per-candidate pool (corners, scores, pending weights);
+    // as much as one CTA can have next to the static part, so small images keep long pending lists on chip
+    const size_t lists = (size_t)kPairsCta * 10;
+    const size_t most = (227 * 1024 - sizeof(K3Smem) - 1024 - lists) & ~(size_t)15;
+    const size_t smem = lists + most;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k3_softnms_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    k3_softnms_kernel<NT><<<a.B, NT, smem, st>>>(a, (int)most);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_k3(const K3Args& a, cudaStream_t st) {
     int dev = 0;
@@ -701,18 +859,11 @@ cudaError_t launch_k3(const K3Args& a, cudaStream_t st) {
         if (e0 != cudaSuccess) return e0;
         g_exp_tab_ready[dev] = true;
     }
-    const int smem_S = a.fastS;
-    // dynamic shared memory: pair lists + the per-candidate pool (corners, scores, pending weights);
-    // as much as one CTA can have next to the static part, so small images keep long pending lists on chip
-    const size_t lists = (size_t)kK3Warps * kSegCap * 8;
-    const size_t most = (227 * 1024 - sizeof(K3Smem) - 1024 - lists) & ~(size_t)15;
-    static_assert((size_t)kFastS * 25 <= 227 * 1024 - sizeof(K3Smem) - 1024 - (size_t)kK3Warps * kSegCap * 8 - 16,
-                  "kFastS candidates must fit the shared-memory pool");
-    const size_t smem = lists + most;
-    cudaError_t e = cudaFuncSetAttribute(k3_softnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k3_softnms_kernel<<<a.B, kK3Threads, smem, st>>>(a, smem_S, (int)most);
-    return cudaGetLastError();
+    switch (a.threads) {
+        case 256: return launch_k3_nt<256>(a, st);
+        case 1024: return launch_k3_nt<1024>(a, st);
+        default: return launch_k3_nt<512>(a, st);
+    }
 }
 
 }  // namespace bod

@@ -1,7 +1,9 @@
-// k4_fusion.cu — stage K4: per-cluster Bayesian fusion.  Compiled with -fmad=false.
+// k4_fusion.cu — stage K4: cluster membership + per-cluster Bayesian fusion.  Compiled with -fmad=false.
 //
-// Reference lines replaced: bayes_od_clustering, inference_utils.py:285-364
-//   :316       members = affinity[:, centre] > threshold          (bitmask row from K3)
+// Reference lines replaced: inference_utils.py:214-215 (box_utils.bbox_iou_vuvu(corners, corners), [S,S]:
+// only the D centre columns are ever read, :316, so only those are evaluated, as bits) and
+// bayes_od_clustering, inference_utils.py:285-364
+//   :316       members = affinity[:, centre] > threshold          (one bitmask row per centre)
 //   :321-324   P_i = inv(Sigma_i);  Sigma_f = inv(sum_i P_i)       (information form)
 //   :327-331   mu_f = Sigma_f * sum_i P_i mu_i
 //   :334-349   normalised member scores; more than 3 members: keep the 3 with the
@@ -10,7 +12,10 @@
 //   :351-352   cat_param = mean of the kept scores, cat_count = sum of the kept counts
 //   :361       Sigma_f * 70
 //
-// One warp per (image, centre).  The member bits of a cluster are scattered over
+// One warp per (image, centre).  The warp first tests every survivor of the image against its centre
+// (32 survivors per step: one coalesced 512-byte read of corners, the ballot is the row's next word; the
+// exact IoU with its division only runs for boxes that can overlap at all) and writes the bitmask row
+// consumers fetch (bod_fetch_members).  The member bits of a cluster are scattered over
 // the survivor index space, so they are first compacted into an ascending index
 // list; then 32 members at a time are handled densely: lanes invert the members'
 // covariances in parallel, while the sums over members stay sequential in
@@ -62,7 +67,7 @@ k4_fusion_kernel(K4Args a) {
     }
     const int S = a.num_survivors[b];
     const int nwords = (S + 31) >> 5;
-    const uint32_t* row = a.member + ((size_t)b * a.Dmax + d) * a.words;
+    uint32_t* row = a.member + ((size_t)b * a.Dmax + d) * a.words;
     const float* cnt = a.cnt_post + (size_t)b * a.capacity * K;
     const float4* mu = reinterpret_cast<const float4*>(a.mu_post) + (size_t)b * a.capacity;
     const float4* sig = reinterpret_cast<const float4*>(a.sig_post) + (size_t)b * a.capacity * 4;
@@ -70,11 +75,36 @@ k4_fusion_kernel(K4Args a) {
     float (*st)[21] = stage[warp];
     uint32_t* ml = mlist[warp];
 
-    // cluster size first (the KL ranking is only needed for more than 3 members, :338)
+    // membership row of this centre (:214-215, :316) and the cluster size (the KL ranking is only needed
+    // for more than 3 members, :338)
     int m = 0;
-    for (int w = lane; w < nwords; w += 32) m += __popc(row[w]);
+    if (a.corners) {
+        const float4* corn = a.corners + (size_t)b * a.capacity;
+        const float4 bx = corn[centre];
+        const float thr = a.iou_threshold;
+        for (int w0 = 0; w0 < nwords; w0 += 4) {             // four words per step: the reads are in flight together
+            float4 bs[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+            for (int i = 0; i < 4; ++i) {
+                const int s = ((w0 + i) << 5) + lane;
+                bs[i] = (s < S) ? corn[s] : make_float4(NAN, NAN, NAN, NAN);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int s = ((w0 + i) << 5) + lane;
+                const unsigned bal = __ballot_sync(0xffffffffu, s < S && is_member(bs[i], bx, thr));
+                if (w0 + i < nwords) {
+                    if (lane == 0) row[w0 + i] = bal;
+                    m += __popc(bal);
+                }
+            }
+        }
+        __syncwarp();                                        // the row is re-read below by the other lanes
+    } else {
+        for (int w = lane; w < nwords; w += 32) m += __popc(row[w]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    }
     const bool need_kl = m > 3;
 
     // centre's raw counts and its normalised, re-normalised score (:339-340 and scipy's pk / sum(pk))

@@ -1,8 +1,10 @@
+"""Per-stage CUDA-event times of one serial context on the bench scene (K1 / scan / K2 / soft-NMS / K4).
+Env: DIAG_K (classes), DIAG_B (images), DIAG_RANK, BOD_K3_THREADS (256 / 512 / 1024)."""
 import os, sys, json, ctypes as C, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bayes_od_rc_b200 import synthetic, _cabi
 from bayes_od_rc_b200.engine import BayesODConfig, BayesODEngine
-K=int(os.environ.get('DIAG_K','11')); B=32
+K=int(os.environ.get('DIAG_K','11')); B=int(os.environ.get('DIAG_B','32'))
 spec=synthetic.SceneSpec(N=10,K=K,config_id=3)
 batch=synthetic.make_batch(spec,B,device='cuda',with_counts=False)
 A=batch['anchors'].shape[0]
@@ -11,16 +13,19 @@ eng=BayesODEngine(B,10,A,K,cfg)
 for i in range(5): eng.run(batch['cls'],batch['box'],batch['cov'],batch['anchors'],None)
 eng.stage_ms_accum()
 for i in range(20): eng.run(batch['cls'],batch['box'],batch['cov'],batch['anchors'],None)
-s,n=eng.stage_ms_accum(); print('K',K,'k1dbg',os.environ.get('BOD_K1_DEBUG'),{k:round(v/n,4) for k,v in s.items()})
-if os.environ.get('BOD_K3_DEBUG'):
-    out=(C.c_longlong*(B*8))()
+s,n=eng.stage_ms_accum(); print('K',K,'B',B,'k3 threads',os.environ.get('BOD_K3_THREADS','512'),{k:round(v/n,4) for k,v in s.items()})
+if os.environ.get('BOD_K3_DEBUG'):     # needs a library built with -DBOD_DIAGNOSTICS (k3_softnms.cu, bod_api.cu)
+    out=(C.c_longlong*(B*384+8))()
     lib=_cabi.load(); lib.bod_debug_k3_counters.argtypes=[C.c_void_p,C.c_void_p]
     print('rc',lib.bod_debug_k3_counters(eng._ctx,out))
-    a=np.array(out[:]).reshape(B,8)
-    r=a[:,3]
-    names=['pass A','pass B','rank','rounds','pairwise','walk+writes','warp merge','wait at barrier']
-    print('rounds',a[:8,3])
-    tot=sum(a[:,i] for i in (0,1,2,4,5,6,7))
-    for i in (6,7,2,4,5,0,1):
-        print('%-16s per round %s share %.2f' % (names[i], (a[:,i]/r).round(0)[:8], a[:,i].sum()/tot.sum()))
-    print('total cycles per image (max)', tot.max(), 'mean', tot.mean())
+    cnt=np.array(out[B*384:]); a=np.array(out[:B*384]).reshape(B,32,12)
+    print('walk counters (cumulative over all launches: walks, bounded, untouched, products, product entries, folds, woken):', cnt)
+    nw=int(os.environ.get('BOD_K3_THREADS','512'))//32
+    a=a[:,:nw]
+    names=['merge','wait barrier 1','rank','pairwise','walk','wait barrier 2','pass A','pass B','listed','spilled weights','rounds','psm']
+    rounds=a[:,0,10]
+    print('rounds',rounds[:8],'psm',a[:8,0,11])
+    print('listed candidates per image',a[:,:,8].sum(1)[:8],'spilled weights read',a[:,:,9].sum(1)[:8])
+    for i in range(8):
+        print('%-16s warp 0 per round %s | mean over warps %s | max over warps %s' % (names[i], (a[:8,0,i]/rounds[:8]).round(0), (a[:8,:,i].mean(1)/rounds[:8]).round(0), (a[:8,:,i].max(1)/rounds[:8]).round(0)))
+    print('total cycles warp 0 (mean over images)', a[:,0,:8].sum(1).mean())

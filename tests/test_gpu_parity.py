@@ -83,12 +83,14 @@ def test_synthetic_batch_bit_exact(name):
         compare_image_with_oracle(eng, res, b, r, spec.K)
 
 
-@pytest.mark.parametrize("env", [dict(BOD_K3_SEGCAP="8"), dict(BOD_K3_SEGCAP="0"), dict(BOD_K3_PSM_MAX="0"),
-                                 dict(BOD_K3_PSM_MAX="2", BOD_K3_SEGCAP="40")])
+@pytest.mark.parametrize("env", [dict(BOD_K3_PSM_MAX="0"), dict(BOD_K3_PSM_MAX="4"), dict(BOD_K3_THREADS="256"),
+                                 dict(BOD_K3_THREADS="1024"), dict(BOD_K3_THREADS="256", BOD_K3_PSM_MAX="0"),
+                                 dict(BOD_K3_SEGCAP="32"), dict(BOD_K3_SEGCAP="48", BOD_K3_PSM_MAX="0", BOD_K3_THREADS="1024")])
 @pytest.mark.parametrize("name", ["bdd_covar_k8", "dense_cluster", "dense_cluster_sigma", "hard_nms"])
-def test_softnms_overflow_paths(name, env, monkeypatch):
-    """The soft-NMS kernel's rarely taken paths on small inputs: pair-list segments that overflow (candidates
-    handled in place) and pending weights that spill from shared memory to the global rows."""
+def test_softnms_variants(name, env, monkeypatch):
+    """The soft-NMS kernel's other shapes on small inputs: pending weights that spill from shared memory to
+    the global rows, the 256- / 1024-thread CTAs (other candidate-to-warp maps, other per-warp list lengths), and
+    pair lists that overflow the warp's segment (a batch applied centre by centre / row by row)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     test_synthetic_batch_bit_exact(name)
