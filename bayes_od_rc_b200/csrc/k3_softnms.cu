@@ -190,7 +190,7 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
 // ---------------------------------------------------------------------------
 constexpr int kTop = 16;              // candidates examined per round
 constexpr int kBatch = 15;            // centres selected per round at most (pair entries name them in 4 bits; 15 = "no centre")
-constexpr int kTauRank = 31;          // rank (among the listed keys) of the key below which scores are kept as upper bounds
+constexpr float kTauFrac = 0.97f;     // scores below this fraction of the lowest examined score are kept as upper bounds
 constexpr int kListed = 64;           // keys listed per round by all warps together
 constexpr int kExpTab = 129;
 constexpr int kTeamWarps = 4;         // warps that share a round's acceptance work
@@ -437,20 +437,18 @@ BOD_DEVINL void warp_top_merge2(Top2 t, unsigned long long (&out)[kTop1], unsign
 #define K3_ACC(slot, t1, t0)
 #endif
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 1)
-k3_softnms_kernel(K3Args a, int pool_bytes) {
+// The rounds of one image.  BIG: per-candidate state in the workspace's global rows (more survivors than the
+// shared-memory pool holds); otherwise every state pointer is derived from the dynamic shared array, so the
+// compiler emits LDS / STS instead of generic accesses.
+template <int NT, bool BIG>
+BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, const int S) {
     constexpr int W = NT / 32;                              // warps
     constexpr int kTop1 = kListed / W;                      // keys every warp lists per round
     constexpr int kSegCap = kPairsCta / W;                  // pairs per warp segment
     constexpr int kCH = NT >= 1024 ? 4 : 8;                 // candidates per thread handled per pass-A/B block (registers)
     static_assert(W >= kTeamWarps && kTop1 >= 2 && kTop1 * W == kListed && kSegCap >= 32, "CTA size");
     extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ K3Smem sm;
-
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = a.num_survivors[b];
-    if (S > a.max_rows) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
 
     // Candidate rows: thread `tid` owns survivor s = k*NT + lane*W + warp of row k; its state row (shared
     // memory) is si = k*NT + tid.  More survivors than the pool holds: state in the workspace's global
@@ -460,7 +458,7 @@ k3_softnms_kernel(K3Args a, int pool_bytes) {
     uint32_t* list = reinterpret_cast<uint32_t*>(dyn);                    // [W][kSegCap] pair entries (ent_make)
     float* wl = reinterpret_cast<float*>(list + kPairsCta);               // [W][kSegCap] their soft-NMS weights
     uint16_t* hl = reinterpret_cast<uint16_t*>(wl + kPairsCta);           // [W][kSegCap] first pair of every listed candidate
-    const bool big = (long long)SP * 25 > (long long)pool_bytes || a.force_big != 0;
+    constexpr bool big = BIG;
     float4* corn = reinterpret_cast<float4*>(hl + kPairsCta);             // [SP] corners
     float* ucur = reinterpret_cast<float*>(corn + SP);                    // [SP] up-to-date score, -inf = not queued
     float* stl = ucur + SP;                                               // [SP] score as of the last fold
@@ -471,7 +469,7 @@ k3_softnms_kernel(K3Args a, int pool_bytes) {
     psm &= ~3;                                                            // rows are read four weights at a time
     float* pws = stl + SP;                                                // [SP][psm]
     uint8_t* npend = reinterpret_cast<uint8_t*>(pws + (size_t)psm * SP);  // [SP] pending entries per candidate
-    if (big) {
+    if constexpr (BIG) {
         corn = const_cast<float4*>(a.corners + (size_t)b * a.capacity);   // read in place, never written
         ucur = a.cur + (size_t)b * a.capacity;
         stl = a.stale + (size_t)b * a.capacity;
@@ -544,7 +542,7 @@ k3_softnms_kernel(K3Args a, int pool_bytes) {
             if (lane == 0) sm.bound_w[warp] = bound > ixw ? bound : ixw;
         }
         if (tid < kTop) { sm.cand_key[tid] = 0ull; sm.rowmask[tid] = 0u; }     // filled by the acceptance team below
-        if (tid == 0) sm.tau[rnd & 1] = 0ull;                                  // fewer than kTauRank+1 listed keys: every score exact
+        if (tid == 0) sm.tau[rnd & 1] = 0ull;
         K3_T(c1);
         __syncthreads();
         K3_T(c2);
@@ -567,7 +565,6 @@ k3_softnms_kernel(K3Args a, int pool_bytes) {
                         rank += (int)(kk.x > key) + (int)(kk.y > key);
                     }
                     if (rank < kTop) { sm.cand_key[rank] = key; sm.cand_box[rank] = corn[row_of(key_index(key))]; }
-                    if (rank == kTauRank) sm.tau[rnd & 1] = key;
                 }
             }
             team_barrier();
@@ -638,6 +635,8 @@ k3_softnms_kernel(K3Args a, int pool_bytes) {
             // nothing examinable although keys exist (every listed key is below some candidate's upper bound):
             // a refresh round (-1) makes all bounds exact
             if (lane == 0) {
+                // laziness threshold of the round's passes: a fixed fraction below the lowest examined score
+                if (nvalid > 0) sm.tau[rnd & 1] = make_key(key_score(sm.cand_key[nvalid - 1]) * kTauFrac, 0x7fffffff);
                 unsigned long long G = 0ull;
                 for (int w = 0; w < W; ++w) G = sm.bound_w[w] > G ? sm.bound_w[w] : G;
                 sm.batch_n = (m == 0 && G != 0ull) ? -1 : m;
@@ -826,6 +825,18 @@ k3_softnms_kernel(K3Args a, int pool_bytes) {
         a.centre_anchor[(size_t)b * Dmax + d] = -1;
         a.nms_score[(size_t)b * Dmax + d] = 0.0f;
     }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
+k3_softnms_kernel(K3Args a, int pool_bytes) {
+    __shared__ K3Smem sm;
+    const int b = blockIdx.x;
+    const int S = a.num_survivors[b];
+    if (S > a.max_rows) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
+    const long long SP = (long long)((S + NT - 1) / NT) * NT;
+    if (SP * 25 > (long long)pool_bytes || a.force_big != 0) k3_rounds<NT, true>(a, pool_bytes, sm, S);
+    else k3_rounds<NT, false>(a, pool_bytes, sm, S);
 }
 
 static bool g_exp_tab_ready[64] = {false};
