@@ -35,6 +35,21 @@ struct Lane {
     cudaEvent_t head_done = nullptr, tail_done = nullptr;
     cudaStream_t tail_stream = nullptr;   // the lane's own tail stream: tails of different lanes run concurrently
     bool tail_pending = false;        // a tail has been issued on this lane (tail_done is meaningful)
+    // CUDA-graph replay of a whole run on this lane (pipelined contexts; see issue_run)
+    cudaGraph_t graph[2] = {nullptr, nullptr}; cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // head, tail
+    cudaGraphNode_t gk1 = nullptr, gk2 = nullptr;     // the moments / posterior kernel nodes (their inputs change per run)
+    K1Args ga1{}; K2Args ga2{};                       // what those nodes currently point at
+    int uses = 0;                                     // runs issued on this lane (the first one goes through the streams: lazy one-time setup)
+    cudaEvent_t k1_begin = nullptr, k1_end = nullptr; // timing of the lane's last replayed moments kernel
+    bool k1_timed = false;
+};
+
+// what run_range does differently while a lane's graphs are being captured: only one half of the run is
+// issued (1: the head -- ticket reset, moments kernel, scan; 2: the tail -- posterior, soft-NMS, fusion)
+struct GraphHooks {
+    int phase;
+    cudaEvent_t k1_begin, k1_end;     // timing of the moments kernel (event nodes in the head graph)
+    K1Args* k1_out; K2Args* k2_out;   // the arguments the captured moments / posterior kernels were given
 };
 
 struct bod_ctx {
@@ -46,7 +61,7 @@ struct bod_ctx {
     // one slab of device memory, carved up below
     unsigned char* slab = nullptr;
     size_t slab_bytes = 0;
-    static constexpr int kMaxLanes = 8;
+    static constexpr int kMaxLanes = 16;
     Lane lane[kMaxLanes];
     int nlanes = 1, cur = 0;          // cur: lane of the last issued run
     int32_t* status = nullptr;
@@ -55,8 +70,7 @@ struct bod_ctx {
     unsigned long long* pf_key = nullptr; unsigned long long* pf_thr = nullptr;
     int32_t* pf_anchor = nullptr; float* pf_counts = nullptr; int32_t* pf_tile_count = nullptr;
     bool prefilter = false;
-    uint32_t* ticket = nullptr;       // K1's dynamic tile scheduler: monotonically increasing ticket counter
-    uint32_t ticket_next = 0;         // its value once every launch issued so far has finished
+    uint32_t* ticket = nullptr;       // K1's dynamic tile scheduler: ticket counter, zeroed before every launch
     float* probs = nullptr; float* sampled = nullptr;
     int pstride = 0, pw_rows = 0, k3_rows = 0, k3_threads = 512, k3_force_big = 0;
     // device staging of host inputs (bod_run_host), allocated on first use
@@ -82,6 +96,8 @@ struct bod_ctx {
     long long* k3_dbg = nullptr;      // BOD_K3_DEBUG (diagnostic builds only): [B][32][12] cycle counters
 #endif
     bool k2_on_tail = true;           // pipelined contexts: K2 rides with the tail (see run_range); BOD_K2_TAIL=0 keeps it on the head
+    bool use_graphs = true;           // pipelined contexts replay each lane's run as a CUDA graph (BOD_GRAPHS=0: stream launches)
+    double g_k1_ms = 0.0; long long g_k1_runs = 0;    // moments-kernel time of replayed runs (harvested when a lane is reused)
     int k3_psm_max = -1, k3_seg_cap = -1;   // BOD_K3_PSM_MAX / BOD_K3_SEGCAP (tests: reach the spill rows / the piecewise pass B on small inputs)
 };
 
@@ -263,6 +279,8 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
 #endif
     c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
     if (const char* d = getenv("BOD_K2_TAIL")) c->k2_on_tail = atoi(d) != 0;
+    if (const char* d = getenv("BOD_GRAPHS")) c->use_graphs = atoi(d) != 0;
+    for (int l = 0; l < c->nlanes; ++l) { cudaEventCreate(&c->lane[l].k1_begin); cudaEventCreate(&c->lane[l].k1_end); }
     if (const char* d = getenv("BOD_K3_PSM_MAX")) c->k3_psm_max = atoi(d);
     if (const char* d = getenv("BOD_K3_SEGCAP")) c->k3_seg_cap = atoi(d);
     e = cudaDeviceSynchronize();
@@ -281,7 +299,16 @@ extern "C" void bod_destroy(bod_ctx* c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto& L : c->lane) if (L.tail_stream) cudaStreamDestroy(L.tail_stream);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
-    for (auto& L : c->lane) { if (L.head_done) cudaEventDestroy(L.head_done); if (L.tail_done) cudaEventDestroy(L.tail_done); }
+    for (auto& L : c->lane) {
+        if (L.head_done) cudaEventDestroy(L.head_done);
+        if (L.tail_done) cudaEventDestroy(L.tail_done);
+        if (L.k1_begin) cudaEventDestroy(L.k1_begin);
+        if (L.k1_end) cudaEventDestroy(L.k1_end);
+        for (int i = 0; i < 2; ++i) {
+            if (L.gexec[i]) cudaGraphExecDestroy(L.gexec[i]);
+            if (L.graph[i]) cudaGraphDestroy(L.graph[i]);
+        }
+    }
     for (auto& set : c->evring) for (auto& ev : set) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
     delete c;
@@ -309,7 +336,8 @@ static LevelTable levels_split(const bod_ctx* c, const float* const* cls, const 
 }
 
 static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
-                     const float* anchors, const float* counts, cudaStream_t hs, cudaStream_t ts, bool record) {
+                     const float* anchors, const float* counts, cudaStream_t hs, cudaStream_t ts, bool record,
+                     const GraphHooks* gh = nullptr) {
     const bod_config& g = c->cfg;
     const size_t A = g.A, K = g.K, cap = c->capacity, D = c->Dmax;
     const size_t slots = (size_t)c->tiles * kTileAnchors;
@@ -323,6 +351,10 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     // that tail is done -- also when K2 stays on the head stream (pre-NMS filter), where the scans would otherwise
     // rewrite num_survivors under a running tail.
     if (hs != ts && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
+    const bool do_head = !gh || gh->phase == 1, do_tail = !gh || gh->phase == 2;   // graph capture: one half at a time
+    // the moments kernel's tile scheduler counts tickets from zero (its launches never overlap within a context)
+    if (do_head) CU(c, cudaMemsetAsync(c->ticket, 0, sizeof(uint32_t), hs));
+    if (gh && do_head) CU(c, cudaEventRecordWithFlags(gh->k1_begin, hs, cudaEventRecordExternal));
     if (record) CU(c, cudaEventRecord(c->ev[0], hs));
     K1Args k1{};
     k1.lv = lv; k1.counts_in = counts;
@@ -335,10 +367,10 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
 #ifdef BOD_DIAGNOSTICS
     k1.debug = c->k1_debug;
 #endif
-    k1.leave_room = (hs != ts) ? 1 : 0;
-    k1.ticket = c->ticket; k1.ticket_base = c->ticket_next;
-    c->ticket_next += k1_tickets_per_launch(k1);           // K1 launches of a context never overlap each other
-    CU(c, launch_k1(k1, hs));
+    k1.leave_room = (hs != ts || gh) ? 1 : 0;
+    k1.ticket = c->ticket; k1.ticket_base = 0u;
+    if (do_head) CU(c, launch_k1(k1, hs));
+    if (gh && do_head) { CU(c, cudaEventRecordWithFlags(gh->k1_end, hs, cudaEventRecordExternal)); *gh->k1_out = k1; }
     if (record) CU(c, cudaEventRecord(c->ev[1], hs));
 
     int launches = 3;
@@ -348,7 +380,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     sc.tile_count = k1.tile_count; sc.tile_off = L.tile_off + (size_t)b0 * (c->tiles + 1);
     sc.num_survivors = L.num_survivors + b0; sc.status = c->status;
     sc.B = nb; sc.tiles = c->tiles; sc.capacity = c->capacity;
-    if (c->prefilter) {
+    if (c->prefilter && do_head) {
         // scan (dense indexing of the slots) -> filter -> scan again on the new counts; the capacity check
         // belongs to the second scan only
         ScanArgs s0 = sc;
@@ -376,10 +408,11 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     // Long ones lose ~1 % that way (the soft-NMS CTAs then find no free SM at the kernel boundary), so they keep the scan.
     static const int scan_tail_env = getenv("BOD_SCAN_TAIL") ? atoi(getenv("BOD_SCAN_TAIL")) : -1;     // experiments
     const bool scan_tail = k2_tail && (scan_tail_env >= 0 ? scan_tail_env != 0 : 4.0 * nb * g.N * A * K < 0.8e9);
-    if (!scan_tail) {
+    if (!scan_tail && do_head) {
         CU(c, launch_scan(sc, hs));
         if (record) CU(c, cudaEventRecord(c->ev[2], hs));
     }
+    if (!do_tail) return BOD_OK;
     if (k2_tail) {
         CU(c, cudaEventRecord(L.head_done, hs));
         CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));
@@ -409,6 +442,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     if (!(c->skip_mask & 1))
 #endif
     CU(c, launch_k2(k2, k2s));
+    if (gh) *gh->k2_out = k2;
     if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, k2s)); ++launches; }
     if (record) CU(c, cudaEventRecord(c->ev[3], k2s));
     if (hs != ts && !k2_tail) {
@@ -468,12 +502,101 @@ static int check_inputs(bod_ctx* c, const float* cls, const float* box, const fl
     return BOD_OK;
 }
 
+// moments-kernel time of the lane's last replayed run (if it has finished), into the context's accumulators
+static void harvest_k1_time(bod_ctx* c, Lane& L) {
+    if (!L.k1_timed) return;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, L.k1_begin, L.k1_end) == cudaSuccess) { c->g_k1_ms += ms; ++c->g_k1_runs; }
+    else cudaGetLastError();
+    L.k1_timed = false;
+}
+
+// Capture (first replay of a lane) or re-point (input tensors changed) the lane's two graphs -- head: ticket
+// reset, moments kernel, scan; tail: posterior, soft-NMS, fusion -- and launch them on the lane's stream.  The
+// event that tells other streams "the head is done" is recorded between the two launches by an ordinary
+// cudaEventRecord, so its meaning for later cudaStreamWaitEvent calls is the usual one.
+static int capture_half(bod_ctx* c, Lane& L, int phase, const LevelTable& lv, const float* anchors, const float* counts) {
+    cudaStream_t ls = L.tail_stream;
+    GraphHooks gh{phase, L.k1_begin, L.k1_end, &L.ga1, &L.ga2};
+    CU(c, cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed));
+    int rc = run_range(c, L, 0, c->cfg.B, lv, anchors, counts, ls, ls, false, &gh);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ls, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(c, BOD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    L.graph[phase - 1] = g;
+    // the kernel node whose arguments follow the caller's tensors
+    size_t n = 0;
+    CU(c, cudaGraphGetNodes(g, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    CU(c, cudaGraphGetNodes(g, nodes.data(), &n));
+    const void* want = phase == 1 ? k1_kernel_func(L.ga1) : k2_kernel_func(L.ga2);
+    cudaGraphNode_t found = nullptr;
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType t;
+        CU(c, cudaGraphNodeGetType(nd, &t));
+        if (t != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams p;
+        CU(c, cudaGraphKernelNodeGetParams(nd, &p));
+        if (p.func == want) found = nd;
+    }
+    if (!found) return fail(c, BOD_ERR_CUDA, "graph capture: %s kernel node not found", phase == 1 ? "moments" : "posterior");
+    (phase == 1 ? L.gk1 : L.gk2) = found;
+    CU(c, cudaGraphInstantiate(&L.gexec[phase - 1], g, 0));
+    return BOD_OK;
+}
+
+static int replay_run(bod_ctx* c, Lane& L, const LevelTable& lv, const float* anchors, const float* counts) {
+    cudaStream_t ls = L.tail_stream;
+    if (L.gexec[0] && (L.ga1.counts_in == nullptr) != (counts == nullptr)) {   // sampler <-> injected counts: other outputs
+        for (int i = 0; i < 2; ++i) {
+            cudaGraphExecDestroy(L.gexec[i]); cudaGraphDestroy(L.graph[i]);
+            L.gexec[i] = nullptr; L.graph[i] = nullptr;
+        }
+    }
+    harvest_k1_time(c, L);
+    if (!L.gexec[0]) {
+        int rc = capture_half(c, L, 1, lv, anchors, counts);
+        if (!rc) rc = capture_half(c, L, 2, lv, anchors, counts);
+        if (rc) return rc;
+    } else {
+        K1Args a1 = L.ga1;
+        a1.lv = lv; a1.counts_in = counts;
+        if (memcmp(&a1, &L.ga1, sizeof a1) != 0) {
+            cudaError_t e = k1_graph_update(L.gexec[0], L.gk1, a1);
+            if (e != cudaSuccess) return fail(c, BOD_ERR_CUDA, "graph update (moments kernel): %s", cudaGetErrorString(e));
+            L.ga1 = a1;
+        }
+        K2Args a2 = L.ga2;
+        a2.lv = lv; a2.anchors = anchors;
+        if (!cov_width(c->cfg.cov_layout)) for (int l = 0; l < a2.lv.n; ++l) a2.lv.cov[l] = nullptr;
+        if (memcmp(&a2, &L.ga2, sizeof a2) != 0) {
+            cudaError_t e = k2_graph_update(L.gexec[1], L.gk2, a2);
+            if (e != cudaSuccess) return fail(c, BOD_ERR_CUDA, "graph update (posterior kernel): %s", cudaGetErrorString(e));
+            L.ga2 = a2;
+        }
+    }
+    // the caller's tensors are ready; the previous lane's moments kernel is done (they share the ticket counter)
+    const Lane& P = c->lane[(int)((&L - c->lane) + c->nlanes - 1) % c->nlanes];
+    CU(c, cudaStreamWaitEvent(ls, c->ev_in, 0));
+    CU(c, cudaStreamWaitEvent(ls, P.head_done, 0));
+    CU(c, cudaGraphLaunch(L.gexec[0], ls));
+    CU(c, cudaEventRecord(L.head_done, ls));
+    CU(c, cudaGraphLaunch(L.gexec[1], ls));
+    CU(c, cudaEventRecord(L.tail_done, ls));
+    L.tail_pending = true;
+    L.k1_timed = true;
+    c->launches = 6;            // ticket reset, moments, scan, posterior, soft-NMS, fusion
+    return BOD_OK;
+}
+
 // issue one whole run (serial on the caller's stream, or head / tail on the context's streams)
 static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, const float* counts, void* cuda_stream) {
     if (c->cfg.N < 2) return fail(c, BOD_ERR_INVALID, "bod_run needs N (mc_dropout_samples) >= 2: the sample covariance divides by N-1");
     CU(c, cudaSetDevice(c->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     int rc;
+    bool recorded = c->timing;        // stage events are recorded by the stream launches, not by graph replays
     c->launches = 0;
     c->ev = c->evring[c->runs_recorded % bod_ctx::kEvRing];
     if (c->nlanes == 1) {
@@ -488,14 +611,32 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
         c->cur = (c->cur + 1) % c->nlanes;
         Lane& L = c->lane[c->cur];
         CU(c, cudaEventRecord(c->ev_in, st));
-        CU(c, cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
-        rc = run_range(c, L, 0, c->cfg.B, lv, anchors, counts, c->own_stream, L.tail_stream, c->timing);
-        if (rc) return rc;
+        const bool graphs = c->use_graphs && !c->prefilter && c->k2_on_tail;
+        if (graphs) recorded = false;
+        if (graphs && L.uses > 0) {
+            // Replay: the whole run (moments, scan, posterior, soft-NMS, fusion) is one graph launch on the lane's
+            // stream -- a dozen stream calls per run make batches of a few images host-bound.  Stream order puts it
+            // behind the lane's previous run; an event node inside the graph puts its moments kernel behind the
+            // previous lane's; only the two kernels that read the caller's tensors are re-pointed when those change.
+            rc = replay_run(c, L, lv, anchors, counts);
+            if (rc) return rc;
+        } else {
+            CU(c, cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
+            if (graphs) {
+                // first run of the lane: through the streams (one-time kernel attributes and tables are set up here);
+                // its head has to follow the previous lane's, which may have been a replay
+                const Lane& P = c->lane[(c->cur + c->nlanes - 1) % c->nlanes];
+                if (P.uses > 0) CU(c, cudaStreamWaitEvent(c->own_stream, P.head_done, 0));
+            }
+            rc = run_range(c, L, 0, c->cfg.B, lv, anchors, counts, c->own_stream, L.tail_stream, c->timing && !graphs);
+            if (rc) return rc;
+        }
+        ++L.uses;
         CU(c, cudaStreamWaitEvent(st, L.head_done, 0));
         c->last_stream = L.tail_stream;
     }
-    if (c->timing) ++c->runs_recorded;
-    c->last_timed = c->timing;
+    if (recorded) ++c->runs_recorded;
+    c->last_timed = recorded;
     c->ran = true; c->used_sampler = (counts == nullptr);
     return BOD_OK;
 }
@@ -734,10 +875,18 @@ extern "C" int bod_stage_ms_accum(bod_ctx* c, float sum_ms[6], int32_t* runs) {
     if (!c || !sum_ms || !runs) return BOD_ERR_INVALID;
     for (int i = 0; i < 6; ++i) sum_ms[i] = 0.0f;
     *runs = 0;
-    if (c->runs_recorded == c->runs_reported) return BOD_OK;
+    if (c->runs_recorded == c->runs_reported && !c->ran) return BOD_OK;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->last_stream));
+    if (c->last_stream) CU(c, cudaStreamSynchronize(c->last_stream));
     { int rc0 = drain_tails(c); if (rc0) return rc0; }      // earlier runs' tails live on other streams
+    // graph replays (pipelined contexts) time their moments kernel only; the other stages read as zero there
+    for (int l = 0; l < c->nlanes; ++l) harvest_k1_time(c, c->lane[l]);
+    if (c->g_k1_runs > 0) {
+        sum_ms[0] = (float)c->g_k1_ms; *runs = (int32_t)c->g_k1_runs;
+        c->g_k1_ms = 0.0; c->g_k1_runs = 0;
+        c->runs_reported = c->runs_recorded;
+        return BOD_OK;
+    }
     long long first = c->runs_reported;
     if (c->runs_recorded - first > bod_ctx::kEvRing) first = c->runs_recorded - bod_ctx::kEvRing;
     for (long long r = first; r < c->runs_recorded; ++r) {

@@ -46,6 +46,9 @@ struct K1Args {
 uint32_t k1_tickets_per_launch(const K1Args& a);
 cudaError_t launch_k1(const K1Args& a, cudaStream_t st);
 bool k1_supports(int K);
+// CUDA graphs: the kernel launch_k1 launches for these arguments; re-pointing a captured launch at other input tensors
+const void* k1_kernel_func(const K1Args& a);
+cudaError_t k1_graph_update(cudaGraphExec_t exec, cudaGraphNode_t node, const K1Args& a);
 
 // ---- K1b: per-image exclusive scan of tile counts (+ optional pre-NMS top-k) --
 struct ScanArgs {
@@ -97,6 +100,8 @@ struct K2Args {
     int anchor_mode, im_h, im_w;
 };
 cudaError_t launch_k2(const K2Args& a, cudaStream_t st);
+const void* k2_kernel_func(const K2Args& a);
+cudaError_t k2_graph_update(cudaGraphExec_t exec, cudaGraphNode_t node, const K2Args& a);
 // joint_entropy ranking: normalise the information gains over each image's survivors
 cudaError_t launch_rank_normalise(const K2Args& a, cudaStream_t st);
 

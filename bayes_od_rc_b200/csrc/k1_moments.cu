@@ -671,6 +671,35 @@ cudaError_t launch_k1(const K1Args& a0, cudaStream_t st) {
     }
 }
 
+// ---- CUDA-graph support: which kernel launch_k1 launches for these arguments, and how to point a captured
+// launch of it at new arguments (same shapes; other input tensors) ----
+template <int K>
+static const void* k1_func_k(const K1Args& a) {
+    return k1_aligned(a) ? (const void*)k1_moments_pipe_kernel<K> : (const void*)k1_moments_kernel<K, false>;
+}
+const void* k1_kernel_func(const K1Args& a) {
+    switch (a.K) {
+#define BOD_CASE(KK) case KK: return k1_func_k<KK>(a);
+        BOD_CASE(2) BOD_CASE(3) BOD_CASE(4) BOD_CASE(5) BOD_CASE(6) BOD_CASE(7) BOD_CASE(8) BOD_CASE(9)
+        BOD_CASE(10) BOD_CASE(11) BOD_CASE(12) BOD_CASE(13) BOD_CASE(16) BOD_CASE(21) BOD_CASE(32)
+#undef BOD_CASE
+        default: return nullptr;
+    }
+}
+cudaError_t k1_graph_update(cudaGraphExec_t exec, cudaGraphNode_t node, const K1Args& a0) {
+    K1Args a = a0;
+    cudaError_t e;
+    a.ratio_slot = ratio_slot_for(a.num_draws, &e);
+    if (e != cudaSuccess) return e;
+    cudaKernelNodeParams p;
+    e = cudaGraphKernelNodeGetParams(node, &p);
+    if (e != cudaSuccess) return e;
+    if (p.func != k1_kernel_func(a)) return cudaErrorInvalidValue;      // alignment class changed: recapture
+    void* args[2] = {&a, p.kernelParams[1]};                            // (K1Args, ring depth / samples per stage)
+    p.kernelParams = args;
+    return cudaGraphExecKernelNodeSetParams(exec, node, &p);
+}
+
 bool k1_supports(int K) {
     switch (K) {
         case 2: case 3: case 4: case 5: case 6: case 7: case 8: case 9: case 10: case 11: case 12: case 13:

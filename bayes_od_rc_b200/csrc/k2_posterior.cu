@@ -612,6 +612,27 @@ cudaError_t launch_k2(const K2Args& a, cudaStream_t st) {
     }
 }
 
+// ---- CUDA-graph support (see k1_kernel_func) ----
+const void* k2_kernel_func(const K2Args& a) {
+    switch (a.K) {
+#define BOD_CASE(KK) case KK: return (const void*)k2_posterior_kernel<KK>;
+        BOD_CASE(2) BOD_CASE(3) BOD_CASE(4) BOD_CASE(5) BOD_CASE(6) BOD_CASE(7) BOD_CASE(8) BOD_CASE(9)
+        BOD_CASE(10) BOD_CASE(11) BOD_CASE(12) BOD_CASE(13) BOD_CASE(16) BOD_CASE(21) BOD_CASE(32)
+#undef BOD_CASE
+        default: return nullptr;
+    }
+}
+cudaError_t k2_graph_update(cudaGraphExec_t exec, cudaGraphNode_t node, const K2Args& a0) {
+    K2Args a = a0;
+    cudaKernelNodeParams p;
+    cudaError_t e = cudaGraphKernelNodeGetParams(node, &p);
+    if (e != cudaSuccess) return e;
+    if (p.func != k2_kernel_func(a)) return cudaErrorInvalidValue;
+    void* args[2] = {&a, p.kernelParams[1]};                            // (K2Args, AnchorLevels)
+    p.kernelParams = args;
+    return cudaGraphExecKernelNodeSetParams(exec, node, &p);
+}
+
 cudaError_t launch_rank_normalise(const K2Args& a, cudaStream_t st) {
     rank_normalise_kernel<<<a.B, 1024, 0, st>>>(a);
     return cudaGetLastError();

@@ -440,12 +440,11 @@ BOD_DEVINL void warp_top_merge2(Top2 t, unsigned long long (&out)[kTop1], unsign
 // The rounds of one image.  BIG: per-candidate state in the workspace's global rows (more survivors than the
 // shared-memory pool holds); otherwise every state pointer is derived from the dynamic shared array, so the
 // compiler emits LDS / STS instead of generic accesses.
-template <int NT, bool BIG>
+template <int NT, bool BIG, int kCH>
 BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, const int S) {
     constexpr int W = NT / 32;                              // warps
     constexpr int kTop1 = kListed / W;                      // keys every warp lists per round
     constexpr int kSegCap = kPairsCta / W;                  // pairs per warp segment
-    constexpr int kCH = NT >= 1024 ? 4 : 8;                 // candidates per thread handled per pass-A/B block (registers)
     static_assert(W >= kTeamWarps && kTop1 >= 2 && kTop1 * W == kListed && kSegCap >= 32, "CTA size");
     extern __shared__ __align__(16) unsigned char dyn[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -835,8 +834,9 @@ k3_softnms_kernel(K3Args a, int pool_bytes) {
     const int S = a.num_survivors[b];
     if (S > a.max_rows) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
     const long long SP = (long long)((S + NT - 1) / NT) * NT;
-    if (SP * 25 > (long long)pool_bytes || a.force_big != 0) k3_rounds<NT, true>(a, pool_bytes, sm, S);
-    else k3_rounds<NT, false>(a, pool_bytes, sm, S);
+    constexpr int kCH = NT >= 1024 ? 4 : 8;                 // candidates per thread handled per pass-A/B block (registers)
+    if (SP * 25 > (long long)pool_bytes || a.force_big != 0) k3_rounds<NT, true, kCH>(a, pool_bytes, sm, S);
+    else k3_rounds<NT, false, kCH>(a, pool_bytes, sm, S);
 }
 
 static bool g_exp_tab_ready[64] = {false};

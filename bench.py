@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = auto)")
-    ap.add_argument("--pipeline", type=int, default=0, choices=list(range(0, 9)),
+    ap.add_argument("--pipeline", type=int, default=0, choices=list(range(0, 17)),
                     help="bod_config.pipeline_depth (lanes): step i+1's K1/K2 overlap the soft-NMS/fusion of the steps "
                          "before it; 1 = one step at a time; 0 = auto: 4 lanes once a batch fills the GPU "
                          "(soft-NMS holds one SM per image), up to 8 for small batches")
@@ -190,7 +190,7 @@ def main():
     B = args.batch or wl["B"]
     N, K = wl["N"], wl["K"]
     if args.pipeline == 0:
-        args.pipeline = min(8, max(4, 64 // B))
+        args.pipeline = min(16, max(4, 64 // B))
     spec = synthetic.SceneSpec(im_h=wl["im_h"], im_w=wl["im_w"], N=N, K=K, config_id=wl["config_id"], **wl.get("spec", {}))
     first_image = rank * B                      # global image ids: shard-invariant RNG + data
 
