@@ -77,6 +77,8 @@ SYMBOLS = {
     "bod_run": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
     "bod_run_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bod_wait_results": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bod_set_sampler_stream": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
+    "bod_set_image_scale": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "bod_validate_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BodValScaling), C.c_void_p]),
     "bod_run_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(BodHostResults)]),
     "bod_last_host_traffic": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -84,6 +86,12 @@ SYMBOLS = {
                                    C.c_void_p, C.c_float, C.POINTER(BodHostResults)]),
     "bod_fetch": (C.c_int, [C.c_void_p, C.POINTER(BodHostResults)]),
     "bod_device_results_of": (C.c_int, [C.c_void_p, C.POINTER(BodDeviceResults)]),
+    "bod_last_ticket": (C.c_int64, [C.c_void_p]),
+    "bod_fetch_async": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(BodHostResults)]),
+    "bod_ticket_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "bod_device_results_at": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(BodDeviceResults)]),
+    "bod_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "bod_host_free": (None, [C.c_void_p]),
     "bod_fetch_survivors": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(BodHostSurvivors)]),
     "bod_fetch_members": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "bod_fetch_probs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

@@ -40,6 +40,10 @@ struct Lane {
     cudaGraphNode_t gk1 = nullptr, gk2 = nullptr;     // the moments / posterior kernel nodes (their inputs change per run)
     K1Args ga1{}; K2Args ga2{};                       // what those nodes currently point at
     int uses = 0;                                     // runs issued on this lane (the first one goes through the streams: lazy one-time setup)
+    long long ticket = 0;                             // the run whose results the lane holds (0: none yet)
+    cudaEvent_t fetch_done = nullptr;                 // after the copies of the lane's last bod_fetch_async
+    bool fetch_pending = false;
+    int32_t* h_status = nullptr;                      // pinned: the context's status word as of that fetch
     cudaEvent_t k1_begin = nullptr, k1_end = nullptr; // timing of the lane's last replayed moments kernel
     bool k1_timed = false;
 };
@@ -98,6 +102,7 @@ struct bod_ctx {
     bool k2_on_tail = true;           // pipelined contexts: K2 rides with the tail (see run_range); BOD_K2_TAIL=0 keeps it on the head
     bool use_graphs = true;           // pipelined contexts replay each lane's run as a CUDA graph (BOD_GRAPHS=0: stream launches)
     double g_k1_ms = 0.0; long long g_k1_runs = 0;    // moments-kernel time of replayed runs (harvested when a lane is reused)
+    long long next_ticket = 0;        // tickets of issued runs: 1, 2, 3, ...
     int k3_psm_max = -1, k3_seg_cap = -1;   // BOD_K3_PSM_MAX / BOD_K3_SEGCAP (tests: reach the spill rows / the piecewise pass B on small inputs)
 };
 
@@ -280,7 +285,12 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
     if (const char* d = getenv("BOD_K2_TAIL")) c->k2_on_tail = atoi(d) != 0;
     if (const char* d = getenv("BOD_GRAPHS")) c->use_graphs = atoi(d) != 0;
-    for (int l = 0; l < c->nlanes; ++l) { cudaEventCreate(&c->lane[l].k1_begin); cudaEventCreate(&c->lane[l].k1_end); }
+    for (int l = 0; l < c->nlanes; ++l) {
+        cudaEventCreate(&c->lane[l].k1_begin); cudaEventCreate(&c->lane[l].k1_end);
+        cudaEventCreateWithFlags(&c->lane[l].fetch_done, cudaEventDisableTiming);
+        cudaMallocHost(&c->lane[l].h_status, sizeof(int32_t));
+        if (c->lane[l].h_status) *c->lane[l].h_status = 0;
+    }
     if (const char* d = getenv("BOD_K3_PSM_MAX")) c->k3_psm_max = atoi(d);
     if (const char* d = getenv("BOD_K3_SEGCAP")) c->k3_seg_cap = atoi(d);
     e = cudaDeviceSynchronize();
@@ -304,6 +314,8 @@ extern "C" void bod_destroy(bod_ctx* c) {
         if (L.tail_done) cudaEventDestroy(L.tail_done);
         if (L.k1_begin) cudaEventDestroy(L.k1_begin);
         if (L.k1_end) cudaEventDestroy(L.k1_end);
+        if (L.fetch_done) cudaEventDestroy(L.fetch_done);
+        if (L.h_status) cudaFreeHost(L.h_status);
         for (int i = 0; i < 2; ++i) {
             if (L.gexec[i]) cudaGraphExecDestroy(L.gexec[i]);
             if (L.graph[i]) cudaGraphDestroy(L.graph[i]);
@@ -562,6 +574,7 @@ static int replay_run(bod_ctx* c, Lane& L, const LevelTable& lv, const float* an
     } else {
         K1Args a1 = L.ga1;
         a1.lv = lv; a1.counts_in = counts;
+        a1.seed = c->cfg.seed; a1.image_id_base = c->cfg.image_id_base;
         if (memcmp(&a1, &L.ga1, sizeof a1) != 0) {
             cudaError_t e = k1_graph_update(L.gexec[0], L.gk1, a1);
             if (e != cudaSuccess) return fail(c, BOD_ERR_CUDA, "graph update (moments kernel): %s", cudaGetErrorString(e));
@@ -569,6 +582,7 @@ static int replay_run(bod_ctx* c, Lane& L, const LevelTable& lv, const float* an
         }
         K2Args a2 = L.ga2;
         a2.lv = lv; a2.anchors = anchors;
+        a2.scale_v = c->cfg.scale_v; a2.scale_u = c->cfg.scale_u;
         if (!cov_width(c->cfg.cov_layout)) for (int l = 0; l < a2.lv.n; ++l) a2.lv.cov[l] = nullptr;
         if (memcmp(&a2, &L.ga2, sizeof a2) != 0) {
             cudaError_t e = k2_graph_update(L.gexec[1], L.gk2, a2);
@@ -635,6 +649,8 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
         CU(c, cudaStreamWaitEvent(st, L.head_done, 0));
         c->last_stream = L.tail_stream;
     }
+    c->lane[c->cur].ticket = ++c->next_ticket;
+    c->lane[c->cur].fetch_pending = false;
     if (recorded) ++c->runs_recorded;
     c->last_timed = recorded;
     c->ran = true; c->used_sampler = (counts == nullptr);
@@ -668,6 +684,18 @@ extern "C" int bod_run_levels(bod_ctx* c, const float* const* cls, const float* 
     return issue_run(c, levels_split(c, cls, box, c->cfg.cov_layout != BOD_COV_NONE ? cov : nullptr), anchors, counts, cuda_stream);
 }
 
+extern "C" int bod_set_sampler_stream(bod_ctx* c, uint64_t seed, uint32_t image_id_base) {
+    if (!c) return BOD_ERR_INVALID;
+    c->cfg.seed = seed; c->cfg.image_id_base = image_id_base;
+    return BOD_OK;
+}
+extern "C" int bod_set_image_scale(bod_ctx* c, float scale_v, float scale_u) {
+    if (!c) return BOD_ERR_INVALID;
+    if (!(scale_v > 0.0f) || !(scale_u > 0.0f)) return fail(c, BOD_ERR_INVALID, "scale factors must be positive");
+    c->cfg.scale_v = scale_v; c->cfg.scale_u = scale_u;
+    return BOD_OK;
+}
+
 extern "C" int bod_wait_results(bod_ctx* c, void* cuda_stream) {
     if (!c) return BOD_ERR_INVALID;
     if (!c->ran) return fail(c, BOD_ERR_STATE, "no bod_run has been issued on this context");
@@ -689,6 +717,7 @@ extern "C" int bod_validate_run(bod_ctx* c, const float* cls, const float* box, 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     { int rc0 = drain_tails(c); if (rc0) return rc0; }                  // drain pipelined runs first
     c->cur = 0;
+    c->lane[0].ticket = ++c->next_ticket; c->lane[0].fetch_pending = false;
     Lane& L = c->lane[0];
     const bod_config& g = c->cfg;
     c->launches = 0;
@@ -741,9 +770,8 @@ static int sync_and_status(bod_ctx* c) {
     return BOD_OK;
 }
 
-static int copy_results(bod_ctx* c, bod_host_results* out, cudaStream_t st) {
+static int copy_results(bod_ctx* c, const Lane& L, bod_host_results* out, cudaStream_t st) {
     const size_t B = c->cfg.B, D = c->Dmax, K = c->cfg.K;
-    const Lane& L = c->lane[c->cur];
 #define D2H(dst, src, bytes) if (out->dst) CU(c, cudaMemcpyAsync(out->dst, L.src, (bytes), cudaMemcpyDeviceToHost, st))
     D2H(num_dets, num_dets, B * 4);
     D2H(num_survivors, num_survivors, B * 4);
@@ -762,7 +790,7 @@ extern "C" int bod_fetch(bod_ctx* c, bod_host_results* out) {
     if (!c || !out) return BOD_ERR_INVALID;
     int rc = sync_and_status(c);
     if (rc) return rc;
-    rc = copy_results(c, out, c->last_stream);
+    rc = copy_results(c, c->lane[c->cur], out, c->last_stream);
     if (rc) return rc;
     CU(c, cudaStreamSynchronize(c->last_stream));
     return BOD_OK;
@@ -776,6 +804,75 @@ extern "C" int bod_device_results_of(bod_ctx* c, bod_device_results* out) {
     out->nms_indices = L.nms_idx; out->centre_anchor_idx = L.centre_anchor; out->centre_scores = L.nms_score;
     return BOD_OK;
 }
+
+// ---- streaming retrieval: every run's results, by ticket ----
+static Lane* lane_of_ticket(bod_ctx* c, long long ticket) {
+    if (ticket <= 0) return nullptr;
+    for (int l = 0; l < c->nlanes; ++l) if (c->lane[l].ticket == ticket) return &c->lane[l];
+    return nullptr;
+}
+static cudaStream_t stream_of_lane(bod_ctx* c, const Lane& L) { return c->nlanes > 1 ? L.tail_stream : c->last_stream; }
+
+extern "C" int64_t bod_last_ticket(const bod_ctx* c) { return c ? (int64_t)c->next_ticket : 0; }
+
+extern "C" int bod_fetch_async(bod_ctx* c, int64_t ticket, bod_host_results* out) {
+    if (!c || !out) return BOD_ERR_INVALID;
+    Lane* L = lane_of_ticket(c, ticket);
+    if (!L) return fail(c, BOD_ERR_STATE, "the results of run %lld are gone: its lane has been reused (pipeline_depth = %d)",
+                        (long long)ticket, c->nlanes);
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream_of_lane(c, *L);
+    int rc = copy_results(c, *L, out, st);
+    if (rc) return rc;
+    if (L->h_status) CU(c, cudaMemcpyAsync(L->h_status, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaEventRecord(L->fetch_done, st));
+    L->fetch_pending = true;
+    // the lane's next run must not overwrite what these copies still have to read
+    if (c->nlanes > 1 && L->tail_pending) CU(c, cudaEventRecord(L->tail_done, st));
+    return BOD_OK;
+}
+
+extern "C" int bod_ticket_wait(bod_ctx* c, int64_t ticket) {
+    if (!c) return BOD_ERR_INVALID;
+    Lane* L = lane_of_ticket(c, ticket);
+    if (!L) return fail(c, BOD_ERR_STATE, "run %lld is not in flight any more (pipeline_depth = %d)", (long long)ticket, c->nlanes);
+    CU(c, cudaSetDevice(c->device));
+    if (L->fetch_pending) {
+        CU(c, cudaEventSynchronize(L->fetch_done));
+        if (L->h_status && (*L->h_status & 1)) {
+            CU(c, cudaMemset(c->status, 0, 4));        // sticky until reported once
+            *L->h_status = 0;
+            return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
+        }
+        return BOD_OK;
+    }
+    CU(c, cudaStreamSynchronize(stream_of_lane(c, *L)));
+    int32_t status = 0;
+    CU(c, cudaMemcpy(&status, c->status, 4, cudaMemcpyDeviceToHost));
+    if (status & 1) {
+        CU(c, cudaMemset(c->status, 0, 4));
+        return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
+    }
+    return BOD_OK;
+}
+
+extern "C" int bod_device_results_at(bod_ctx* c, int64_t ticket, bod_device_results* out) {
+    if (!c || !out) return BOD_ERR_INVALID;
+    Lane* Lp = lane_of_ticket(c, ticket);
+    if (!Lp) return fail(c, BOD_ERR_STATE, "the results of run %lld are gone: its lane has been reused", (long long)ticket);
+    const Lane& L = *Lp;
+    out->num_dets = L.num_dets; out->num_survivors = L.num_survivors;
+    out->means = L.out_means; out->covs = L.out_covs; out->cat_param = L.out_param; out->cat_count = L.out_count;
+    out->nms_indices = L.nms_idx; out->centre_anchor_idx = L.centre_anchor; out->centre_scores = L.nms_score;
+    return BOD_OK;
+}
+
+extern "C" void* bod_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void bod_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" int bod_fetch_survivors(bod_ctx* c, int32_t b, bod_host_survivors* out) {
     if (!c || !out || b < 0 || b >= c->cfg.B) return BOD_ERR_INVALID;
@@ -942,6 +1039,7 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
     cudaStream_t cs = c->copy_stream, st = c->own_stream;
     { int rc0 = drain_tails(c); if (rc0) return rc0; }                  // drain pipelined runs; this entry is synchronous
     c->cur = 0;
+    c->lane[0].ticket = ++c->next_ticket; c->lane[0].fetch_pending = false;
     Lane& L = c->lane[0];
     c->launches = 0;
     c->last_timed = false;
@@ -977,7 +1075,7 @@ extern "C" int bod_run_host(bod_ctx* c, const float* cls, const float* box, cons
         if (rc) return rc;
     }
     c->last_stream = st; c->ran = true; c->used_sampler = (counts == nullptr);
-    rc = copy_results(c, out, st);
+    rc = copy_results(c, L, out, st);
     if (rc) return rc;
     CU(c, cudaStreamSynchronize(st));
     int32_t status = 0;
@@ -1026,6 +1124,7 @@ extern "C" int bod_cluster_host(bod_ctx* c, int32_t S, const float* counts, cons
     cudaStream_t st = c->own_stream;
     { int rc0 = drain_tails(c); if (rc0) return rc0; }
     c->cur = 0;
+    c->lane[0].ticket = ++c->next_ticket; c->lane[0].fetch_pending = false;
     Lane& L = c->lane[0];
     const size_t K = c->cfg.K, Dm = c->Dmax;
     c->launches = 0;
@@ -1060,7 +1159,7 @@ extern "C" int bod_cluster_host(bod_ctx* c, int32_t S, const float* counts, cons
     bod_host_results o = *out;
     const size_t keepB = c->cfg.B;
     c->cfg.B = 1;
-    rc = copy_results(c, &o, st);
+    rc = copy_results(c, L, &o, st);
     c->cfg.B = (int32_t)keepB;
     if (rc) return rc;
     CU(c, cudaStreamSynchronize(st));

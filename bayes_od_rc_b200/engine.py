@@ -144,6 +144,8 @@ def device_ptr(x, expect_elems=None, keepalive=None):
     if type(x).__name__ == "PyCapsule":
         return _from_dlpack_capsule(x, expect_elems)
     if hasattr(x, "__dlpack__"):
+        if hasattr(x, "__dlpack_device__") and int(x.__dlpack_device__()[0]) not in (2, 13):     # kDLCUDA, kDLCUDAManaged
+            raise TypeError("DLPack tensor is not in CUDA device memory (stage host tensors through run_host)")
         cap = x.__dlpack__()
         if keepalive is not None:
             keepalive.append(cap)
@@ -194,6 +196,10 @@ class BayesODEngine:
         if getattr(self, "_ctx", None) and self._ctx.value:
             self.lib.bod_destroy(self._ctx)
             self._ctx = C.c_void_p()
+            self._ring = None
+            for base in getattr(self, "_pinned_bases", []):
+                self.lib.bod_host_free(base)
+            self._pinned_bases = []
 
     def __del__(self):
         try:
@@ -285,6 +291,14 @@ class BayesODEngine:
         self._keep = (cls, box, anchors, keep)
         self._check(self.lib.bod_validate_run(self._ctx, p_cls, p_box, p_anc, sc, C.c_void_p(int(stream) or None)))
 
+    def set_sampler_stream(self, seed: int, image_id_base: int):
+        """Philox stream of the next runs: image b draws from (seed, image_id_base + b, anchor)."""
+        self._check(self.lib.bod_set_sampler_stream(self._ctx, int(seed), int(image_id_base) & 0xFFFFFFFF))
+
+    def set_image_scale(self, scale_v: float, scale_u: float):
+        """KITTI rescale factors of the next runs (inference_utils.py:147-167)."""
+        self._check(self.lib.bod_set_image_scale(self._ctx, float(scale_v), float(scale_u)))
+
     def wait_results(self, stream=0):
         """Make ``stream`` wait for the results of the last run (pipeline_depth = 2 only; bod_wait_results)."""
         self._check(self.lib.bod_wait_results(self._ctx, C.c_void_p(int(stream) or None)))
@@ -292,6 +306,56 @@ class BayesODEngine:
     def fetch(self) -> Results:
         self._check(self.lib.bod_fetch(self._ctx, C.byref(self._hres)))
         return self._results()
+
+    # -- streaming retrieval: every run's results, not only the last one's -------------------
+    @property
+    def last_ticket(self) -> int:
+        """Ticket of the run issued last (1, 2, 3, ...): bod_last_ticket."""
+        return int(self.lib.bod_last_ticket(self._ctx))
+
+    def _pinned_block(self):
+        """One set of page-locked host result blocks (bod_host_alloc) viewed as numpy arrays."""
+        B, D, K = self.B, self.Dmax, self.K
+        shapes = dict(num_dets=((B,), np.int32), num_survivors=((B,), np.int32), means=((B, D, 4), np.float32),
+                      covs=((B, D, 4, 4), np.float32), cat_param=((B, D, K), np.float32), cat_count=((B, D, K), np.float32),
+                      nms_indices=((B, D), np.int32), centre_anchor_idx=((B, D), np.int32), centre_scores=((B, D), np.float32))
+        total = sum(int(np.prod(sh)) * 4 for sh, _ in shapes.values())
+        base = self.lib.bod_host_alloc(total)
+        if not base:
+            raise MemoryError("bod_host_alloc failed")
+        self._pinned_bases = getattr(self, "_pinned_bases", [])
+        self._pinned_bases.append(base)
+        arrays, off = {}, 0
+        for k, (sh, dt) in shapes.items():
+            n = int(np.prod(sh))
+            buf = (C.c_byte * (n * 4)).from_address(base + off)
+            arrays[k] = np.frombuffer(buf, dtype=dt, count=n).reshape(sh)
+            off += n * 4
+        return arrays, BodHostResults(**{k: v.ctypes.data for k, v in arrays.items()})
+
+    def fetch_async(self, ticket: int = None) -> int:
+        """Enqueue the device->host copies of run ``ticket`` (default: the last one) behind that run, into the
+        pinned result ring slot of its lane (bod_fetch_async).  Nothing blocks; collect with ``collect(ticket)``
+        before ``pipeline_depth`` further tickets have been fetched (the slot is then reused)."""
+        ticket = self.last_ticket if ticket is None else int(ticket)
+        ring = getattr(self, "_ring", None)
+        if ring is None:
+            ring = self._ring = [self._pinned_block() for _ in range(max(1, int(self.config.pipeline_depth)))]
+        arrays, hres = ring[ticket % len(ring)]
+        self._check(self.lib.bod_fetch_async(self._ctx, ticket, C.byref(hres)))
+        return ticket
+
+    def collect(self, ticket: int, copy=True):
+        """Wait for run ``ticket`` and the copies ``fetch_async`` enqueued for it; its Results."""
+        self._check(self.lib.bod_ticket_wait(self._ctx, int(ticket)))
+        arrays, _ = self._ring[int(ticket) % len(self._ring)]
+        return Results(**{k: v.copy() for k, v in arrays.items()}) if copy else arrays
+
+    def device_results_at(self, ticket: int) -> dict:
+        """Device addresses of run ``ticket``'s padded result blocks (bod_device_results_at)."""
+        out = _cabi.BodDeviceResults()
+        self._check(self.lib.bod_device_results_at(self._ctx, int(ticket), C.byref(out)))
+        return {name: getattr(out, name) for name, _ in out._fields_}
 
     def fetch_into_pinned(self):
         """bod_fetch into the engine's own host blocks without copying them out (bench)."""

@@ -78,13 +78,21 @@ class FusedClusters:
 _engines = {}
 
 
+_PER_RUN = ("seed", "image_id_base", "scale_v", "scale_u")     # set per call on a cached engine, not part of its identity
+
+
 def _engine(B, N, A, K, cfg: BayesODConfig, device=0) -> BayesODEngine:
-    key = (B, N, A, K, device, tuple(sorted(cfg.__dict__.items())))
+    """One engine (workspace, streams, events) per shape and configuration; the sampler stream and the KITTI
+    scale follow the image, so they are applied per call instead of keying the cache (a caller that numbers its
+    images would otherwise build a context per image)."""
+    key = (B, N, A, K, device, tuple(sorted((k, v) for k, v in cfg.__dict__.items() if k not in _PER_RUN)))
     eng = _engines.get(key)
     if eng is None:
         if len(_engines) > 8:                      # shapes rarely change; do not hoard workspaces
             _engines.popitem()[1].close()
         eng = _engines[key] = BayesODEngine(B, N, A, K, cfg, device)
+    eng.set_sampler_stream(cfg.seed, cfg.image_id_base)
+    eng.set_image_scale(cfg.scale_v, cfg.scale_u)
     return eng
 
 
@@ -92,16 +100,49 @@ def _shape(x):
     return tuple(int(d) for d in x.shape)
 
 
+_DL_CPU = (1, 3)            # kDLCPU, kDLCUDAHost
+
+
 def _is_host(x) -> bool:
-    return isinstance(x, np.ndarray)
+    """Host-resident producer output: numpy, or any tensor that says so through DLPack (tf.data / CPU tensors)."""
+    if isinstance(x, np.ndarray):
+        return True
+    if hasattr(x, "is_cuda"):
+        return not x.is_cuda
+    if hasattr(x, "__dlpack_device__"):
+        return int(x.__dlpack_device__()[0]) in _DL_CPU
+    return False
+
+
+def _to_numpy(x, shape=None):
+    """float32 ndarray of a host tensor (numpy, torch CPU, anything with __dlpack__ / __array__)."""
+    if x is None:
+        return None
+    if not isinstance(x, np.ndarray):
+        if hasattr(x, "detach"):
+            x = x.detach().cpu().numpy()
+        elif hasattr(x, "__dlpack__") and hasattr(x, "__dlpack_device__"):
+            x = np.from_dlpack(x)
+        elif hasattr(x, "numpy"):
+            x = x.numpy()
+    a = np.ascontiguousarray(np.asarray(x), np.float32)
+    return a.reshape(shape) if shape is not None else a
+
+
+_image_counter = [0]        # images seen by bayes_od_inference: the default Philox stream id of each call
 
 
 def bayes_od_inference(model, sample_dict, bayes_od_config, nms_config, use_full_covar=False, dataset_name='bdd',
-                       counts=None, seed=1234, image_id=0, device=0):
+                       counts=None, seed=1234, image_id=None, device=0):
     """See module docstring.  Extra keyword arguments (not in the reference):
     ``counts`` [A,K] injects the categorical draw counts (the reference draws them
     unseeded, inference_utils.py:37-46); otherwise the in-kernel Philox sampler is
-    keyed by (``seed``, ``image_id``)."""
+    keyed by (``seed``, ``image_id``); ``image_id`` defaults to the number of images
+    this process has pushed through the function, so that an unchanged
+    run_inference.py gives every image its own random stream."""
+    if image_id is None:
+        image_id = _image_counter[0]
+    _image_counter[0] += 1
     prediction_dict = model(sample_dict[IMAGE_NORMALIZED_KEY], train_val_test='testing')        # :22-23
     cls = prediction_dict[ANCHORS_CLASS_PREDICTIONS_KEY]                                          # [N,A,K]
     box = prediction_dict[ANCHORS_BOX_PREDICTIONS_KEY]                                            # [N,A,4]
@@ -123,15 +164,13 @@ def bayes_od_inference(model, sample_dict, bayes_od_config, nms_config, use_full
     eng = _engine(1, N, A, K, cfg, device)
 
     if _is_host(cls):                       # a host producer: stage through PCIe inside the library
-        res = eng.run_host(cls, box, cov, np.asarray(anchors, np.float32).reshape(A, 4), counts)
+        res = eng.run_host(_to_numpy(cls), _to_numpy(box), _to_numpy(cov), _to_numpy(anchors, (A, 4)), _to_numpy(counts))
     else:                                   # device tensors (TF via DLPack, torch, cupy): zero copy
         import torch                        # device memory plumbing only
-        anc = anchors if hasattr(anchors, "is_cuda") and anchors.is_cuda else \
-            torch.as_tensor(np.asarray(anchors, np.float32).reshape(A, 4)).cuda(device)
+        anc = anchors if not _is_host(anchors) else torch.as_tensor(_to_numpy(anchors, (A, 4))).cuda(device)
         cnt = None
         if counts is not None:
-            cnt = counts if hasattr(counts, "is_cuda") and counts.is_cuda else \
-                torch.as_tensor(np.asarray(counts, np.float32).reshape(1, A, K)).cuda(device)
+            cnt = counts if not _is_host(counts) else torch.as_tensor(_to_numpy(counts, (1, A, K))).cuda(device)
         eng.synchronize()                   # the producer's stream is not ours (TF does not expose it)
         eng.run(cls, box, cov, anc, cnt)
         res = eng.fetch()

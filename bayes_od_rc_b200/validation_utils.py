@@ -25,9 +25,9 @@ import numpy as np
 from . import _cabi
 from .engine import BayesODConfig
 from .inference_utils import (ANCHORS_BOX_PREDICTIONS_KEY, ANCHORS_CLASS_PREDICTIONS_KEY, ANCHORS_KEY,
-                              IMAGE_NORMALIZED_KEY, ORIGINAL_IM_SIZE_KEY, _engine, _ht, _shape)
+                              IMAGE_NORMALIZED_KEY, ORIGINAL_IM_SIZE_KEY, _engine, _ht, _is_host, _shape, _to_numpy)
 
-IMAGE_PADDING_KEY = 'padding'                       # src/core/constants.py
+IMAGE_PADDING_KEY = 'paddings_applied'              # src/core/constants.py:55
 
 
 def _scaling(sample_dict, dataset_name):
@@ -37,7 +37,7 @@ def _scaling(sample_dict, dataset_name):
         orig = np.asarray(sample_dict[ORIGINAL_IM_SIZE_KEY]).reshape(-1)[:2]
         return (_cabi.VAL_SCALE_KITTI, (0, 0, 0, 0), (float(shp[0]), float(shp[1])), (float(orig[0]), float(orig[1])))
     if dataset_name == 'coco':
-        pad = np.asarray(sample_dict[IMAGE_PADDING_KEY], np.float32).reshape(-1, 4)[0]
+        pad = _to_numpy(sample_dict[IMAGE_PADDING_KEY]).reshape(-1, 4)[0]
         shp = np.asarray(_shape(sample_dict[IMAGE_NORMALIZED_KEY])[1:3], np.int32) - (2 * pad[0:2]).astype(np.int32)
         orig = np.asarray(sample_dict[ORIGINAL_IM_SIZE_KEY]).reshape(-1)[:2]
         return (_cabi.VAL_SCALE_COCO, tuple(float(x) for x in pad), (float(shp[0]), float(shp[1])),
@@ -57,11 +57,11 @@ def post_process_predictions(sample_dict, prediction_dict, dataset_name='bdd', d
     import torch                                    # device memory plumbing only
 
     def dev(x, n):
-        if hasattr(x, "is_cuda") and x.is_cuda:
+        """Device view of a producer tensor: CUDA tensors (torch, DLPack capsules / objects) pass through, host
+        tensors (numpy, CPU tensors of any framework -- tf.data hands `anchors` over on the host) are staged."""
+        if type(x).__name__ == "PyCapsule" or not _is_host(x) and (hasattr(x, "is_cuda") or hasattr(x, "__dlpack__")):
             return x
-        if isinstance(x, np.ndarray) or not (hasattr(x, "__dlpack__") or type(x).__name__ == "PyCapsule"):
-            return torch.as_tensor(np.ascontiguousarray(np.asarray(x, np.float32).reshape(n))).cuda(device)
-        return x
+        return torch.as_tensor(_to_numpy(x).reshape(n)).cuda(device)
     eng.synchronize()                               # the producer's stream is not ours
     eng.validate(dev(cls, A * K), dev(box, A * 4), dev(sample_dict[ANCHORS_KEY], A * 4), _scaling(sample_dict, dataset_name))
     res = eng.fetch()

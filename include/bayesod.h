@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BOD_ABI_VERSION 7
+#define BOD_ABI_VERSION 8
 
 typedef enum bod_status {
     BOD_OK            = 0,
@@ -88,7 +88,7 @@ typedef struct bod_config {
     int32_t  max_survivors;      /* per-image survivor capacity; 0 => A                    */
     int32_t  emit_probs;         /* keep the [B,A,K] mean class probabilities (parity)     */
     int32_t  pipeline_depth;     /* 0/1: every bod_run is issued whole, in order, on the
-                                    caller's stream.  L = 2..8: L sets of buffers (lanes);
+                                    caller's stream.  L = 2..16: L sets of buffers (lanes);
                                     run i+1 streams its logits (K1, scan) on the context's own
                                     stream while runs i, i-1, .. are still computing posteriors,
                                     selecting centres and fusing (K2, soft-NMS, K4), each on its
@@ -179,6 +179,13 @@ int64_t bod_workspace_bytes(const bod_ctx* ctx);
 int bod_run(bod_ctx* ctx, const float* cls, const float* box, const float* cov,
             const float* anchors, const float* counts, void* cuda_stream);
 
+/* Per-run parameters of an existing context (they do not change the workspace, so a caller that streams
+ * single images does not need one context per image): the sampler stream of the next runs -- image b of a
+ * run draws from Philox counters keyed by (seed, image_id_base + b, anchor) -- and the KITTI rescale factors
+ * (inference_utils.py:147-167: original size / network input size, which follow the image). */
+int bod_set_sampler_stream(bod_ctx* ctx, uint64_t seed, uint32_t image_id_base);
+int bod_set_image_scale(bod_ctx* ctx, float scale_v, float scale_u);
+
 /* Make `cuda_stream` wait (on the device, without blocking the host) until the
  * results of the last bod_run are complete.  Only needed with pipeline_depth >= 2
  * by consumers that read bod_device_results_of on their own stream; a no-op
@@ -250,6 +257,32 @@ int bod_cluster_host(bod_ctx* ctx, int32_t S, const float* counts /*[S,K]*/,
 
 /* Wait for the last bod_run and copy the padded result blocks to the host. */
 int bod_fetch(bod_ctx* ctx, bod_host_results* out);
+
+/*
+ * Streaming retrieval (every run's results, not only the last one's).  A pipelined
+ * context keeps pipeline_depth runs in flight, each on its own lane of buffers; the
+ * reference hands every image's result on as soon as it exists
+ * (run_inference.py:141-161), so a streaming caller needs the same without
+ * draining the pipeline:
+ *   t = bod_last_ticket(ctx)           ticket of the run just issued (1, 2, 3, ...)
+ *   bod_fetch_async(ctx, t, &blocks)   enqueue the device->host copies of run t's padded
+ *                                      result blocks behind that run, on its lane's stream
+ *                                      (`blocks` should be pinned memory: bod_host_alloc);
+ *                                      nothing blocks, later runs keep streaming
+ *   bod_ticket_wait(ctx, t)            block the host until run t (and its copies) are complete;
+ *                                      returns BOD_ERR_OVERFLOW like bod_fetch
+ * A run's device results stay valid until pipeline_depth - 1 further runs have been
+ * issued (then its lane is reused): bod_fetch_async / bod_device_results_at fail with
+ * BOD_ERR_STATE for tickets older than that.  Copies enqueued by bod_fetch_async are
+ * ordered before the lane's next run, so they never see a later run's data.
+ */
+int64_t bod_last_ticket(const bod_ctx* ctx);
+int bod_fetch_async(bod_ctx* ctx, int64_t ticket, bod_host_results* out);
+int bod_ticket_wait(bod_ctx* ctx, int64_t ticket);
+int bod_device_results_at(bod_ctx* ctx, int64_t ticket, bod_device_results* out);
+/* Page-locked host memory for result blocks (cudaMallocHost / cudaFreeHost). */
+void* bod_host_alloc(size_t bytes);
+void bod_host_free(void* p);
 /* Device pointers of the padded result blocks (no sync, no copy). */
 int bod_device_results_of(bod_ctx* ctx, bod_device_results* out);
 

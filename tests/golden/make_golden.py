@@ -153,6 +153,9 @@ VAL_CASES = {
     "val_kitti_k4": (dict(im_h=64, im_w=128, N=2, K=4, g_min=3, g_max=5, box_hi=60., config_id=22),
                      dict(dataset_name='kitti', orig_size=(47, 94))),
     "val_none_k8":  (dict(im_h=64, im_w=96, N=2, K=8, g_min=3, g_max=4, box_hi=60., config_id=23), dict(all_background=True)),
+    # the coco branch (validation_utils.py:60-66): corners shifted by the applied padding, normalised by the unpadded size
+    "val_coco_k8":  (dict(im_h=96, im_w=160, N=2, K=8, g_min=4, g_max=6, box_hi=90., config_id=26),
+                     dict(dataset_name='coco', orig_size=(61, 113), padding=(8.0, 12.0, 8.0, 12.0))),
     # full size: outputs + input digest only (see FULL_CASES)
     "val_full_bdd_k8": (dict(im_h=720, im_w=1280, N=2, K=8, config_id=24), dict(digest_only=True)),
     "val_full_kitti_k4": (dict(im_h=375, im_w=1242, N=2, K=4, config_id=25),
@@ -176,9 +179,12 @@ def run_val_case(name, spec_kw, ov, vu, ag, cs):
     pred = {cs.ANCHORS_CLASS_PREDICTIONS_KEY: shim._t(cls[None]), cs.ANCHORS_BOX_PREDICTIONS_KEY: shim._t(box[None])}
     sample_dict = {cs.IMAGE_NORMALIZED_KEY: shim._t(image_norm[None]), cs.ANCHORS_KEY: shim._t(anchors[None]),
                    cs.ORIGINAL_IM_SIZE_KEY: shim._t(np.asarray([[orig[0], orig[1], 3]], np.int32))}
+    if "padding" in ov:
+        sample_dict[cs.IMAGE_PADDING_KEY] = shim._t(np.asarray([ov["padding"]], np.float32))
     classes_out, corners_out = vu.post_process_predictions(sample_dict, pred, dataset_name=dataset_name)
     classes_out, corners_out = np.asarray(classes_out, np.float32), np.asarray(corners_out, np.float32)
     meta = dict(case=name, spec=spec_kw, dataset_name=dataset_name, orig_size=list(orig), image_shape=[spec.im_h, spec.im_w],
+                padding=list(ov.get("padding", ())),
                 numpy=np.__version__, generator="tests/golden/make_golden.py over tf_numpy_shim; "
                 "validation_utils.post_process_predictions executed verbatim")
     if ov.get("digest_only"):
@@ -208,7 +214,10 @@ def main():
             run_case(name, spec_kw, ov, iu, bu, ag, cs, Categorical, store_inputs=False)
     import importlib
     vu = importlib.import_module("src.retina_net.experiments.validation_utils")
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
     for name, (spec_kw, ov) in VAL_CASES.items():
+        if only and name not in only:
+            continue
         run_val_case(name, spec_kw, ov, vu, ag, cs)
 
 

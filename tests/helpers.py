@@ -34,10 +34,14 @@ def val_golden_cases():
 
 
 def val_scaling_of(meta):
-    """(scale_mode, norm_hw, scale_hw) as validation_utils.py:54-66 derives them."""
+    """(scale_mode, shift, norm_hw, scale_hw) as validation_utils.py:54-66 derives them."""
     if meta["dataset_name"] == "kitti":
-        return 1, tuple(float(x) for x in meta["image_shape"]), tuple(float(x) for x in meta["orig_size"])
-    return 0, (1.0, 1.0), (1.0, 1.0)
+        return 1, (0, 0, 0, 0), tuple(float(x) for x in meta["image_shape"]), tuple(float(x) for x in meta["orig_size"])
+    if meta["dataset_name"] == "coco":          # :60-66: shift by the padding, normalise by the unpadded size
+        pad = [float(x) for x in meta["padding"]]
+        shp = [int(meta["image_shape"][i]) - int(2 * pad[i]) for i in (0, 1)]
+        return 2, tuple(pad), (float(shp[0]), float(shp[1])), tuple(float(x) for x in meta["orig_size"])
+    return 0, (0, 0, 0, 0), (1.0, 1.0), (1.0, 1.0)
 
 
 _FULL_CACHE = {}

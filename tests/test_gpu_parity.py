@@ -256,6 +256,178 @@ def test_pipelined_runs_equal_serial_runs(depth):
         assert_bit_equal(getattr(res, k), getattr(serial[2], k), f"host entry: {k}")
 
 
+@pytest.mark.parametrize("graphs", ["1", "0"])
+@pytest.mark.parametrize("depth", [1, 2, 4])
+def test_streaming_retrieval_of_every_run(depth, graphs, monkeypatch):
+    """bod_fetch_async / bod_ticket_wait: a stream of different batches through one (pipelined) context, every
+    run's result blocks copied out behind its own tail while later runs keep streaming; device results of run i
+    survive the issue of runs i+1 .. i+L-1 (fetched oldest first after L back-to-back runs); tickets older than
+    that are refused.  With graph replay and with plain stream launches."""
+    import torch
+    from gpu_common import engine_config_from_oracle
+    from bayes_od_rc_b200.engine import BayesODEngine
+    from bayes_od_rc_b200._cabi import BodError
+    monkeypatch.setenv("BOD_GRAPHS", graphs)
+    spec = synthetic.SceneSpec(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=46)
+    B, runs = 2, 13
+    oc = oracle.OracleConfig()
+    batches = [synthetic.to_numpy(synthetic.make_batch(spec, B, first_image_id=50 * i)) for i in range(runs)]
+    serial = [run_gpu_batch(oc, b["cls"], b["box"], b["cov"], b["anchors"], b["counts"], emit_probs=False)[1] for b in batches]
+    N, A, K = batches[0]["cls"].shape[1:]
+    eng = BayesODEngine(B, N, A, K, engine_config_from_oracle(oc, pipeline_depth=depth))
+    dev = [{k: torch.from_numpy(b[k]).cuda() for k in ("cls", "box", "cov", "anchors", "counts")} for b in batches]
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    keys = ("num_dets", "num_survivors", "means", "covs", "cat_param", "cat_count", "nms_indices", "centre_anchor_idx",
+            "centre_scores")
+
+    def check(res, i, what):
+        for k in keys:
+            assert_bit_equal(getattr(res, k), getattr(serial[i], k), f"{what}, run {i}: {k}")
+
+    # (a) fetch_async right behind every run, collected `depth - 1` runs later
+    tickets = []
+    for i in range(runs):
+        d = dev[i]
+        eng.run(d["cls"], d["box"], d["cov"], d["anchors"], d["counts"], stream=st.cuda_stream)
+        tickets.append(eng.fetch_async())
+        assert tickets[-1] == eng.last_ticket
+        j = i - (depth - 1)
+        if j >= 0:
+            check(eng.collect(tickets[j]), j, "streamed")
+    for j in range(max(0, runs - depth + 1), runs):
+        check(eng.collect(tickets[j]), j, "drained")
+    # (b) L runs back to back, then every one of them fetched, oldest first: results survive in their lanes
+    first = 3
+    tk = []
+    for i in range(first, first + depth):
+        d = dev[i]
+        eng.run(d["cls"], d["box"], d["cov"], d["anchors"], d["counts"], stream=st.cuda_stream)
+        tk.append(eng.last_ticket)
+    for n, t in enumerate(tk):
+        eng.fetch_async(t)
+        check(eng.collect(t), first + n, "kept in its lane")
+    # (c) a ticket whose lane has been reused is refused
+    with pytest.raises(BodError) as e:
+        eng.fetch_async(tk[0] - 1 if depth > 1 else tk[0] - 1)
+    assert e.value.status == _status("BOD_ERR_STATE")
+    # (d) the input tensors of a lane change from run to run (graph nodes are re-pointed): covered by (a) --
+    # and a run with the sampler instead of injected counts re-captures
+    d = dev[0]
+    eng.run(d["cls"], d["box"], d["cov"], d["anchors"], None, stream=st.cuda_stream)
+    t = eng.fetch_async()
+    res = eng.collect(t)
+    _, ref = run_gpu_batch(oc, batches[0]["cls"], batches[0]["box"], batches[0]["cov"], batches[0]["anchors"], None,
+                           emit_probs=False)
+    for k in keys:
+        assert_bit_equal(getattr(res, k), getattr(ref, k), f"sampler run after injected runs: {k}")
+
+
+def _status(name):
+    from bayes_od_rc_b200 import _cabi
+    return getattr(_cabi, name)
+
+
+@pytest.mark.parametrize("depth", [2, 3])
+def test_pipelined_prefilter_every_run(depth):
+    """Pipelined context with the pre-NMS filter (K2 stays on the head stream there): back-to-back runs of
+    different batches, every run's results checked -- the lane's survivor counts must not be rewritten by the
+    next run on that lane while its soft-NMS / fusion kernels still read them."""
+    import torch
+    from gpu_common import engine_config_from_oracle
+    from bayes_od_rc_b200.engine import BayesODEngine
+    spec = synthetic.SceneSpec(im_h=192, im_w=320, N=10, K=8, g_min=6, g_max=10, box_hi=150., config_id=57)
+    B, runs = 2, 9
+    oc = oracle.OracleConfig(pre_nms_top_k=150)
+    batches = [synthetic.to_numpy(synthetic.make_batch(spec, B, first_image_id=70 * i)) for i in range(runs)]
+    serial = [run_gpu_batch(oc, b["cls"], b["box"], b["cov"], b["anchors"], b["counts"], emit_probs=False)[1] for b in batches]
+    assert len({int(s.num_survivors[0]) for s in serial}) >= 1
+    N, A, K = batches[0]["cls"].shape[1:]
+    eng = BayesODEngine(B, N, A, K, engine_config_from_oracle(oc, pipeline_depth=depth))
+    dev = [{k: torch.from_numpy(b[k]).cuda() for k in ("cls", "box", "cov", "anchors", "counts")} for b in batches]
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    tickets = []
+    for i in range(runs):
+        d = dev[i]
+        eng.run(d["cls"], d["box"], d["cov"], d["anchors"], d["counts"], stream=st.cuda_stream)
+        tickets.append(eng.fetch_async())
+        j = i - (depth - 1)
+        if j >= 0:
+            res = eng.collect(tickets[j])
+            for k in ("num_dets", "num_survivors", "means", "covs", "cat_param", "cat_count", "nms_indices"):
+                assert_bit_equal(getattr(res, k), getattr(serial[j], k), f"run {j}: {k}")
+
+
+def test_dlpack_inputs():
+    """The TF-interop path of INTEGRATION.md: CUDA DLPack capsules and objects with __dlpack__ go through
+    bayes_od_inference / the engine without a copy; host tensors that only speak DLPack are staged."""
+    import torch
+    from torch.utils.dlpack import to_dlpack
+    from gpu_common import engine_config_from_oracle
+    from bayes_od_rc_b200.engine import BayesODEngine
+    spec = synthetic.SceneSpec(im_h=96, im_w=160, N=6, K=8, g_min=4, g_max=6, box_hi=90., config_id=47)
+    B = 2
+    nb = synthetic.to_numpy(synthetic.make_batch(spec, B))
+    oc = oracle.OracleConfig()
+    _, ref = run_gpu_batch(oc, nb["cls"], nb["box"], nb["cov"], nb["anchors"], nb["counts"], emit_probs=False)
+    N, A, K = nb["cls"].shape[1:]
+    dev = {k: torch.from_numpy(nb[k]).cuda() for k in ("cls", "box", "cov", "anchors", "counts")}
+
+    class OnlyDLPack:                       # what a foreign framework's tensor looks like: no data_ptr, no CAI
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, stream=None, **kw):
+            return to_dlpack(self._t)
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    keys = ("num_dets", "num_survivors", "means", "covs", "cat_param", "cat_count", "nms_indices")
+    for wrap in (to_dlpack, OnlyDLPack):
+        eng = BayesODEngine(B, N, A, K, engine_config_from_oracle(oc))
+        eng.run(*[wrap(dev[k]) for k in ("cls", "box", "cov", "anchors", "counts")])
+        res = eng.fetch()
+        for k in keys:
+            assert_bit_equal(getattr(res, k), getattr(ref, k), f"{wrap.__name__}: {k}")
+    # through the drop-in, one image: DLPack-only objects for the head outputs (device) and the anchors (host)
+    from bayes_od_rc_b200 import inference_utils as iu
+
+    class HostDLPack(OnlyDLPack):
+        def __init__(self, t):
+            super().__init__(t)
+            self.shape = tuple(t.shape)
+
+    class DevDLPack(OnlyDLPack):
+        def __init__(self, t):
+            super().__init__(t)
+            self.shape = tuple(t.shape)
+
+    pred = {iu.ANCHORS_CLASS_PREDICTIONS_KEY: DevDLPack(dev["cls"][0]), iu.ANCHORS_BOX_PREDICTIONS_KEY: DevDLPack(dev["box"][0]),
+            iu.ANCHORS_COVAR_PREDICTIONS_KEY: DevDLPack(dev["cov"][0])}
+    model = lambda image, train_val_test="testing": pred      # noqa: E731
+    sample_dict = {iu.IMAGE_NORMALIZED_KEY: np.zeros((1, spec.im_h, spec.im_w, 3), np.float32),
+                   iu.ANCHORS_KEY: HostDLPack(torch.from_numpy(nb["anchors"][None].copy())),
+                   iu.ORIGINAL_IM_SIZE_KEY: np.asarray([[spec.im_h, spec.im_w, 3]], np.int32)}
+    bcfg = dict(dirichlet_prior=dict(type="non_informative"),
+                gaussian_prior=dict(type="isotropic", isotropic_variance=100000.0), ranking_method="score")
+    ncfg = dict(max_output_size=100, iou_threshold=0.5, soft_nms_sigma=0.5)
+    out = iu.bayes_od_inference(model, sample_dict, bcfg, ncfg, use_full_covar=True, dataset_name="bdd", counts=nb["counts"][0])
+    fused = iu.bayes_od_clustering(*[o.numpy() for o in out], affinity_threshold=0.5)
+    d = int(ref.num_dets[0])
+    assert_bit_equal(np.asarray(fused[1])[:, :, 0], ref.means[0, :d], "drop-in fused means from DLPack inputs")
+    # consecutive calls without image_id use consecutive Philox streams on ONE cached engine
+    n_eng = len(iu._engines)
+    a = iu.bayes_od_inference(model, sample_dict, bcfg, ncfg, use_full_covar=True, dataset_name="bdd")
+    b = iu.bayes_od_inference(model, sample_dict, bcfg, ncfg, use_full_covar=True, dataset_name="bdd")
+    c = iu.bayes_od_inference(model, sample_dict, bcfg, ncfg, use_full_covar=True, dataset_name="bdd", image_id=12345)
+    c2 = iu.bayes_od_inference(model, sample_dict, bcfg, ncfg, use_full_covar=True, dataset_name="bdd", image_id=12345)
+    assert len(iu._engines) == n_eng, "a context per image id"
+    assert not np.array_equal(np.asarray(a[0]), np.asarray(b[0])), "every image drew the same random stream"
+    assert np.array_equal(np.asarray(c[0]), np.asarray(c2[0]))
+
+
 def test_philox_sampler_matches_restatement():
     """Sampler mode: the counts the kernel draws equal the oracle's Philox restatement
     run on the kernel's own mean probabilities, bit for bit; every row sums to T."""
@@ -610,10 +782,10 @@ def _compare_validate(eng, res, b, r, K):
 @pytest.mark.parametrize("name", val_golden_cases())
 def test_validation_golden(name):
     g = load_golden(name)
-    mode, norm_hw, scale_hw = val_scaling_of(g["meta"])
+    mode, shift, norm_hw, scale_hw = val_scaling_of(g["meta"])
     eng, res = _run_validate(g["cls"][None], g["box"][None], g["anchors"],
-                             scaling=None if mode == 0 else (mode, (0, 0, 0, 0), norm_hw, scale_hw))
-    r = oracle.val_postprocess(g["cls"], g["box"], g["anchors"], scale_mode=mode, norm_hw=norm_hw, scale_hw=scale_hw)
+                             scaling=None if mode == 0 else (mode, shift, norm_hw, scale_hw))
+    r = oracle.val_postprocess(g["cls"], g["box"], g["anchors"], scale_mode=mode, shift=shift, norm_hw=norm_hw, scale_hw=scale_hw)
     _compare_validate(eng, res, 0, r, g["cls"].shape[1])
     D = len(g["classes_out"])                      # and against the reference's own function
     assert int(res.num_dets[0]) == D
@@ -647,17 +819,36 @@ def test_validation_batch_bit_exact(case):
         _compare_validate(eng, res, b, r, spec.K)
 
 
-def test_validation_dropin():
-    """bayes_od_rc_b200.validation_utils.post_process_predictions driven the way run_validation.py:143-147 does."""
+@pytest.mark.parametrize("name", ["val_kitti_k4", "val_coco_k8", "val_bdd_k8"])
+@pytest.mark.parametrize("host_anchors", ["numpy", "dlpack_cpu"])
+def test_validation_dropin(name, host_anchors):
+    """bayes_od_rc_b200.validation_utils.post_process_predictions driven the way run_validation.py:143-147 does:
+    the kitti, coco (constants.IMAGE_PADDING_KEY = 'paddings_applied') and bdd branches; `anchors` from the host as
+    numpy or as a CPU tensor that only speaks DLPack (a tf.data pipeline hands them over on the host)."""
     import torch
     from bayes_od_rc_b200 import validation_utils as fast
-    g = load_golden("val_kitti_k4")
+    assert fast.IMAGE_PADDING_KEY == "paddings_applied"                                 # src/core/constants.py:55
+    g = load_golden(name)
     meta = g["meta"]
     pred = {fast.ANCHORS_CLASS_PREDICTIONS_KEY: torch.from_numpy(g["cls"][None]).cuda(),
             fast.ANCHORS_BOX_PREDICTIONS_KEY: torch.from_numpy(g["box"][None]).cuda()}
     h, w = meta["image_shape"]
-    sample_dict = {fast.IMAGE_NORMALIZED_KEY: np.zeros((1, h, w, 3), np.float32), fast.ANCHORS_KEY: g["anchors"][None],
+    anchors = g["anchors"][None]
+    if host_anchors == "dlpack_cpu":
+        class OnlyDLPack:
+            def __init__(self, t):
+                self._t, self.shape = t, tuple(t.shape)
+
+            def __dlpack__(self, stream=None, **kw):
+                return self._t.__dlpack__()
+
+            def __dlpack_device__(self):
+                return self._t.__dlpack_device__()
+        anchors = OnlyDLPack(torch.from_numpy(np.ascontiguousarray(anchors)))
+    sample_dict = {fast.IMAGE_NORMALIZED_KEY: np.zeros((1, h, w, 3), np.float32), fast.ANCHORS_KEY: anchors,
                    fast.ORIGINAL_IM_SIZE_KEY: np.asarray([[meta["orig_size"][0], meta["orig_size"][1], 3]], np.int32)}
+    if meta["dataset_name"] == "coco":
+        sample_dict[fast.IMAGE_PADDING_KEY] = np.asarray([meta["padding"]], np.float32)
     output_classes, output_boxes = fast.post_process_predictions(sample_dict, pred, dataset_name=meta["dataset_name"])
     output_boxes = output_boxes.numpy(); output_classes = output_classes.numpy()       # run_validation.py:146-147
     assert output_classes.shape == g["classes_out"].shape and output_boxes.shape == g["corners_out"].shape

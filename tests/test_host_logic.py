@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bayesod.h but not exported"
         assert n in _cabi.SYMBOLS, f"{n} has no ctypes prototype"
-    assert lib.bod_abi_version() == 7
+    assert lib.bod_abi_version() == 8
     assert lib.bod_status_string(-5).decode().startswith("more survivors")
 
 

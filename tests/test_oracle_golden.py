@@ -130,8 +130,8 @@ def test_validation_postprocess(name):
     """validation_utils.post_process_predictions (validation_utils.py:10-77), executed verbatim over the shim,
     against the oracle restatement: same boxes selected in the same order, values within tolerance."""
     g = load_golden(name)
-    mode, norm_hw, scale_hw = val_scaling_of(g["meta"])
-    r = oracle.val_postprocess(g["cls"], g["box"], g["anchors"], scale_mode=mode, norm_hw=norm_hw, scale_hw=scale_hw)
+    mode, shift, norm_hw, scale_hw = val_scaling_of(g["meta"])
+    r = oracle.val_postprocess(g["cls"], g["box"], g["anchors"], scale_mode=mode, shift=shift, norm_hw=norm_hw, scale_hw=scale_hw)
     D = len(g["classes_out"])
     assert len(r.nms_indices) == D
     if D == 0:
