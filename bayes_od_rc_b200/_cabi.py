@@ -118,6 +118,11 @@ SYMBOLS = {
     "bod_pdq_losses": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 8),
     "bod_pdq_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bod_pdq_bvn_cdf": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bod_entropies": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bod_mu_error": (C.c_int, [C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                               C.c_void_p]),
+    "bod_uncertainty_last_error": (C.c_char_p, []),
     "bod_generate_anchors": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

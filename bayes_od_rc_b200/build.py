@@ -29,6 +29,7 @@ UNITS = {
     "bod_api.cu": ["-fmad=false"],
     "bod_io.cu": [],                          # host-only: npy / json / txt writers
     "kp_pdq.cu": [],                          # PDQ heat maps and loss sums: binary64 CDF, tolerance-checked
+    "ku_uncertainty.cu": ["-fmad=false"],     # entropies + MUE curve (binary64 like the reference's numpy)
 }
 HEADERS = ["bod_common.cuh", "bod_kernels.h", os.path.join("..", "..", "include", "bayesod.h")]
 

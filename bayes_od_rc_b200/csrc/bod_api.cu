@@ -700,8 +700,11 @@ extern "C" int bod_wait_results(bod_ctx* c, void* cuda_stream) {
     if (!c) return BOD_ERR_INVALID;
     if (!c->ran) return fail(c, BOD_ERR_STATE, "no bod_run has been issued on this context");
     CU(c, cudaSetDevice(c->device));
-    Lane& L = c->lane[c->cur];
-    if (c->nlanes > 1 && L.tail_pending) CU(c, cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(cuda_stream), L.tail_done, 0));
+    // every run issued so far (each lane's last one), together with the copies bod_fetch_async put behind them
+    if (c->nlanes > 1)
+        for (int l = 0; l < c->nlanes; ++l)
+            if (c->lane[l].tail_pending)
+                CU(c, cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(cuda_stream), c->lane[l].tail_done, 0));
     return BOD_OK;
 }
 

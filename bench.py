@@ -46,6 +46,8 @@ WORKLOADS = {
     "stress_b16_n40_k11": dict(im_h=720, im_w=1280, N=40, K=11, B=16, use_full_covar=True, config_id=5,
                                spec=dict(g_min=80, g_max=120, fg_iou=0.2, fg_logit=1.0, bg_logit_for_fg=0.0, stray_frac=0.02),
                                score_threshold=0.01, pre_nms_top_k=10000),
+    # BASELINE.json config 4, second shape: raw KITTI frames (375x1242, A = 88 398), no resize => no rescale
+    "kitti_raw_b64_n20_k4": dict(im_h=375, im_w=1242, N=20, K=4, B=64, use_full_covar=True, config_id=6),
     # BASELINE.json config 1 shape on the GPU: one image per call, as run_inference.py drives the path (:68, :137-149)
     "bdd_covar_b1_k8": dict(im_h=720, im_w=1280, N=10, K=8, B=1, use_full_covar=True, config_id=1),
     "tiny": dict(im_h=192, im_w=320, N=10, K=8, B=4, use_full_covar=True, config_id=9),
@@ -125,6 +127,15 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(s[3] for s in sel), "samples": len(sel), "note": note}
 
 
+def workload_string(name, wl, A):
+    """config.workload: the same string from both arms (ours / --impl reference)."""
+    extra = ""
+    if wl.get("pre_nms_top_k") or wl.get("score_threshold") is not None and wl.get("score_threshold", float("-inf")) > float("-inf"):
+        extra = f" score_threshold={wl.get('score_threshold')} pre_nms_top_k={wl.get('pre_nms_top_k', 0)}"
+    return (f"{name}: {wl['im_h']}x{wl['im_w']} A={A} N={wl['N']} K={wl['K']} B={wl['B']} images per step and GPU "
+            f"use_full_covar={wl['use_full_covar']} cov=[N,A,4,4] philox-sampler seed=1234{extra}")
+
+
 def bytes_min_per_image(N, A, K, S_mean, D_mean, cov_width, injected_counts=False, anchors_gathered=True):
     """SURVEY.md §8(d) / BASELINE.md §3 contract figure."""
     b = 4 * N * A * K + 4 * N * S_mean * (4 + cov_width) + (16 * S_mean if anchors_gathered else 0)
@@ -150,6 +161,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the bit-for-bit check of timed results against the oracle")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (global batch split over the GPUs)")
+    ap.add_argument("--no-stream-fetch", action="store_true", help="do not copy every step's result blocks to the host")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -188,6 +202,7 @@ def main():
 
     wl = dict(WORKLOADS[args.workload])
     B = args.batch or wl["B"]
+    wl["B"] = B
     N, K = wl["N"], wl["K"]
     if args.pipeline == 0:
         args.pipeline = min(16, max(4, 64 // B))
@@ -214,8 +229,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    stream_fetch = not args.no_stream_fetch
+
     def step():
+        # one pass of the path over the batch; every step's padded result blocks (576 KB at B = 32) are copied to
+        # pinned host memory behind its own tail (bod_fetch_async), as a streaming consumer would take them
         eng.run(cls, box, cov, anchors, None, stream=stream.cuda_stream)
+        if stream_fetch:
+            eng.fetch_async()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -236,7 +257,8 @@ def main():
     t1 = time.perf_counter()
     elapsed_ms = ev0.elapsed_time(ev1)
     stage_sum, stage_runs = eng.stage_ms_accum()
-    res = eng.fetch()
+    res = eng.collect(eng.last_ticket) if stream_fetch else eng.fetch()
+    d2h_stream = int(sum(v.nbytes for v in eng._h.values())) if stream_fetch else 0
     S_mean = float(res.num_survivors.mean())
     D_mean = float(res.num_dets.mean())
     launches_per_step = eng.launch_count
@@ -280,13 +302,64 @@ def main():
         e2e = dict(seconds=te, steps=n_e2e, h2d=tr["h2d_copied"] + tr["h2d_gathered"], d2h=tr["d2h"],
                    h2d_copied=tr["h2d_copied"], h2d_gathered=tr["h2d_gathered"],
                    host_bytes=(cls.numel() + box.numel() + cov.numel() + anchors.numel()) * 4)
+    # ---- strong scaling: the workload's batch as ONE global batch split over the GPUs (BASELINE.json configs 3 / 4:
+    # "batch 32 ... image-sharded across 8xB200"): B/world images per GPU and step, streamed through the pipelined context
+    strong = None
+    if not args.no_strong and world > 1 and B % world == 0:
+        Bg = B // world
+        first_s = rank * Bg
+        sb = synthetic.make_batch(spec, Bg, device=dev, with_counts=False, first_image_id=first_s)
+        import dataclasses
+        lanes_s = min(16, max(4, 64 // Bg))
+        eng_s = BayesODEngine(Bg, N, A, K, dataclasses.replace(cfg, image_id_base=first_s, pipeline_depth=lanes_s), device=local_rank)
+
+        def step_s():
+            eng_s.run(sb["cls"], sb["box"], sb["cov"], sb["anchors"], None, stream=stream.cuda_stream)
+            if stream_fetch:
+                eng_s.fetch_async()
+        for _ in range(max(args.warmup, 3) + lanes_s):
+            step_s()
+        barrier()
+        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        z0.record(stream)
+        for _ in range(args.steps):
+            step_s()
+        eng_s.wait_results(stream.cuda_stream)
+        z1.record(stream)
+        barrier()
+        strong = dict(ms=z0.elapsed_time(z1), images_per_gpu=Bg, lanes=lanes_s)
+        eng_s.close()
+        del sb
+
+    # ---- the timed results against the oracle, bit for bit (outside every timed region) ----
+    verification = None
+    if not args.no_verify and rank == 0:
+        verification = verify_against_oracle(cls, box, cov, anchors, wl, cfg, res, first_image, N, A, K, local_rank)
+
+    # ---- what a bare pinned host->device copy reaches on this box (the e2e leg's ceiling) ----
+    h2d_probe = None
+    if e2e is not None:
+        n_probe = min(cls.numel(), 256 << 20)
+        src = h_cls.view(-1)[:n_probe]
+        dst = torch.empty(n_probe, dtype=torch.float32, device=dev)
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        p1.record(); torch.cuda.synchronize()
+        h2d_probe = 3 * n_probe * 4 / (p0.elapsed_time(p1) * 1e-3) / 1e9
+        del dst
     sampler.stop()
 
     # ---- max over ranks ----
     if world > 1:
-        tt = torch.tensor([elapsed_ms, e2e["seconds"] if e2e else 0.0], device=dev, dtype=torch.float64)
+        tt = torch.tensor([elapsed_ms, e2e["seconds"] if e2e else 0.0, strong["ms"] if strong else 0.0], device=dev,
+                          dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms = float(tt[0]); e2e_seconds = float(tt[1])
+        if strong:
+            strong["ms"] = float(tt[2])
         ss = torch.tensor([S_mean, D_mean], device=dev, dtype=torch.float64)
         dist.all_reduce(ss, op=dist.ReduceOp.SUM)
         S_mean, D_mean = float(ss[0]) / world, float(ss[1]) / world
@@ -315,11 +388,12 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['im_h']}x{wl['im_w']} A={A} N={N} K={K} B={B}/GPU "
-                                   f"use_full_covar={wl['use_full_covar']} cov=[N,A,4,4] philox-sampler seed=1234",
+            "config": {"workload": workload_string(args.workload, wl, A),
                        "images_per_gpu": B, "global_batch": B * world, "parallelism": f"image-shard x{world}, no collective",
                        "l2": "inputs (%.2f GB per step) larger than L2" % ((cls.numel() + box.numel() + cov.numel()) * 4 / 1e9),
                        "pipeline_depth": args.pipeline,
+                       "results": ("every step's padded result blocks copied to pinned host memory behind its tail "
+                                   f"(bod_fetch_async, {d2h_stream} bytes per step)") if stream_fetch else "left on the device",
                        "mean_survivors": round(S_mean, 1), "mean_dets": round(D_mean, 1),
                        "bytes_min_per_image": int(bmin), "path_roofline_frac": round(path_frac, 4)},
             "gpu_launches": launches_per_step * args.steps,
@@ -330,6 +404,24 @@ def main():
                          "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": round(k1_ms, 4)},
             "clocks": sampler.summary(t0, t1),
         }
+        if verification is not None:
+            line["verified"] = bool(verification["ok"])
+            line["verification"] = verification
+        # weak scaling is the line's `value`; the strong block is the same workload's batch as one global batch
+        if strong:
+            sv = B * args.steps / (strong["ms"] * 1e-3)
+            line["strong"] = {"global_batch": B, "images_per_gpu": strong["images_per_gpu"], "n_gpus": world,
+                              "value": round(sv, 1), "unit": "images/s", "ms_per_step": round(strong["ms"] / args.steps, 4),
+                              "pipeline_depth": strong["lanes"],
+                              "one_gpu_reference": round(value / world, 1),
+                              "speedup_vs_one_gpu": round(sv / (value / world), 3),
+                              "note": "one_gpu_reference = this run's per-GPU throughput at the full batch per GPU (the weak-"
+                                      "scaling `value` / n_gpus), i.e. what one GPU does with the whole global batch"}
+        elif world == 1 and not args.no_strong:
+            line["strong"] = {"global_batch": B, "images_per_gpu": B, "n_gpus": 1, "value": round(value, 1), "unit": "images/s",
+                              "ms_per_step": round(elapsed_ms / args.steps, 4), "pipeline_depth": args.pipeline,
+                              "one_gpu_reference": round(value, 1), "speedup_vs_one_gpu": 1.0,
+                              "note": "one GPU: the strong- and weak-scaling runs are the same run"}
         if serial:
             line["serial"] = serial           # pipeline_depth = 1: whole steps back to back, stage times undisturbed
             k1_alone = serial["stage_ms"]["moments_filter"]
@@ -344,6 +436,9 @@ def main():
                            "d2h_bytes_per_step": int(e2e["d2h"]), "steps": e2e["steps"],
                            "h2d_copied": int(e2e["h2d_copied"]), "h2d_gathered_in_place": int(e2e["h2d_gathered"]),
                            "host_input_bytes": int(e2e["host_bytes"]), "host_placement": numa_note,
+                           "h2d_gbs": round(e2e["h2d_copied"] * e2e["steps"] / e2e["seconds"] / 1e9, 1),
+                           "h2d_probe_gbs": round(h2d_probe, 1) if h2d_probe else None,
+                           "pcie_frac": round(e2e["h2d_copied"] * e2e["steps"] / e2e["seconds"] / 1e9 / h2d_probe, 3) if h2d_probe else None,
                            "api": "bod_run_host: pinned host buffers -> padded host result blocks; cls is copied in "
                                   "image chunks overlapped with compute, box/cov rows of the survivors are "
                                   "gathered in place from pinned memory"}
@@ -354,6 +449,55 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def verify_against_oracle(cls, box, cov, anchors, wl, cfg, res, first_image, N, A, K, device, n=2):
+    """Images 0..n-1 of the timed batch against the oracle, bit for bit (sampler included): a second context
+    that keeps the mean probabilities and the sampled counts re-runs those images; its Philox counts must equal
+    the oracle's restatement on the kernel's own probabilities (the one tolerance-checked quantity of the path),
+    the oracle then runs the rest of the path on those counts, and BOTH the re-run and the timed run's last
+    results must equal it exactly."""
+    import dataclasses
+    import numpy as np
+    import oracle
+    from bayes_od_rc_b200.engine import BayesODEngine
+    n = min(n, cls.shape[0])
+    out = {"ok": False, "images": n, "checked": ["num_dets", "nms_indices", "centre_scores", "means", "covs", "cat_param", "cat_count"]}
+    try:
+        engv = BayesODEngine(n, N, A, K, dataclasses.replace(cfg, pipeline_depth=1, emit_probs=True, image_id_base=first_image),
+                             device=device)
+        engv.run(cls[:n].contiguous(), box[:n].contiguous(), cov[:n].contiguous(), anchors, None)
+        rv = engv.fetch()
+        oc = _oracle_cfg(wl, first_image)
+        a = anchors.cpu().numpy()
+        bad = []
+        for b in range(n):
+            counts = engv.sampled_counts(b)
+            ref_counts = oracle.philox_counts(engv.probs(b), 30, 1234, first_image + b)
+            if not np.array_equal(counts, ref_counts):
+                bad.append(f"image {b}: sampled counts")
+            r = oracle.run_image(oc, cls[b].cpu().numpy(), box[b].cpu().numpy(), cov[b].cpu().numpy(), a, counts,
+                                 image_id=b, with_probs=False)
+            D = len(r.nms_indices)
+            for name, got in (("re-run", rv), ("timed run", res)):
+                pairs = [("num_dets", int(got.num_dets[b]), D), ("nms_indices", got.nms_indices[b, :D], r.nms_indices),
+                         ("centre_scores", got.centre_scores[b, :D], r.nms_scores), ("means", got.means[b, :D], r.final_means),
+                         ("covs", got.covs[b, :D], r.final_covs), ("cat_param", got.cat_param[b, :D], r.final_scores),
+                         ("cat_count", got.cat_count[b, :D], r.final_counts)]
+                for key, x, y in pairs:
+                    x = np.asarray(x); y = np.asarray(y)
+                    if x.shape != y.shape or x.tobytes() != y.tobytes():
+                        bad.append(f"image {b}, {name}: {key}")
+            out.setdefault("dets", []).append(D)
+            out.setdefault("survivors", []).append(int(len(r.keep)))
+        engv.close()
+        out["ok"] = not bad
+        out["mismatches"] = bad
+        out["how"] = ("oracle/bayesod_oracle.c on the same inputs; Philox counts checked against the restatement on the kernel's "
+                      "own mean probabilities; every fused output compared byte for byte")
+    except Exception as e:  # pragma: no cover
+        out["error"] = repr(e)
+    return out
 
 
 def _oracle_cfg(wl, image_id_base):
@@ -398,31 +542,45 @@ def reference_arm(args, rank):
     import oracle
     from bayes_od_rc_b200 import synthetic
     wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["B"] = args.batch
     N, K = wl["N"], wl["K"]
     cores = os.cpu_count() or 1
-    n = args.cpu_sample or min(wl["B"], max(4, min(cores, 32)))
+    n = wl["B"]                                   # one step = the workload's batch, as in the other arm
     threads = min(cores, n)
     spec = synthetic.SceneSpec(im_h=wl["im_h"], im_w=wl["im_w"], N=N, K=K, config_id=wl["config_id"], **wl.get("spec", {}))
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    batch = synthetic.to_numpy(synthetic.make_batch(spec, n, device=dev, with_counts=False))
+    # the sample held in host memory: up to 16 distinct images, repeated to fill a step (the CPU cost per image is what
+    # is measured; 32 BDD-shape images are 6.9 GB of host memory, 64 KITTI ones 20 GB)
+    n_distinct = min(n, 16)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, n_distinct, device=dev, with_counts=False))
     oc = _oracle_cfg(wl, 0)
     A = batch["anchors"].shape[0]
-    run = lambda: oracle.run_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], None, nthreads=threads)   # noqa: E731
-    for _ in range(min(args.warmup, 1)):
+    reps = -(-n // n_distinct)
+
+    def run():
+        done = 0
+        for _ in range(reps):
+            m = min(n_distinct, n - done)
+            oracle.run_batch(oc, batch["cls"][:m], batch["box"][:m], batch["cov"][:m], batch["anchors"], None,
+                             nthreads=min(threads, m))
+            done += m
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
         run()
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    # exactly --steps steps unless that would take more than ~2 minutes (then as many as fit; the line says how many)
+    steps, t0 = 0, time.perf_counter()
+    while steps < max(1, args.steps) and (steps < 2 or time.perf_counter() - t0 < 120.0):
         run()
+        steps += 1
     dt = time.perf_counter() - t0
     value = n * steps / dt
     line = {"impl": "reference", "metric": "BayesOD images/s (head out -> fused dets)", "value": round(value, 3),
-            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['im_h']}x{wl['im_w']} A={A} N={N} K={K} "
-                                   f"use_full_covar={wl['use_full_covar']} cov=[N,A,4,4] philox-sampler seed=1234",
-                       "images_per_step": n},
+            "config": {"workload": workload_string(args.workload, wl, A), "images_per_step": n,
+                       "distinct_images": n_distinct},
             "cpu_baseline": {"value": round(value, 3), "unit": "images/s", "cores": threads, "kind": "port",
                              "sample": f"{n} images per step x {steps} steps; the reference path is Python/TF (not "
                                        f"installable offline), timed: its C oracle port on {threads} host threads"},

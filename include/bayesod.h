@@ -187,7 +187,8 @@ int bod_set_sampler_stream(bod_ctx* ctx, uint64_t seed, uint32_t image_id_base);
 int bod_set_image_scale(bod_ctx* ctx, float scale_v, float scale_u);
 
 /* Make `cuda_stream` wait (on the device, without blocking the host) until the
- * results of the last bod_run are complete.  Only needed with pipeline_depth >= 2
+ * results of every bod_run issued so far (and the copies bod_fetch_async enqueued
+ * behind them) are complete.  Only needed with pipeline_depth >= 2
  * by consumers that read bod_device_results_of on their own stream; a no-op
  * otherwise (the run is already ordered on the caller's stream). */
 int bod_wait_results(bod_ctx* ctx, void* cuda_stream);
@@ -394,6 +395,32 @@ int bod_pdq_losses(bod_pdq_ctx* ctx, int32_t n_images, const int32_t* det_offset
 int bod_pdq_last_ms(const bod_pdq_ctx* ctx, float ms[3], int64_t* table_floats, int64_t* launches);
 /* The device's bivariate normal CDF P(X <= h, Y <= k; r) on n points (test hook). */
 int bod_pdq_bvn_cdf(bod_pdq_ctx* ctx, int32_t n, const double* h, const double* k, const double* r, double* out);
+
+/*
+ * Uncertainty scoring of fused detections (second half): what
+ * src/retina_net/offline_eval/{bdd,kitti}/compute_uncertainty_error.py:91-132 computes in Python
+ * loops over every detection of the validation set.  Host arrays in and out.
+ *
+ * bod_entropies: evaluation_utils_2d.py:280-285 compute_gaussian_entropy_np of n covariances
+ *   covs [n,4,4] f32 -> gaussian_out [n] f64 (determinant, np.round(., 5) + 1e-12 and log in binary32 as numpy
+ *   does on binary32 arrays, then the binary64 constant is added), and
+ *   :288-290 compute_categorical_entropy_np of n parameter vectors cat_params [n,K] f32 ->
+ *   categorical_out [n] f32.  Either input may be NULL.
+ * bod_mu_error: evaluation_utils_2d.py:129-212 compute_mu_error for the predictions of ONE category:
+ *   pred_boxes [n,4] f64 [x1,y1,x2,y2], pred_image [n] (image ids 0 .. n_images-1), the ranking
+ *   `order` [n] = stable arg-sort of the entropy scores (ascending; rank -> prediction), by_image /
+ *   img_off = the ranks grouped by image (img_off [n_images+1]; inside an image ascending),
+ *   ground truth as CSR rows per image (gt_off [n_images+1], gt_boxes [G,4] f64), IoU thresholds.
+ *   Outputs: min over the whole [n, n_thr] uncertainty-error matrix, its first flat arg-min (the
+ *   reference indexes its score list with it, :211-213), and optionally (TP, FP) totals per threshold.
+ */
+int bod_entropies(int device, int32_t n, int32_t K, const float* covs, const float* cat_params,
+                  double* gaussian_out, float* categorical_out);
+int bod_mu_error(int device, int32_t n, const double* pred_boxes, const int32_t* pred_image, const int32_t* order,
+                 int32_t n_images, const int32_t* img_off, const int32_t* by_image,
+                 const int32_t* gt_off, const double* gt_boxes, int32_t n_thr, const double* thresholds,
+                 double* min_u_error, int64_t* argmin_flat, double* totals);
+const char* bod_uncertainty_last_error(void);
 
 /* FPN anchors exactly as fpn_anchor_generator.py:21-59 produces them for levels
  * 3..7, 3 aspect ratios x 3 scales, concatenated P3->P7

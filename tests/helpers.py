@@ -20,7 +20,25 @@ def _all_cases():
 
 def golden_cases():
     """Fixtures of bayes_od_inference / bayes_od_clustering (inference_utils.py)."""
-    return [c for c in _all_cases() if not c.startswith(("val_", "pdq_", "writers_"))]      # incl. the full-size "full_*" ones
+    return [c for c in _all_cases() if not c.startswith(("val_", "pdq_", "writers_", "mue_"))]      # incl. the full-size "full_*" ones
+
+
+def mue_golden_cases():
+    """Fixtures of evaluation_utils_2d.py's entropy / MUE scoring (tests/golden/make_mue_golden.py)."""
+    return [c for c in _all_cases() if c.startswith("mue_")]
+
+
+def load_mue_golden(name):
+    """-> dict with the arrays, meta, results and the gt / pred dict lists the reference functions take."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files if k not in ("meta", "results")}
+    g["meta"] = json.loads(str(z["meta"])); g["results"] = json.loads(str(z["results"]))
+    cats = g["meta"]["categories"]
+    g["gt"] = [dict(name=f"frame_{int(i):04d}", category=cats[int(c)], bbox=[float(v) for v in b])
+               for i, c, b in zip(g["gt_image"], g["gt_cat"], g["gt_box"])]
+    g["pred"] = [dict(name=f"frame_{int(i):04d}", category=cats[int(c)], bbox=[float(v) for v in b])
+                 for i, c, b in zip(g["pred_image"], g["pred_cat"], g["pred_box"])]
+    return g
 
 
 def pdq_golden_cases():

@@ -658,6 +658,60 @@ def test_validation_random(seed):
         _compare_validate(eng, res, b, oracle.val_postprocess(cls[b], box[b], batch["anchors"], **okw), K)
 
 
+FULL_BATCHES = {
+    # BASELINE.json configurations at full size, every image of the batch bit for bit against the oracle
+    # name: (SceneSpec kwargs, OracleConfig kwargs, B, pipeline_depth)
+    "bdd_covar_b32_k11": (dict(N=10, K=11, config_id=3), dict(), 32, 1),                      # the benchmarked configuration
+    "bdd_covar_b32_k11_pipelined": (dict(N=10, K=11, config_id=3), dict(), 32, 4),
+    "kitti_512x1696_b8_n20_k4": (dict(im_h=512, im_w=1696, N=20, K=4, config_id=4),
+                                 dict(scale_v=375 / 512, scale_u=1242 / 1696), 8, 1),
+    "kitti_raw_375x1242_b8_n20_k4": (dict(im_h=375, im_w=1242, N=20, K=4, config_id=6), dict(), 8, 1),
+    "bdd_kendall_b8_k8": (dict(N=10, K=8, config_id=2), dict(use_full_covar=False), 8, 1),
+    "stress_b4_n40_k11_topk": (dict(N=40, K=11, config_id=5, g_min=80, g_max=120, fg_iou=0.2, fg_logit=1.0, bg_logit_for_fg=0.0,
+                                    stray_frac=0.02), dict(score_threshold=0.01, pre_nms_top_k=10000), 4, 1),
+}
+
+
+@pytest.mark.parametrize("sampler", ["injected", "philox"])
+@pytest.mark.parametrize("name", sorted(FULL_BATCHES))
+def test_full_size_batches_bit_exact(name, sampler):
+    """Full-size batches of BASELINE.json's configurations (the benchmarked B = 32, K = 11, full covariance among
+    them): every image's padded result block equals the oracle's, with injected counts and with the in-kernel
+    Philox sampler (its counts are checked against the restatement on the kernel's own mean probabilities, the
+    oracle then runs on those counts).  Inputs are generated on the device by the seeded generator."""
+    import torch
+    from gpu_common import engine_config_from_oracle
+    from bayes_od_rc_b200.engine import BayesODEngine
+    spec_kw, oc_kw, B, depth = FULL_BATCHES[name]
+    if sampler == "philox" and depth > 1:
+        pytest.skip("one sampler case per shape")
+    spec = synthetic.SceneSpec(**spec_kw)
+    batch = synthetic.make_batch(spec, B, device="cuda", with_counts=(sampler == "injected"), first_image_id=40)
+    N, A, K = batch["cls"].shape[1:]
+    oc = oracle.OracleConfig(seed=4321, image_id_base=40, **oc_kw)
+    cap = min(A, 49152)
+    eng = BayesODEngine(B, N, A, K, engine_config_from_oracle(oc, pipeline_depth=depth, emit_probs=(sampler == "philox"),
+                                                              max_survivors=cap))
+    counts = batch["counts"] if sampler == "injected" else None
+    for _ in range(3 if depth > 1 else 1):                  # pipelined: stream path, then graph replays
+        eng.run(batch["cls"], batch["box"], batch["cov"], batch["anchors"], counts)
+    res = eng.fetch()
+    if sampler == "philox":
+        cnt = np.stack([eng.sampled_counts(b) for b in range(B)])
+        for b in range(0, B, max(1, B // 4)):               # the restatement is slow in Python: a quarter of the images
+            assert_bit_equal(cnt[b], oracle.philox_counts(eng.probs(b), 30, 4321, 40 + b), f"image {b}: philox counts")
+    else:
+        cnt = batch["counts"].cpu().numpy()
+    h = {k: batch[k].cpu().numpy() for k in ("cls", "box", "cov", "anchors")}
+    ref = oracle.run_batch(oc, h["cls"], h["box"], h["cov"], h["anchors"], cnt, nthreads=16)
+    assert ref["num_survivors"].min() > 1000
+    if "topk" in name:
+        assert (ref["num_survivors"] == 10000).all()
+    for k in ("num_survivors", "num_dets", "nms_indices", "centre_anchor_idx", "means", "cat_param", "cat_count"):
+        assert_bit_equal(getattr(res, k), ref[k], f"{name}: {k}")
+    assert_bit_equal(res.covs.reshape(B, -1, 16), ref["covs"], f"{name}: covs")
+
+
 def test_full_size_batch_properties():
     """The bench workload at full size (8 BDD-shape images, N = 10, K = 11, Philox sampler) through
     size-independent properties: survivors ascending, centres unique and in selection-score order, every
