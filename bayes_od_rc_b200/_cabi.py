@@ -87,6 +87,8 @@ SYMBOLS = {
     "bod_fetch": (C.c_int, [C.c_void_p, C.POINTER(BodHostResults)]),
     "bod_device_results_of": (C.c_int, [C.c_void_p, C.POINTER(BodDeviceResults)]),
     "bod_last_ticket": (C.c_int64, [C.c_void_p]),
+    "bod_result_block_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bod_fetch_block_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "bod_fetch_async": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(BodHostResults)]),
     "bod_ticket_wait": (C.c_int, [C.c_void_p, C.c_int64]),
     "bod_device_results_at": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(BodDeviceResults)]),

@@ -34,6 +34,7 @@ struct Lane {
     float* out_means = nullptr; float* out_covs = nullptr; float* out_param = nullptr; float* out_count = nullptr;
     cudaEvent_t head_done = nullptr, tail_done = nullptr;
     cudaStream_t tail_stream = nullptr;   // the lane's own tail stream: tails of different lanes run concurrently
+    uint32_t* tile_ticket = nullptr;      // the lane's own ticket counter of the moments kernel's tile scheduler
     bool tail_pending = false;        // a tail has been issued on this lane (tail_done is meaningful)
     // CUDA-graph replay of a whole run on this lane (pipelined contexts; see issue_run)
     cudaGraph_t graph[2] = {nullptr, nullptr}; cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // head, tail
@@ -44,6 +45,9 @@ struct Lane {
     cudaEvent_t fetch_done = nullptr;                 // after the copies of the lane's last bod_fetch_async
     bool fetch_pending = false;
     int32_t* h_status = nullptr;                      // pinned: the context's status word as of that fetch
+    unsigned char* block = nullptr;                   // the lane's result arrays are one contiguous block (bod_result_block_layout)
+    int32_t* block_status = nullptr;                  // its last word: the context's status as of the end of the lane's last tail
+    const int32_t* h_block_status = nullptr;          // where that word lands on the host (last bod_fetch_block_async)
     cudaEvent_t k1_begin = nullptr, k1_end = nullptr; // timing of the lane's last replayed moments kernel
     bool k1_timed = false;
 };
@@ -74,7 +78,6 @@ struct bod_ctx {
     unsigned long long* pf_key = nullptr; unsigned long long* pf_thr = nullptr;
     int32_t* pf_anchor = nullptr; float* pf_counts = nullptr; int32_t* pf_tile_count = nullptr;
     bool prefilter = false;
-    uint32_t* ticket = nullptr;       // K1's dynamic tile scheduler: ticket counter, zeroed before every launch
     float* probs = nullptr; float* sampled = nullptr;
     int pstride = 0, pw_rows = 0, k3_rows = 0, k3_threads = 512, k3_force_big = 0;
     // device staging of host inputs (bod_run_host), allocated on first use
@@ -101,8 +104,11 @@ struct bod_ctx {
 #endif
     bool k2_on_tail = true;           // pipelined contexts: K2 rides with the tail (see run_range); BOD_K2_TAIL=0 keeps it on the head
     bool use_graphs = true;           // pipelined contexts replay each lane's run as a CUDA graph (BOD_GRAPHS=0: stream launches)
+    bool force_graphs = false;        // BOD_GRAPHS=2: also for short runs
     double g_k1_ms = 0.0; long long g_k1_runs = 0;    // moments-kernel time of replayed runs (harvested when a lane is reused)
     long long next_ticket = 0;        // tickets of issued runs: 1, 2, 3, ...
+    int64_t block_off[10] = {0};      // result block: offsets of num_dets, num_survivors, means, covs, cat_param, cat_count,
+    int64_t block_bytes = 0;          //   nms_indices, centre_anchor_idx, centre_scores, status; total size
     int k3_psm_max = -1, k3_seg_cap = -1;   // BOD_K3_PSM_MAX / BOD_K3_SEGCAP (tests: reach the spill rows / the piecewise pass B on small inputs)
 };
 
@@ -215,7 +221,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     std::vector<Piece> pieces;
 #define TAKE(ptr, bytes) pieces.push_back(Piece{reinterpret_cast<void**>(&ptr), take(bytes)})
     TAKE(c->status, 256);
-    TAKE(c->ticket, 256);
+    for (int l = 0; l < bod_ctx::kMaxLanes; ++l) TAKE(c->lane[l].tile_ticket, 256);
     c->prefilter = cfg->pre_nms_top_k > 0 || cfg->score_threshold > -INFINITY;
     if (c->prefilter) {
         const size_t slots = (size_t)c->tiles * kTileAnchors;
@@ -224,13 +230,20 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
         TAKE(c->pf_tile_count, (size_t)B * c->tiles * 4);
     }
     if (cfg->emit_probs) { TAKE(c->probs, (size_t)B * A * K * 4); TAKE(c->sampled, (size_t)B * A * K * 4); }
+    {
+        // every lane's result arrays in one block, so that a run's results leave the device in ONE copy
+        const size_t sz[10] = {(size_t)B * 4, (size_t)B * 4, (size_t)B * D * 16, (size_t)B * D * 64, (size_t)B * D * K * 4,
+                               (size_t)B * D * K * 4, (size_t)B * D * 4, (size_t)B * D * 4, (size_t)B * D * 4, 16};
+        int64_t o = 0;
+        for (int i = 0; i < 10; ++i) { c->block_off[i] = o; o += (int64_t)((sz[i] + 15) & ~(size_t)15); }
+        c->block_bytes = o;
+    }
     for (int l = 0; l < c->nlanes; ++l) {
         Lane& L = c->lane[l];
         TAKE(L.slot_anchor, (size_t)B * c->tiles * kTileAnchors * 4);
         TAKE(L.slot_counts, (size_t)B * c->tiles * kTileAnchors * K * 4);
         TAKE(L.tile_count, (size_t)B * c->tiles * 4);
         TAKE(L.tile_off, (size_t)B * (c->tiles + 1) * 4);
-        TAKE(L.num_survivors, (size_t)B * 4);
         TAKE(L.surv_anchor, B * cap * 4);
         TAKE(L.cnt_post, B * cap * K * 4);
         TAKE(L.mu_post, B * cap * 16);
@@ -243,15 +256,8 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
         TAKE(L.begin, B * cap * 4);
         TAKE(L.pend, B * cap * kPendStride * 4);
         TAKE(L.pw, (size_t)B * c->pw_rows * c->pstride * 4);
-        TAKE(L.nms_idx, B * D * 4);
-        TAKE(L.nms_score, B * D * 4);
-        TAKE(L.centre_anchor, B * D * 4);
-        TAKE(L.num_dets, (size_t)B * 4);
+        TAKE(L.block, (size_t)c->block_bytes);
         TAKE(L.member, B * D * c->words * 4);
-        TAKE(L.out_means, B * D * 16);
-        TAKE(L.out_covs, B * D * 64);
-        TAKE(L.out_param, B * D * K * 4);
-        TAKE(L.out_count, B * D * K * 4);
     }
 #undef TAKE
     c->slab_bytes = off;
@@ -261,6 +267,15 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
         cudaGetLastError(); delete c; return BOD_ERR_NOMEM;
     }
     for (auto& p : pieces) *p.p = c->slab + p.o;
+    for (int l = 0; l < c->nlanes; ++l) {
+        Lane& L = c->lane[l];
+        unsigned char* b = L.block;
+        L.num_dets = reinterpret_cast<int32_t*>(b + c->block_off[0]); L.num_survivors = reinterpret_cast<int32_t*>(b + c->block_off[1]);
+        L.out_means = reinterpret_cast<float*>(b + c->block_off[2]); L.out_covs = reinterpret_cast<float*>(b + c->block_off[3]);
+        L.out_param = reinterpret_cast<float*>(b + c->block_off[4]); L.out_count = reinterpret_cast<float*>(b + c->block_off[5]);
+        L.nms_idx = reinterpret_cast<int32_t*>(b + c->block_off[6]); L.centre_anchor = reinterpret_cast<int32_t*>(b + c->block_off[7]);
+        L.nms_score = reinterpret_cast<float*>(b + c->block_off[8]); L.block_status = reinterpret_cast<int32_t*>(b + c->block_off[9]);
+    }
     cudaMemset(c->slab, 0, off);
     cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
@@ -284,7 +299,7 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
 #endif
     c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
     if (const char* d = getenv("BOD_K2_TAIL")) c->k2_on_tail = atoi(d) != 0;
-    if (const char* d = getenv("BOD_GRAPHS")) c->use_graphs = atoi(d) != 0;
+    if (const char* d = getenv("BOD_GRAPHS")) { c->use_graphs = atoi(d) != 0; c->force_graphs = atoi(d) >= 2; }
     for (int l = 0; l < c->nlanes; ++l) {
         cudaEventCreate(&c->lane[l].k1_begin); cudaEventCreate(&c->lane[l].k1_end);
         cudaEventCreateWithFlags(&c->lane[l].fetch_done, cudaEventDisableTiming);
@@ -364,8 +379,8 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     // rewrite num_survivors under a running tail.
     if (hs != ts && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
     const bool do_head = !gh || gh->phase == 1, do_tail = !gh || gh->phase == 2;   // graph capture: one half at a time
-    // the moments kernel's tile scheduler counts tickets from zero (its launches never overlap within a context)
-    if (do_head) CU(c, cudaMemsetAsync(c->ticket, 0, sizeof(uint32_t), hs));
+    // (the moments kernel's tile scheduler counts tickets from zero: the slab starts zeroed and every launch puts
+    // the counter back itself; launches of a context never overlap)
     if (gh && do_head) CU(c, cudaEventRecordWithFlags(gh->k1_begin, hs, cudaEventRecordExternal));
     if (record) CU(c, cudaEventRecord(c->ev[0], hs));
     K1Args k1{};
@@ -380,7 +395,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     k1.debug = c->k1_debug;
 #endif
     k1.leave_room = (hs != ts || gh) ? 1 : 0;
-    k1.ticket = c->ticket; k1.ticket_base = 0u;
+    k1.ticket = L.tile_ticket; k1.ticket_base = 0u;
     if (do_head) CU(c, launch_k1(k1, hs));
     if (gh && do_head) { CU(c, cudaEventRecordWithFlags(gh->k1_end, hs, cudaEventRecordExternal)); *gh->k1_out = k1; }
     if (record) CU(c, cudaEventRecord(c->ev[1], hs));
@@ -419,12 +434,18 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     // onwards) rides with the tail and the head stream carries K1 back to back (B = 8, K = 8: 69.0 -> 73.8 k images/s).
     // Long ones lose ~1 % that way (the soft-NMS CTAs then find no free SM at the kernel boundary), so they keep the scan.
     static const int scan_tail_env = getenv("BOD_SCAN_TAIL") ? atoi(getenv("BOD_SCAN_TAIL")) : -1;     // experiments
-    const bool scan_tail = k2_tail && (scan_tail_env >= 0 ? scan_tail_env != 0 : 4.0 * nb * g.N * A * K < 0.8e9);
-    if (!scan_tail && do_head) {
+    const bool small_run = scan_tail_env >= 0 ? scan_tail_env != 0 : 4.0 * nb * g.N * A * K < 0.8e9;
+    const bool scan_tail = k2_tail && small_run;
+    // graph replay: the scan stays with the head (measured: with the scan opening the tail graph the posterior kernel of a
+    // small run only finds room when the NEXT moments kernel ends, and every small-batch workload loses 10-25 %);
+    // BOD_SCAN_TAIL=1 moves it for experiments
+    const bool scan_in_tail_graph = gh && scan_tail_env > 0 && !c->prefilter;
+    if (!scan_tail && !scan_in_tail_graph && do_head) {
         CU(c, launch_scan(sc, hs));
         if (record) CU(c, cudaEventRecord(c->ev[2], hs));
     }
     if (!do_tail) return BOD_OK;
+    if (scan_in_tail_graph) CU(c, launch_scan(sc, ts, true));
     if (k2_tail) {
         CU(c, cudaEventRecord(L.head_done, hs));
         CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));
@@ -489,6 +510,8 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     k4.out_param = L.out_param + b0 * D * K; k4.out_count = L.out_count + b0 * D * K;
     k4.B = nb; k4.K = g.K; k4.capacity = c->capacity; k4.Dmax = c->Dmax; k4.words = c->words;
     k4.calibration = g.cov_calibration; k4.iou_threshold = g.iou_threshold;
+    // the context's (sticky) status word rides in the lane's result block, so a block fetch brings it along
+    k4.status_in = c->status; k4.status_out = (b0 + nb == c->cfg.B) ? L.block_status : nullptr;
 #ifdef BOD_DIAGNOSTICS
     if (!(c->skip_mask & 4))
 #endif
@@ -590,7 +613,7 @@ static int replay_run(bod_ctx* c, Lane& L, const LevelTable& lv, const float* an
             L.ga2 = a2;
         }
     }
-    // the caller's tensors are ready; the previous lane's moments kernel is done (they share the ticket counter)
+    // the caller's tensors are ready; the previous lane's moments kernel is done (one moments kernel at a time has the GPU)
     const Lane& P = c->lane[(int)((&L - c->lane) + c->nlanes - 1) % c->nlanes];
     CU(c, cudaStreamWaitEvent(ls, c->ev_in, 0));
     CU(c, cudaStreamWaitEvent(ls, P.head_done, 0));
@@ -625,7 +648,11 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
         c->cur = (c->cur + 1) % c->nlanes;
         Lane& L = c->lane[c->cur];
         CU(c, cudaEventRecord(c->ev_in, st));
-        const bool graphs = c->use_graphs && !c->prefilter && c->k2_on_tail;
+        // Graph replay pays once a run is long (B = 32: +4 %); runs of a few images are faster through the streams,
+        // where a result fetch behind every run costs nothing (measured at B = 4, 300 steps: streams 47.9 k images/s
+        // with a fetch per run, graphs 44.9 k without and 33.9 k with it).  BOD_GRAPHS=2 forces replay.
+        const bool long_run = 4.0 * c->cfg.B * c->cfg.N * c->cfg.A * c->cfg.K >= 0.8e9;
+        const bool graphs = c->use_graphs && !c->prefilter && c->k2_on_tail && (long_run || c->force_graphs);
         if (graphs) recorded = false;
         if (graphs && L.uses > 0) {
             // Replay: the whole run (moments, scan, posterior, soft-NMS, fusion) is one graph launch on the lane's
@@ -635,10 +662,13 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
             rc = replay_run(c, L, lv, anchors, counts);
             if (rc) return rc;
         } else {
+            // Heads (moments kernel + scan) go one after the other on the context's own stream.  (Measured and rejected:
+            // a head stream per lane, so that the next moments kernel's CTAs move in while the previous one's retire --
+            // the block scheduler interleaves the two grids instead, every run finishes later and small batches lose
+            // 20-25 %.)  With graphs the first run of a lane goes through the streams: one-time kernel attributes and
+            // tables are set up there, and its head has to follow the previous lane's, which may have been a replay.
             CU(c, cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
             if (graphs) {
-                // first run of the lane: through the streams (one-time kernel attributes and tables are set up here);
-                // its head has to follow the previous lane's, which may have been a replay
                 const Lane& P = c->lane[(c->cur + c->nlanes - 1) % c->nlanes];
                 if (P.uses > 0) CU(c, cudaStreamWaitEvent(c->own_stream, P.head_done, 0));
             }
@@ -651,6 +681,7 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
     }
     c->lane[c->cur].ticket = ++c->next_ticket;
     c->lane[c->cur].fetch_pending = false;
+    c->lane[c->cur].h_block_status = nullptr;
     if (recorded) ++c->runs_recorded;
     c->last_timed = recorded;
     c->ran = true; c->used_sampler = (counts == nullptr);
@@ -830,7 +861,30 @@ extern "C" int bod_fetch_async(bod_ctx* c, int64_t ticket, bod_host_results* out
     if (L->h_status) CU(c, cudaMemcpyAsync(L->h_status, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(c, cudaEventRecord(L->fetch_done, st));
     L->fetch_pending = true;
+    L->h_block_status = nullptr;
     // the lane's next run must not overwrite what these copies still have to read
+    if (c->nlanes > 1 && L->tail_pending) CU(c, cudaEventRecord(L->tail_done, st));
+    return BOD_OK;
+}
+
+extern "C" int bod_result_block_layout(const bod_ctx* c, int64_t offsets[10], int64_t* bytes) {
+    if (!c || !offsets || !bytes) return BOD_ERR_INVALID;
+    for (int i = 0; i < 10; ++i) offsets[i] = c->block_off[i];
+    *bytes = c->block_bytes;
+    return BOD_OK;
+}
+
+extern "C" int bod_fetch_block_async(bod_ctx* c, int64_t ticket, void* host_block) {
+    if (!c || !host_block) return BOD_ERR_INVALID;
+    Lane* L = lane_of_ticket(c, ticket);
+    if (!L) return fail(c, BOD_ERR_STATE, "the results of run %lld are gone: its lane has been reused (pipeline_depth = %d)",
+                        (long long)ticket, c->nlanes);
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream_of_lane(c, *L);
+    CU(c, cudaMemcpyAsync(host_block, L->block, (size_t)c->block_bytes, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaEventRecord(L->fetch_done, st));
+    L->fetch_pending = true;
+    L->h_block_status = reinterpret_cast<const int32_t*>(static_cast<const unsigned char*>(host_block) + c->block_off[9]);
     if (c->nlanes > 1 && L->tail_pending) CU(c, cudaEventRecord(L->tail_done, st));
     return BOD_OK;
 }
@@ -842,9 +896,10 @@ extern "C" int bod_ticket_wait(bod_ctx* c, int64_t ticket) {
     CU(c, cudaSetDevice(c->device));
     if (L->fetch_pending) {
         CU(c, cudaEventSynchronize(L->fetch_done));
-        if (L->h_status && (*L->h_status & 1)) {
+        const int32_t seen = L->h_block_status ? *L->h_block_status : (L->h_status ? *L->h_status : 0);
+        if (seen & 1) {
             CU(c, cudaMemset(c->status, 0, 4));        // sticky until reported once
-            *L->h_status = 0;
+            if (L->h_status) *L->h_status = 0;
             return fail(c, BOD_ERR_OVERFLOW, "an image produced more survivors than max_survivors=%d", c->capacity);
         }
         return BOD_OK;
@@ -977,7 +1032,7 @@ extern "C" int bod_stage_ms_accum(bod_ctx* c, float sum_ms[6], int32_t* runs) {
     *runs = 0;
     if (c->runs_recorded == c->runs_reported && !c->ran) return BOD_OK;
     CU(c, cudaSetDevice(c->device));
-    if (c->last_stream) CU(c, cudaStreamSynchronize(c->last_stream));
+    CU(c, cudaStreamSynchronize(c->last_stream));
     { int rc0 = drain_tails(c); if (rc0) return rc0; }      // earlier runs' tails live on other streams
     // graph replays (pipelined contexts) time their moments kernel only; the other stages read as zero there
     for (int l = 0; l < c->nlanes; ++l) harvest_k1_time(c, c->lane[l]);

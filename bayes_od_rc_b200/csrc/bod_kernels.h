@@ -152,6 +152,8 @@ struct K4Args {
     float* out_count;        // [B,Dmax,K]
     int B, K, capacity, Dmax, words;
     float calibration, iou_threshold;
+    const int32_t* status_in;   // the context's status word ...
+    int32_t* status_out;        // ... copied into the lane's result block by the kernel's first thread (or nullptr)
 };
 cudaError_t launch_k4(const K4Args& a, cudaStream_t st);
 

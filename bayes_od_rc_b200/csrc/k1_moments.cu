@@ -424,6 +424,10 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
             int stage = 0, round = 0;
             for (;;) {
                 const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
+                // every CTA draws exactly one ticket past the last tile, so the launch draws total_tiles + gridDim.x
+                // tickets in all: whoever draws the last one puts the counter back for the next launch (launches of
+                // a context never overlap), which saves a memset between two launches
+                if (t == (uint32_t)total_tiles + gridDim.x - 1u) *a.ticket = a.ticket_base;
                 if (round > 0) mbar_wait(&empty_bar[stage], (uint32_t)((round - 1) & 1));
                 if (t >= (uint32_t)total_tiles) {                 // no work left: tell the consumers
                     stage_tile[stage] = -1;

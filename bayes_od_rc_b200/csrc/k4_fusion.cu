@@ -57,6 +57,7 @@ k4_fusion_kernel(K4Args a) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = blockIdx.x * kK4Warps + warp, b = blockIdx.y;
+    if (a.status_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.status_out = *a.status_in;
     if (d >= a.Dmax) return;                      // warp-uniform
     if (d >= a.num_dets[b]) {                     // padding rows of the result blocks read as zero
         const size_t prow = (size_t)b * a.Dmax + d;

@@ -314,35 +314,38 @@ class BayesODEngine:
         return int(self.lib.bod_last_ticket(self._ctx))
 
     def _pinned_block(self):
-        """One set of page-locked host result blocks (bod_host_alloc) viewed as numpy arrays."""
+        """One page-locked host copy of a lane's result block (bod_host_alloc), viewed as numpy arrays at the
+        offsets of bod_result_block_layout."""
         B, D, K = self.B, self.Dmax, self.K
-        shapes = dict(num_dets=((B,), np.int32), num_survivors=((B,), np.int32), means=((B, D, 4), np.float32),
-                      covs=((B, D, 4, 4), np.float32), cat_param=((B, D, K), np.float32), cat_count=((B, D, K), np.float32),
-                      nms_indices=((B, D), np.int32), centre_anchor_idx=((B, D), np.int32), centre_scores=((B, D), np.float32))
-        total = sum(int(np.prod(sh)) * 4 for sh, _ in shapes.values())
-        base = self.lib.bod_host_alloc(total)
+        offs, total = (C.c_int64 * 10)(), C.c_int64()
+        self._check(self.lib.bod_result_block_layout(self._ctx, offs, C.byref(total)))
+        shapes = [("num_dets", (B,), np.int32), ("num_survivors", (B,), np.int32), ("means", (B, D, 4), np.float32),
+                  ("covs", (B, D, 4, 4), np.float32), ("cat_param", (B, D, K), np.float32), ("cat_count", (B, D, K), np.float32),
+                  ("nms_indices", (B, D), np.int32), ("centre_anchor_idx", (B, D), np.int32), ("centre_scores", (B, D), np.float32)]
+        base = self.lib.bod_host_alloc(int(total.value))
         if not base:
             raise MemoryError("bod_host_alloc failed")
         self._pinned_bases = getattr(self, "_pinned_bases", [])
         self._pinned_bases.append(base)
-        arrays, off = {}, 0
-        for k, (sh, dt) in shapes.items():
+        arrays = {}
+        for i, (k, sh, dt) in enumerate(shapes):
             n = int(np.prod(sh))
-            buf = (C.c_byte * (n * 4)).from_address(base + off)
+            buf = (C.c_byte * (n * 4)).from_address(base + int(offs[i]))
             arrays[k] = np.frombuffer(buf, dtype=dt, count=n).reshape(sh)
-            off += n * 4
-        return arrays, BodHostResults(**{k: v.ctypes.data for k, v in arrays.items()})
+        return arrays, base
 
     def fetch_async(self, ticket: int = None) -> int:
-        """Enqueue the device->host copies of run ``ticket`` (default: the last one) behind that run, into the
-        pinned result ring slot of its lane (bod_fetch_async).  Nothing blocks; collect with ``collect(ticket)``
-        before ``pipeline_depth`` further tickets have been fetched (the slot is then reused)."""
-        ticket = self.last_ticket if ticket is None else int(ticket)
+        """Enqueue the device->host copy of run ``ticket`` (default: the last one) behind that run, into the
+        pinned result ring slot of its lane (one cudaMemcpyAsync of the lane's result block:
+        bod_fetch_block_async).  Nothing blocks; collect with ``collect(ticket)`` before ``pipeline_depth``
+        further tickets have been fetched (the slot is then reused)."""
+        ticket = int(self.lib.bod_last_ticket(self._ctx)) if ticket is None else int(ticket)
         ring = getattr(self, "_ring", None)
         if ring is None:
             ring = self._ring = [self._pinned_block() for _ in range(max(1, int(self.config.pipeline_depth)))]
-        arrays, hres = ring[ticket % len(ring)]
-        self._check(self.lib.bod_fetch_async(self._ctx, ticket, C.byref(hres)))
+        rc = self.lib.bod_fetch_block_async(self._ctx, ticket, ring[ticket % len(ring)][1])
+        if rc != _cabi.BOD_OK:
+            self._check(rc)
         return ticket
 
     def collect(self, ticket: int, copy=True):

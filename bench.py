@@ -205,7 +205,7 @@ def main():
     wl["B"] = B
     N, K = wl["N"], wl["K"]
     if args.pipeline == 0:
-        args.pipeline = min(16, max(4, 64 // B))
+        args.pipeline = min(8, max(4, 64 // B))
     spec = synthetic.SceneSpec(im_h=wl["im_h"], im_w=wl["im_w"], N=N, K=K, config_id=wl["config_id"], **wl.get("spec", {}))
     first_image = rank * B                      # global image ids: shard-invariant RNG + data
 
@@ -310,7 +310,7 @@ def main():
         first_s = rank * Bg
         sb = synthetic.make_batch(spec, Bg, device=dev, with_counts=False, first_image_id=first_s)
         import dataclasses
-        lanes_s = min(16, max(4, 64 // Bg))
+        lanes_s = min(8, max(4, 64 // Bg))
         eng_s = BayesODEngine(Bg, N, A, K, dataclasses.replace(cfg, image_id_base=first_s, pipeline_depth=lanes_s), device=local_rank)
 
         def step_s():

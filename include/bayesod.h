@@ -277,6 +277,12 @@ int bod_fetch(bod_ctx* ctx, bod_host_results* out);
  * BOD_ERR_STATE for tickets older than that.  Copies enqueued by bod_fetch_async are
  * ordered before the lane's next run, so they never see a later run's data.
  */
+/* One-copy variant: a lane's result arrays are ONE contiguous device block; bod_result_block_layout gives the
+ * byte offsets of num_dets, num_survivors, means, covs, cat_param, cat_count, nms_indices, centre_anchor_idx,
+ * centre_scores and the status word inside it (each 16-byte aligned) and its size; bod_fetch_block_async copies
+ * the whole block of run `ticket` into `host_block` (pinned, block-sized) with a single cudaMemcpyAsync. */
+int bod_result_block_layout(const bod_ctx* ctx, int64_t offsets[10], int64_t* bytes);
+int bod_fetch_block_async(bod_ctx* ctx, int64_t ticket, void* host_block);
 int64_t bod_last_ticket(const bod_ctx* ctx);
 int bod_fetch_async(bod_ctx* ctx, int64_t ticket, bod_host_results* out);
 int bod_ticket_wait(bod_ctx* ctx, int64_t ticket);

@@ -256,13 +256,14 @@ def test_pipelined_runs_equal_serial_runs(depth):
         assert_bit_equal(getattr(res, k), getattr(serial[2], k), f"host entry: {k}")
 
 
-@pytest.mark.parametrize("graphs", ["1", "0"])
+@pytest.mark.parametrize("graphs", ["2", "0"])
 @pytest.mark.parametrize("depth", [1, 2, 4])
 def test_streaming_retrieval_of_every_run(depth, graphs, monkeypatch):
     """bod_fetch_async / bod_ticket_wait: a stream of different batches through one (pipelined) context, every
     run's result blocks copied out behind its own tail while later runs keep streaming; device results of run i
     survive the issue of runs i+1 .. i+L-1 (fetched oldest first after L back-to-back runs); tickets older than
-    that are refused.  With graph replay and with plain stream launches."""
+    that are refused.  With graph replay (forced: BOD_GRAPHS=2, short runs default to stream launches) and with
+    plain stream launches."""
     import torch
     from gpu_common import engine_config_from_oracle
     from bayes_od_rc_b200.engine import BayesODEngine
