@@ -188,17 +188,14 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
 // The first psm pending weights of every candidate live in shared memory (psm is
 // what fits for the image's survivor count), the rest spill to global rows.
 // ---------------------------------------------------------------------------
-constexpr int kTop = 16;              // candidates examined per round
-constexpr int kBatch = 15;            // centres selected per round at most (pair entries name them in 4 bits; 15 = "no centre")
+constexpr int kTop = 32;              // candidates examined per round (one per lane of the acceptance warp)
+constexpr int kBatch = 31;            // centres selected per round at most (a bit per centre in a 32-bit mask + the wake bit)
 constexpr float kTauFrac = 0.97f;     // scores below this fraction of the lowest examined score are kept as upper bounds
-constexpr int kListed = 64;           // keys listed per round by all warps together
+constexpr int kStateBytes = 25;       // shared memory per candidate besides its pending weights: corners, two scores, a count
+constexpr int kSimOld = 32;           // pending weights of an examined candidate the batch loop can multiply in itself
+constexpr int kListed = 128;          // keys listed per round by all warps together
 constexpr int kExpTab = 129;
-constexpr int kTeamWarps = 4;         // warps that share a round's acceptance work
 constexpr int kPairsCta = 4096;       // (candidate, centre) pairs the warps' list segments hold together
-
-BOD_DEVINL void team_barrier() {      // named barrier 1: the acceptance team only
-    asm volatile("bar.sync 1, %0;" ::"n"(kTeamWarps * 32) : "memory");
-}
 
 struct K3Smem {
     unsigned long long warp_best[2][32];         // generic kernel scratch
@@ -208,13 +205,17 @@ struct K3Smem {
     float4 sel_box[kMaxOut];
     unsigned long long cand_key[kTop];           // the round's examined candidates ...
     float4 cand_box[kTop];
-    float4 batch_ebox[kBatch];                   // the round's centres grown by 2 px: pass A's lean overlap test
-    float wpair[kTop][kTop];                     // ... their pairwise soft-NMS weights [q][i], i < q
-    uint32_t rowmask[kTop];                      // bit i of row q: wpair[q][i] != 1
+    float4 batch_ebox[kBatch + 1];               // the round's centres grown by 2 px: pass A's lean overlap test
+    float wpair[kTop][kTop + 1];                 // ... their pairwise soft-NMS weights where they are not exactly 1 (both triangles)
+    uint32_t rowmask[kTop];                      // bit i of row q: the weight of the pair (q, i) is not 1
     double exp_tab[kExpTab];                     // exp(-k/64)
     unsigned long long tau[2];                   // the round's laziness threshold (see k3_walk), by round parity
     int batch_n;                                 // centres selected in this round
     int malformed;
+    unsigned long long next_key;                 // best listed key that is not examined (0: none)
+    int rank_cnt[kListed];                       // listed keys larger than listed key t
+    float oldw[kTop][kSimOld + 1];               // the batch loop's copy of an examined candidate's pending weights
+    float4 cand_ebox[kTop];                      // the examined candidates' boxes grown by 2 px (the speculative overlap test)
 };
 
 struct K3State {                                  // kernel-lifetime constants (registers)
@@ -290,14 +291,14 @@ BOD_DEVINL float pend_product(const K3State& C, int si, int s, int n, float v) {
 }
 
 // list entry of one (candidate, centre) pair: row of the block | owner lane << 3 | centre of the batch << 8 |
-// first pair of its candidate << 12 | pairs of the candidate << 13
+// first pair of its candidate << 13 | pairs of the candidate << 14
 BOD_DEVINL uint32_t ent_make(int j, int ln, int q, bool head, int c) {
-    return (uint32_t)j | ((uint32_t)ln << 3) | ((uint32_t)q << 8) | ((uint32_t)head << 12) | ((uint32_t)c << 13);
+    return (uint32_t)j | ((uint32_t)ln << 3) | ((uint32_t)q << 8) | ((uint32_t)head << 13) | ((uint32_t)c << 14);
 }
 BOD_DEVINL int ent_row(uint32_t e) { return (int)(e & 7u); }
 BOD_DEVINL int ent_lane(uint32_t e) { return (int)((e >> 3) & 31u); }
-BOD_DEVINL int ent_q(uint32_t e) { return (int)((e >> 8) & 15u); }
-BOD_DEVINL int ent_pairs(uint32_t e) { return (int)((e >> 13) & 31u); }
+BOD_DEVINL int ent_q(uint32_t e) { return (int)((e >> 8) & 31u); }
+BOD_DEVINL int ent_pairs(uint32_t e) { return (int)((e >> 14) & 63u); }
 
 // Epoch walk of one QUEUED candidate (survivor s, state row si) over a batch of selections whose keys are
 // sel_key[0 .. qlast] (the caller passes the batch's slice of sm.sel_key), driven by the candidate's listed
@@ -349,7 +350,7 @@ BOD_DEVINL float k3_walk(const K3State& C, const unsigned long long* sel_key, in
             if (w != 1.0f) { ub = ub * w * 1.0000005f; ++nn; dead = dead || (!C.is_soft && w == 0.0f); }
         }
         if (dead) { C.ucur[si] = -INFINITY; return -INFINITY; }     // hard-NMS: removed for good
-        if (nn == 0 && was_exact) { K3_CNT(2, 1); return uprev; }   // every weight was exactly 1: untouched
+        if (nn == 0 && was_exact) return uprev;   // every weight was exactly 1: untouched
         if (make_key(ub, s) < tau) {
             K3_CNT(1, 1);
             int base = n_old;
@@ -445,7 +446,7 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
     constexpr int W = NT / 32;                              // warps
     constexpr int kTop1 = kListed / W;                      // keys every warp lists per round
     constexpr int kSegCap = kPairsCta / W;                  // pairs per warp segment
-    static_assert(W >= kTeamWarps && kTop1 >= 2 && kTop1 * W == kListed && kSegCap >= 32, "CTA size");
+    static_assert(kTop1 >= 2 && kTop1 * W == kListed && kSegCap >= 32, "CTA size");
     extern __shared__ __align__(16) unsigned char dyn[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -462,7 +463,7 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
     float* ucur = reinterpret_cast<float*>(corn + SP);                    // [SP] up-to-date score, -inf = not queued
     float* stl = ucur + SP;                                               // [SP] score as of the last fold
     // pending weights per candidate held in shared memory: whatever fits behind the fixed arrays
-    int psm = (SP > 0 && !big) ? (pool_bytes - SP * 25) / (SP * 4) : 0;
+    int psm = (SP > 0 && !big) ? (pool_bytes - SP * kStateBytes) / (SP * 4) : 0;
     psm = psm < 0 ? 0 : (psm > a.pstride ? a.pstride : psm);
     if (a.psm_max >= 0 && psm > a.psm_max) psm = a.psm_max;              // tests: force the global spill rows
     psm &= ~3;                                                            // rows are read four weights at a time
@@ -540,105 +541,169 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
             const unsigned long long ixw = warp_max_u64(ixmax);
             if (lane == 0) sm.bound_w[warp] = bound > ixw ? bound : ixw;
         }
-        if (tid < kTop) { sm.cand_key[tid] = 0ull; sm.rowmask[tid] = 0u; }     // filled by the acceptance team below
-        if (tid == 0) sm.tau[rnd & 1] = 0ull;
+        if (tid < kTop) { sm.cand_key[tid] = 0ull; sm.rowmask[tid] = 0u; }     // filled by the acceptance phases below
+        if (tid < kListed) sm.rank_cnt[tid] = 0;
+        if (tid == 0) { sm.tau[rnd & 1] = 0ull; sm.next_key = 0ull; }
         K3_T(c1);
         __syncthreads();
         K3_T(c2);
         K3_ACC(0, c1, c0); K3_ACC(1, c2, c1);
-        if (warp < kTeamWarps) {
-            // ---- acceptance, by the first four warps (named barrier 1 among them) ----
-            // (i) the block's top-kTop keys: thread t < kListed ranks listed key t by counting the larger ones;
-            // G = the largest cut of any warp's list: below it an untracked key might outrank a listed one,
-            // so such entries are dropped (validity is a prefix of the order)
-            if (tid < kListed) {
-                unsigned long long G = (lane < W) ? sm.bound_w[lane] : 0ull;
-                G = warp_max_u64(G);
-                const unsigned long long key = sm.top_flat[tid];
-                if (key != 0ull && key >= G) {
-                    const ulonglong2* f2 = reinterpret_cast<const ulonglong2*>(sm.top_flat);
-                    int rank = 0;
+        // ---- acceptance (every warp helps with the ranking and the pairwise table; warp 0 then runs the batch) ----
+        // (i) the block's top-kTop keys: listed key t is ranked by counting the larger ones, NT / kListed threads
+        // per key, each over its share of the list.  G = the largest cut of any warp's list: below it an
+        // untracked key might outrank a listed one, so such entries are dropped (validity is a prefix of the order)
+        {
+            constexpr int kParts = NT / kListed;                         // threads per listed key (warp-uniform part)
+            constexpr int kShare = kListed / kParts;                     // keys each of them compares against
+            static_assert(kParts >= 1 && kParts * kListed == NT && kShare % 2 == 0, "ranking layout");
+            const int t = tid & (kListed - 1), part = tid / kListed;
+            const unsigned long long G = warp_max_u64((lane < W) ? sm.bound_w[lane] : 0ull);
+            const unsigned long long key = sm.top_flat[t];
+            if (key != 0ull && key >= G) {
+                const ulonglong2* f2 = reinterpret_cast<const ulonglong2*>(sm.top_flat + part * kShare);
+                int cnt = 0;
 #pragma unroll 4
-                    for (int j = 0; j < kListed / 2; ++j) {
-                        const ulonglong2 kk = f2[j];
-                        rank += (int)(kk.x > key) + (int)(kk.y > key);
-                    }
-                    if (rank < kTop) { sm.cand_key[rank] = key; sm.cand_box[rank] = corn[row_of(key_index(key))]; }
+                for (int j = 0; j < kShare / 2; ++j) {
+                    const ulonglong2 kk = f2[j];
+                    cnt += (int)(kk.x > key) + (int)(kk.y > key);
                 }
+                if (kParts > 1) { if (cnt) atomicAdd(&sm.rank_cnt[t], cnt); } else sm.rank_cnt[t] = cnt;
             }
-            team_barrier();
-            K3_T(c3);
-            K3_ACC(2, c3, c2);
-            // (ii) pairwise weights among the examined candidates, one pair (q, i), i < q, per thread.  Most pairs
-            // do not intersect at all (weight exactly 1): the division + exp runs only for those that do
-            if (tid < kTop * (kTop - 1) / 2) {
-                int q = 1, base = 0;
-                while (base + q <= tid) { base += q; ++q; }
-                const int i = tid - base;
-                if (sm.cand_key[q] != 0ull) {                             // then candidate i < q exists too
-                    const float4 bq = sm.cand_box[q], bi = sm.cand_box[i];
-                    const float dx = fminf(bq.w, bi.w) - fmaxf(bq.y, bi.y);
-                    const float dy = fminf(bq.z, bi.z) - fmaxf(bq.x, bi.x);
-                    float w = 1.0f;
-                    if ((dx > 0.0f && dy > 0.0f) || sm.malformed != 0)
-                        w = nms_weight_fast(tf_iou(bq, bi), C.scale, C.is_soft, C.thr, sm.exp_tab);
-                    sm.wpair[q][i] = w;
-                    if (w != 1.0f) atomicOr(&sm.rowmask[q], 1u << i);
-                }
+            __syncthreads();
+            if (part == 0 && key != 0ull && key >= G) {
+                const int rank = sm.rank_cnt[t];
+                if (rank < kTop) {
+                    const float4 cb = corn[row_of(key_index(key))];
+                    sm.cand_key[rank] = key; sm.cand_box[rank] = cb;
+                    sm.cand_ebox[rank] = make_float4(cb.x - 2.0f, cb.y - 2.0f, cb.z + 2.0f, cb.w + 2.0f);
+                } else if (rank == kTop) sm.next_key = key;               // the best candidate that is not examined
             }
-            team_barrier();
-            K3_T(c4);
-            K3_ACC(3, c4, c3);
+            __syncthreads();
         }
+        K3_T(c3);
+        K3_ACC(2, c3, c2);
+        // (ii) pairwise weights among the examined candidates, one pair (q, i), i < q, per thread.  Most pairs do
+        // not intersect at all (weight exactly 1): the division + exp runs only for those that do
+        for (int p = tid; p < kTop * (kTop - 1) / 2; p += NT) {
+            int q = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (q * (q - 1) / 2 > p) --q;
+            while ((q + 1) * q / 2 <= p) ++q;
+            const int i = p - q * (q - 1) / 2;
+            if (sm.cand_key[q] != 0ull) {                                 // then candidate i < q exists too
+                const float4 bq = sm.cand_box[q], bi = sm.cand_box[i];
+                const float dx = fminf(bq.w, bi.w) - fmaxf(bq.y, bi.y);
+                const float dy = fminf(bq.z, bi.z) - fmaxf(bq.x, bi.x);
+                if ((dx > 0.0f && dy > 0.0f) || sm.malformed != 0) {
+                    const float w = nms_weight_fast(tf_iou(bq, bi), C.scale, C.is_soft, C.thr, sm.exp_tab);
+                    if (w != 1.0f) {
+                        sm.wpair[q][i] = w; sm.wpair[i][q] = w;
+                        atomicOr(&sm.rowmask[q], 1u << i); atomicOr(&sm.rowmask[i], 1u << q);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        K3_T(c4);
+        K3_ACC(3, c4, c3);
         K3_T(c5);
         if (warp == 0) {
-            // (iii) accept centres in key order (see header); every lane walks, lane p < kTop owns candidate p
-            const unsigned long long myk = (lane < kTop) ? sm.cand_key[lane] : 0ull;
+            // (iii) the batch: TF's loop restricted to the examined candidates, one SELECTION per iteration, every lane
+            // (= examined candidate) in parallel.  A lane keeps TF's queue entry of its candidate: the stale score st, the
+            // weights pending since its last pop (earlier rounds' in sm.oldw, this batch's in registers, newest first),
+            // and u = st x pending weights, newest first: the score TF computes when it pops the candidate now.  The
+            // next centre is the lane with the largest key(u): TF pops, updates and re-pushes candidates until the
+            // front of the queue is a candidate whose score does not change, and that is the largest current score.  On
+            // the way it pops exactly the candidates with pending weights whose stale key exceeds the new centre's key
+            // (k3_walk's rule): those lanes fold (st = u, nothing pending).  Then the new centre's weight becomes
+            // pending for the lanes it overlaps.  Every candidate outside the examined set has a current score below Gb
+            // (the listed keys' cut, the bounds of lazily scored candidates, the best listed key that was not
+            // examined) and scores only fall, so while the winner's key is not below Gb it is TF's next selection, bit
+            // for bit; the batch ends where a candidate outside might come first.  Nothing is stored for examined
+            // candidates that are not selected: the passes below walk them like any other.
+            static_assert(kTop == 32, "one examined candidate per lane");
+            const unsigned long long myk = sm.cand_key[lane];
             const int nvalid = __popc(__ballot_sync(0xffffffffu, myk != 0ull));      // candidates are a prefix
-            // everything the walk reads is fetched up front; only the accept / skip decisions are sequential
-            float sqv[kTop];
-            uint32_t rowv[kTop];
-#pragma unroll
-            for (int q = 0; q < kTop; ++q) { sqv[q] = key_score(sm.cand_key[q]); rowv[q] = sm.rowmask[q]; }
+            unsigned long long Gb = warp_max_u64((lane < W) ? sm.bound_w[lane] : 0ull);
+            const bool any_bound = Gb != 0ull;
+            { const unsigned long long nk = sm.next_key; Gb = nk > Gb ? nk : Gb; }
+            const int x = key_index(myk);
+            const int si = (myk != 0ull) ? row_of(x) : 0;
+            float st = 0.0f;
+            int nold = 0;
+            if (myk != 0ull) { st = stl[si]; nold = npend[si]; }
+            const uint32_t nz = sm.rowmask[lane];                        // examined candidates whose weight against this one is not 1
+            bool old = nold > 0;                                         // weights of earlier rounds are pending
+            const bool long_old = nold > kSimOld;                        // ... more than this loop can multiply in itself
+            if (old && !long_old) {
+#pragma unroll 4
+                for (int i = 0; i < nold; ++i)
+                    sm.oldw[lane][i] = (i < C.psm) ? C.pws[si * C.psm + i] : C.pwg[(size_t)x * C.pstride + i];
+            }
+            float u = key_score(myk);                                    // examined candidates have exact scores
+            uint32_t hu = (myk != 0ull) ? float_key(u) : 0u;             // key of u, high word (never 0 for a live lane)
+            uint32_t hs = float_key(st);                                 // key of st, high word
+            const uint32_t lo = (uint32_t)myk;                           // low word of both: ~index
+            float q0 = 1.0f, q1 = 1.0f, q2 = 1.0f, q3 = 1.0f;            // this batch's pending weights, q0 the newest
+            int nq = 0;
+            const uint32_t Gbh = (uint32_t)(Gb >> 32), Gbl = (uint32_t)Gb;
             int m = 0;
-            uint32_t acc = 0u;                                           // accepted candidates (bit q)
-            if (nvalid > 0) {
-                acc = 1u; m = 1;
-                float ub_max = -INFINITY;                                // best score a skipped candidate can still reach
-#pragma unroll
-                for (int q = 1; q < kTop; ++q) {
-                    if (q >= nvalid || r + m >= Dmax || m >= kBatch) break;
-                    const float sq = sqv[q];
-                    const uint32_t hit = rowv[q] & acc;                  // accepted centres it overlaps
-                    if (hit == 0u) {
-                        if (!(sq > ub_max)) break;                       // a skipped candidate might still outrank it
-                        acc |= 1u << q; ++m;
-                    } else {
-                        const float w = sm.wpair[q][__ffs(hit) - 1];
-                        ub_max = fmaxf(ub_max, sq * w * 1.00005f);     // 2n+2 roundings apart, n <= 255
+            float lowest = INFINITY;                                     // lowest score selected
+#pragma unroll 1
+            while (m < kBatch && r + m < Dmax) {
+                const uint32_t mh = __reduce_max_sync(0xffffffffu, hu);
+                if (mh == 0u || mh < Gbh) break;
+                uint32_t bal = __ballot_sync(0xffffffffu, hu == mh);
+                if (bal & (bal - 1u)) {                                  // equal scores: the lower index comes first
+                    const uint32_t ml = __reduce_max_sync(0xffffffffu, hu == mh ? lo : 0u);
+                    bal = __ballot_sync(0xffffffffu, hu == mh && lo == ml);
+                }
+                const int L = __ffs(bal) - 1;
+                const uint32_t ll = __shfl_sync(0xffffffffu, lo, L);
+                if (mh == Gbh && ll < Gbl) break;
+                K3_CNT(2, lane == 0);
+                bool stop = false;
+                if (lane == L) {                                         // selection r + m
+                    const int pos = r + m;
+                    sm.sel_box[pos] = sm.cand_box[lane];
+                    sm.batch_ebox[m] = sm.cand_ebox[lane];
+                    sm.sel_key[pos] = ((unsigned long long)mh << 32) | lo;
+                    ucur[si] = -INFINITY;                                // leaves the queue
+                    a.nms_idx[(size_t)b * Dmax + pos] = x;
+                    a.nms_score[(size_t)b * Dmax + pos] = u;
+                    hu = 0u;
+                } else if (hu != 0u) {
+                    // popped before this selection: pending weights and a stale key above the new centre's
+                    if ((nq > 0 || old) && (hs > mh || (hs == mh && lo > ll))) { st = u; hs = hu; nq = 0; old = false; }
+                    if ((nz >> L) & 1u) {                                // the new centre's weight is pending now
+                        const float w = sm.wpair[lane][L];
+                        if (!C.is_soft && w == 0.0f) hu = 0u;            // hard-NMS: removed for good (the passes below see it too)
+                        else if (nq == 4 || (old && long_old)) stop = true;   // more than this loop keeps: the batch ends here
+                        else {
+                            q3 = q2; q2 = q1; q1 = q0; q0 = w; ++nq;
+                            float v = st * q0;
+                            if (nq > 1) v = v * q1;
+                            if (nq > 2) v = v * q2;
+                            if (nq > 3) v = v * q3;
+                            if (old) {
+#pragma unroll 4
+                                for (int i = nold - 1; i >= 0; --i) v = v * sm.oldw[lane][i];
+                            }
+                            u = v; hu = float_key(u);
+                        }
                     }
                 }
+                ++m; lowest = fminf(lowest, key_score((unsigned long long)mh << 32));
+                if (__any_sync(0xffffffffu, stop)) break;
             }
-            // accepted candidate q becomes selection r + (number of accepted before it)
-            if (lane < kTop && ((acc >> lane) & 1u)) {
-                const int pos = r + __popc(acc & ((1u << lane) - 1u));
-                const int x = key_index(myk);
-                const float4 cb = sm.cand_box[lane];
-                sm.sel_box[pos] = cb;
-                sm.batch_ebox[pos - r] = make_float4(cb.x - 2.0f, cb.y - 2.0f, cb.z + 2.0f, cb.w + 2.0f);
-                sm.sel_key[pos] = myk;
-                ucur[row_of(x)] = -INFINITY;                             // leaves the queue
-                a.nms_idx[(size_t)b * Dmax + pos] = x;
-                a.nms_score[(size_t)b * Dmax + pos] = key_score(myk);
-            }
-            // nothing examinable although keys exist (every listed key is below some candidate's upper bound):
-            // a refresh round (-1) makes all bounds exact
             if (lane == 0) {
-                // laziness threshold of the round's passes: a fixed fraction below the lowest examined score
-                if (nvalid > 0) sm.tau[rnd & 1] = make_key(key_score(sm.cand_key[nvalid - 1]) * kTauFrac, 0x7fffffff);
-                unsigned long long G = 0ull;
-                for (int w = 0; w < W; ++w) G = sm.bound_w[w] > G ? sm.bound_w[w] : G;
-                sm.batch_n = (m == 0 && G != 0ull) ? -1 : m;
+                // laziness threshold of the round's passes: a fixed fraction below the lowest score examined or selected
+                if (nvalid > 0) {
+                    lowest = fminf(lowest, key_score(sm.cand_key[nvalid - 1]));
+                    sm.tau[rnd & 1] = make_key(lowest * kTauFrac, 0x7fffffff);
+                }
+                // nothing examinable although keys exist (every listed key is below some candidate's upper bound):
+                // a refresh round (-1) makes all bounds exact
+                sm.batch_n = (m == 0 && any_bound) ? -1 : m;
             }
         }
         K3_T(c6);
@@ -762,23 +827,29 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
 #endif
                 return true;
             };
-            // The whole block at once; when its pairs overflow the segment (rare): a batch may be applied in pieces
-            // -- rounds are only a grouping of consecutive selections -- so centre by centre, and row by row where
-            // one centre alone overflows (<= 32 pairs then); the owners pick the final scores up afterwards.
+            // The whole block at once; when its pairs overflow the segment: a batch may be applied in pieces of
+            // consecutive centres -- rounds are only a grouping of consecutive selections -- so the centres are
+            // halved until a piece fits, and row by row where one centre alone overflows (<= 32 pairs then); the
+            // owners pick the final scores up afterwards.
             // (One call site: the round loop has to stay small enough for the instruction cache.)
             {
-                uint32_t qm = full | wake;
-                int q = -1, jlo = 0, jhi = kCH;
-                bool add = true;
+                bool whole = true, add = true;
+                int lo = 0, wd = m, jlo = 0, jhi = kCH;
 #pragma unroll 1
                 for (;;) {
+                    const int hi = (lo + wd < m) ? lo + wd : m;
+                    const uint32_t qm = whole ? (full | wake)
+                                              : ((((1u << hi) - 1u) & ~((1u << lo) - 1u)) | (m == 0 ? wake : 0u));
                     if (pass_b(qm, jlo, jhi, add)) {
-                        if (q < 0) break;
-                        if (jhi < kCH) { jlo = jhi; jhi = jlo + 1; }           // next row of this centre
-                        else { ++q; jlo = 0; jhi = kCH; if (q >= m) break; qm = 1u << q; }
+                        if (whole) break;
+                        if (jhi < kCH) { jlo = jhi; jhi = jlo + 1; continue; }   // next row of this piece
+                        lo = hi; jlo = 0; jhi = kCH;
+                        if (lo >= m) break;
                     } else {
                         add = false;
-                        if (q < 0) { q = 0; qm = 1u; }                         // centre by centre
+                        K3_CNT(7, 1);
+                        if (whole) { whole = false; wd = (m + 1) >> 1; }       // halves
+                        else if (wd > 1) wd = (wd + 1) >> 1;
                         else { jlo = 0; jhi = 1; }                             // this centre row by row
                     }
                 }
@@ -834,8 +905,8 @@ k3_softnms_kernel(K3Args a, int pool_bytes) {
     const int S = a.num_survivors[b];
     if (S > a.max_rows) { k3_generic(a, b, sm.warp_best, sm.sel_box); return; }
     const long long SP = (long long)((S + NT - 1) / NT) * NT;
-    constexpr int kCH = NT >= 1024 ? 4 : 8;                 // candidates per thread handled per pass-A/B block (registers)
-    if (SP * 25 > (long long)pool_bytes || a.force_big != 0) k3_rounds<NT, true, kCH>(a, pool_bytes, sm, S);
+    constexpr int kCH = NT >= 512 ? 4 : 8;                  // candidates per thread handled per pass-A/B block (registers, pairs per list segment)
+    if (SP * kStateBytes > (long long)pool_bytes || a.force_big != 0) k3_rounds<NT, true, kCH>(a, pool_bytes, sm, S);
     else k3_rounds<NT, false, kCH>(a, pool_bytes, sm, S);
 }
 
