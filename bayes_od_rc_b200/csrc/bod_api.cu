@@ -50,6 +50,7 @@ struct Lane {
     const int32_t* h_block_status = nullptr;          // where that word lands on the host (last bod_fetch_block_async)
     cudaEvent_t k1_begin = nullptr, k1_end = nullptr; // timing of the lane's last replayed moments kernel
     bool k1_timed = false;
+    bool replayed = false;            // the lane's last run was a graph replay (k1_end was recorded by its head graph)
 };
 
 // what run_range does differently while a lane's graphs are being captured: only one half of the run is
@@ -83,6 +84,8 @@ struct bod_ctx {
     // device staging of host inputs (bod_run_host), allocated on first use
     float* in_cls = nullptr; float* in_box = nullptr; float* in_cov = nullptr; float* in_anchors = nullptr; float* in_counts = nullptr;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t own_stream2 = nullptr;   // second head stream (BOD_HEADS=2): see issue_run
+    int head_flip = 0;
     cudaStream_t last_stream = nullptr;
     cudaEvent_t ev_in = nullptr;
     // stage-timing events: a ring of the last kEvRing runs, 7 events each
@@ -277,7 +280,18 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
         L.nms_score = reinterpret_cast<float*>(b + c->block_off[8]); L.block_status = reinterpret_cast<int32_t*>(b + c->block_off[9]);
     }
     cudaMemset(c->slab, 0, off);
-    cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    {
+        const char* e = getenv("BOD_HEADS");
+        if (e && atoi(e) == 2 && c->nlanes > 1) {
+            // two head streams of different priority: the next run's moments kernel is queued while the current one
+            // still runs and its CTAs move in as the current one's retire; the priorities keep the block scheduler
+            // from interleaving two grids that become eligible at the same moment
+            cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, -1);
+            cudaStreamCreateWithPriority(&c->own_stream2, cudaStreamNonBlocking, 0);
+        } else {
+            cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+        }
+    }
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     {
         int lo = 0, hi = 0;                                  // the tail is latency-bound and short: let its CTAs go first
@@ -321,6 +335,7 @@ extern "C" void bod_destroy(bod_ctx* c) {
     if (c->slab) cudaFree(c->slab);
     for (float* p : {c->in_cls, c->in_box, c->in_cov, c->in_anchors, c->in_counts}) if (p) cudaFree(p);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->own_stream2) cudaStreamDestroy(c->own_stream2);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto& L : c->lane) if (L.tail_stream) cudaStreamDestroy(L.tail_stream);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
@@ -363,8 +378,8 @@ static LevelTable levels_split(const bod_ctx* c, const float* const* cls, const 
 }
 
 static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
-                     const float* anchors, const float* counts, cudaStream_t hs, cudaStream_t ts, bool record,
-                     const GraphHooks* gh = nullptr) {
+                     const float* anchors, const float* counts, cudaStream_t hs, cudaStream_t ts, int record,
+                     const GraphHooks* gh = nullptr) {   // record: 0 no stage events, 1 moments kernel only, 2 every stage
     const bod_config& g = c->cfg;
     const size_t A = g.A, K = g.K, cap = c->capacity, D = c->Dmax;
     const size_t slots = (size_t)c->tiles * kTileAnchors;
@@ -442,7 +457,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     const bool scan_in_tail_graph = gh && scan_tail_env > 0 && !c->prefilter;
     if (!scan_tail && !scan_in_tail_graph && do_head) {
         CU(c, launch_scan(sc, hs));
-        if (record) CU(c, cudaEventRecord(c->ev[2], hs));
+        if (record > 1) CU(c, cudaEventRecord(c->ev[2], hs));
     }
     if (!do_tail) return BOD_OK;
     if (scan_in_tail_graph) CU(c, launch_scan(sc, ts, true));
@@ -452,7 +467,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
         k2s = ts;
         if (scan_tail) {
             CU(c, launch_scan(sc, ts, true));
-            if (record) CU(c, cudaEventRecord(c->ev[2], ts));
+            if (record > 1) CU(c, cudaEventRecord(c->ev[2], ts));
         }
     }
     K2Args k2{};
@@ -477,12 +492,12 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     CU(c, launch_k2(k2, k2s));
     if (gh) *gh->k2_out = k2;
     if (k2.ranking_method == 1) { CU(c, launch_rank_normalise(k2, k2s)); ++launches; }
-    if (record) CU(c, cudaEventRecord(c->ev[3], k2s));
+    if (record > 1) CU(c, cudaEventRecord(c->ev[3], k2s));
     if (hs != ts && !k2_tail) {
         CU(c, cudaEventRecord(L.head_done, hs));
         CU(c, cudaStreamWaitEvent(ts, L.head_done, 0));
     }
-    if (record) CU(c, cudaEventRecord(c->ev[6], ts));
+    if (record > 1) CU(c, cudaEventRecord(c->ev[6], ts));
 
     K3Args k3{};
     k3.corners = k2.corners; k3.score = k2.score; k3.num_survivors = sc.num_survivors; k3.surv_anchor = k2.surv_anchor;
@@ -500,7 +515,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     if (!(c->skip_mask & 2))
 #endif
     CU(c, launch_k3(k3, ts));
-    if (record) CU(c, cudaEventRecord(c->ev[4], ts));
+    if (record > 1) CU(c, cudaEventRecord(c->ev[4], ts));
 
     K4Args k4{};
     k4.cnt_post = k2.cnt_post; k4.mu_post = k2.mu_post; k4.sig_post = k2.sig_post; k4.num_survivors = sc.num_survivors;
@@ -516,7 +531,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     if (!(c->skip_mask & 4))
 #endif
     CU(c, launch_k4(k4, ts));
-    if (record) CU(c, cudaEventRecord(c->ev[5], ts));
+    if (record > 1) CU(c, cudaEventRecord(c->ev[5], ts));
     if (hs != ts) { CU(c, cudaEventRecord(L.tail_done, ts)); L.tail_pending = true; }
     c->launches += launches + 2;   // + soft-NMS, K4 (membership + fusion)
     return BOD_OK;
@@ -616,13 +631,17 @@ static int replay_run(bod_ctx* c, Lane& L, const LevelTable& lv, const float* an
     // the caller's tensors are ready; the previous lane's moments kernel is done (one moments kernel at a time has the GPU)
     const Lane& P = c->lane[(int)((&L - c->lane) + c->nlanes - 1) % c->nlanes];
     CU(c, cudaStreamWaitEvent(ls, c->ev_in, 0));
-    CU(c, cudaStreamWaitEvent(ls, P.head_done, 0));
+    // (BOD_K1_CHAIN=1: behind the previous lane's moments kernel itself -- the event node right behind it in that
+    // lane's head graph -- instead of behind its whole head, whose scan then runs beside this moments kernel)
+    static const bool k1_chain = getenv("BOD_K1_CHAIN") && atoi(getenv("BOD_K1_CHAIN")) != 0;
+    CU(c, cudaStreamWaitEvent(ls, (k1_chain && P.replayed) ? P.k1_end : P.head_done, 0));
     CU(c, cudaGraphLaunch(L.gexec[0], ls));
     CU(c, cudaEventRecord(L.head_done, ls));
     CU(c, cudaGraphLaunch(L.gexec[1], ls));
     CU(c, cudaEventRecord(L.tail_done, ls));
     L.tail_pending = true;
     L.k1_timed = true;
+    L.replayed = true;
     c->launches = 6;            // ticket reset, moments, scan, posterior, soft-NMS, fusion
     return BOD_OK;
 }
@@ -638,7 +657,7 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
     c->ev = c->evring[c->runs_recorded % bod_ctx::kEvRing];
     if (c->nlanes == 1) {
         c->cur = 0;
-        rc = run_range(c, c->lane[0], 0, c->cfg.B, lv, anchors, counts, st, st, c->timing);
+        rc = run_range(c, c->lane[0], 0, c->cfg.B, lv, anchors, counts, st, st, c->timing ? 2 : 0);
         if (rc) return rc;
         c->last_stream = st;
     } else {
@@ -667,12 +686,17 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
             // the block scheduler interleaves the two grids instead, every run finishes later and small batches lose
             // 20-25 %.)  With graphs the first run of a lane goes through the streams: one-time kernel attributes and
             // tables are set up there, and its head has to follow the previous lane's, which may have been a replay.
-            CU(c, cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
+            cudaStream_t hs = c->own_stream;
+            if (c->own_stream2 && !graphs && (c->head_flip ^= 1)) hs = c->own_stream2;
+            CU(c, cudaStreamWaitEvent(hs, c->ev_in, 0));
             if (graphs) {
                 const Lane& P = c->lane[(c->cur + c->nlanes - 1) % c->nlanes];
-                if (P.uses > 0) CU(c, cudaStreamWaitEvent(c->own_stream, P.head_done, 0));
+                if (P.uses > 0) CU(c, cudaStreamWaitEvent(hs, P.head_done, 0));
             }
-            rc = run_range(c, L, 0, c->cfg.B, lv, anchors, counts, c->own_stream, L.tail_stream, c->timing && !graphs);
+            // (pipelined: only the moments kernel is timed -- its launch time is what the roofline needs; seven event
+            // records per run are a tenth of the host time of a one-image run)
+            rc = run_range(c, L, 0, c->cfg.B, lv, anchors, counts, hs, L.tail_stream, (c->timing && !graphs) ? 1 : 0);
+            L.replayed = false;
             if (rc) return rc;
         }
         ++L.uses;
@@ -1015,6 +1039,11 @@ extern "C" int bod_last_stage_ms(bod_ctx* c, float ms[6]) {
     if (rc) return rc;
     if (!c->last_timed || c->runs_recorded == 0) return fail(c, BOD_ERR_STATE, "the last run recorded no stage events");
     cudaEvent_t* ev = c->evring[(c->runs_recorded - 1) % bod_ctx::kEvRing];
+    if (c->nlanes > 1) {                                     // pipelined contexts time the moments kernel only
+        for (int i = 1; i < 6; ++i) ms[i] = 0.0f;
+        CU(c, cudaEventElapsedTime(&ms[0], ev[0], ev[1]));
+        return BOD_OK;
+    }
     for (int i = 0; i < 5; ++i) CU(c, cudaEventElapsedTime(&ms[i], ev[i == 3 ? 6 : i], ev[i + 1]));
     CU(c, cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
     return BOD_OK;
@@ -1047,8 +1076,12 @@ extern "C" int bod_stage_ms_accum(bod_ctx* c, float sum_ms[6], int32_t* runs) {
     for (long long r = first; r < c->runs_recorded; ++r) {
         cudaEvent_t* ev = c->evring[r % bod_ctx::kEvRing];
         float ms = 0.0f;
-        for (int i = 0; i < 5; ++i) { CU(c, cudaEventElapsedTime(&ms, ev[i == 3 ? 6 : i], ev[i + 1])); sum_ms[i] += ms; }
-        CU(c, cudaEventElapsedTime(&ms, ev[0], ev[5])); sum_ms[5] += ms;
+        if (c->nlanes > 1) {                                 // pipelined contexts time the moments kernel only
+            CU(c, cudaEventElapsedTime(&ms, ev[0], ev[1])); sum_ms[0] += ms;
+        } else {
+            for (int i = 0; i < 5; ++i) { CU(c, cudaEventElapsedTime(&ms, ev[i == 3 ? 6 : i], ev[i + 1])); sum_ms[i] += ms; }
+            CU(c, cudaEventElapsedTime(&ms, ev[0], ev[5])); sum_ms[5] += ms;
+        }
         ++*runs;
     }
     c->runs_reported = c->runs_recorded;

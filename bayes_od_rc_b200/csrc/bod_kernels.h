@@ -3,7 +3,43 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <vector>
+
 namespace bod {
+
+// ---- launch-time attribute caches: one-image runs issue a kernel every few microseconds, where a
+// cudaFuncSetAttribute / occupancy query per launch is a visible share of the host time ----
+// cudaFuncAttributeMaxDynamicSharedMemorySize of `fn` on the current device is at least `bytes` afterwards
+inline cudaError_t ensure_dyn_smem(const void* fn, size_t bytes) {
+    struct Entry { const void* fn; int dev; size_t bytes; };
+    static std::mutex mu;
+    static std::vector<Entry> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (Entry& e : seen)
+        if (e.fn == fn && e.dev == dev) {
+            if (e.bytes >= bytes) return cudaSuccess;
+            cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (r == cudaSuccess) e.bytes = bytes;
+            return r;
+        }
+    cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (r == cudaSuccess) seen.push_back(Entry{fn, dev, bytes});
+    return r;
+}
+// SMs of the current device
+inline int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < 64) cached[dev] = sms;
+    return sms;
+}
 
 // Head outputs either as one tensor per kind ([B,N,A,*], n = 1) or as one tensor per FPN level
 // ([B,N,A_l,*], concatenated P3 -> P7 along the anchor axis by the reference, retinanet_model.py:82-112):

@@ -33,6 +33,73 @@ namespace bod {
 BOD_DEVINL float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 BOD_DEVINL float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// Packed binary32 pairs: sm_100 issues one FFMA2 / FADD2 for two values (the softmax loop is issue-bound, not
+// pipe-bound: the pipelined step shares its SMs with the posterior / soft-NMS / fusion kernels of earlier runs).
+BOD_DEVINL uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+BOD_DEVINL void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+BOD_DEVINL uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+BOD_DEVINL uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// H2 (inference_utils.py:31-32, 38): sum over the MC samples of softmax(logits row).  exp(x_k - c) for ANY common
+// shift c gives the same softmax; the shift used first is the row's background logit (the last column: the largest
+// entry of almost every anchor, and a few units from the largest one elsewhere), which costs one multiplication
+// instead of a max over the row.  Rows whose entries are so far apart that the sum leaves [1e-30, 1e30] (overflow,
+// total underflow, NaN) are redone with the row maximum.  Tolerance-checked output (<= 2e-6 absolute vs the oracle).
+template <int K> struct SoftmaxSum {
+    static constexpr int KP = K / 2;                 // whole pairs; an odd K keeps its last column in `last`
+    uint64_t p2[KP > 0 ? KP : 1];
+    float last;
+    BOD_DEVINL void clear() {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) p2[j] = 0ull;
+        last = 0.0f;
+    }
+    static BOD_DEVINL float terms(const float (&x)[K], float c, float (&e)[K]) {
+        constexpr float L = 1.4426950408889634f;     // exp(x - c') = 2^(x*log2e - c), c = c'*log2e
+        const uint64_t L2 = pk2(L, L), nc2 = pk2(-c, -c);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            float t0, t1;
+            upk2(fma2(pk2(x[2 * j], x[2 * j + 1]), L2, nc2), t0, t1);
+            e[2 * j] = ex2_approx(t0); e[2 * j + 1] = ex2_approx(t1);
+        }
+        if (K & 1) e[K - 1] = ex2_approx(__fmaf_rn(x[K - 1], L, -c));
+        float s = 0.0f;
+        if (KP > 0) {
+            uint64_t s2 = pk2(e[0], e[1]);
+#pragma unroll
+            for (int j = 1; j < KP; ++j) s2 = add2(s2, pk2(e[2 * j], e[2 * j + 1]));
+            float s0, s1;
+            upk2(s2, s0, s1);
+            s = s0 + s1;
+        }
+        if (K & 1) s += e[K - 1];
+        return s;
+    }
+    BOD_DEVINL void add_row(const float (&x)[K]) {
+        float e[K];
+        float s = terms(x, x[K - 1] * 1.4426950408889634f, e);
+        if (!(s >= 1e-30f && s <= 1e30f)) {
+            float m = x[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k) m = fmaxf(m, x[k]);
+            s = terms(x, m * 1.4426950408889634f, e);
+        }
+        const float inv = rcp_approx(s);
+        const uint64_t inv2 = pk2(inv, inv);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) p2[j] = fma2(pk2(e[2 * j], e[2 * j + 1]), inv2, p2[j]);
+        if (K & 1) last = __fmaf_rn(e[K - 1], inv, last);
+    }
+    BOD_DEVINL void mean(float scale, float (&p)[K]) const {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) { float a, b; upk2(p2[j], a, b); p[2 * j] = a * scale; p[2 * j + 1] = b * scale; }
+        if (K & 1) p[K - 1] = last * scale;
+    }
+};
+
 BOD_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 BOD_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -286,8 +353,8 @@ k1_moments_kernel(K1Args a, int NC) {
 
     // H2: softmax per sample, mean over samples (fast-math allowed here)
     float p[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) p[k] = 0.0f;
+    SoftmaxSum<K> acc;
+    acc.clear();
     for (int c = 0; c < nchunks; ++c) {
         const int n0 = c * NC, n1 = min(N, n0 + NC);
         const float* stage = ring + (USE_BULK ? (c & 1) : 0) * stage_stride;
@@ -309,16 +376,7 @@ k1_moments_kernel(K1Args a, int NC) {
                 float x[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) x[k] = row[k];
-                float m = x[0];
-#pragma unroll
-                for (int k = 1; k < K; ++k) m = fmaxf(m, x[k]);
-                float s = 0.0f;
-                const float m2 = m * -1.4426950408889634f;                 // exp(x - m) = 2^(x*log2e - m*log2e)
-#pragma unroll
-                for (int k = 0; k < K; ++k) { x[k] = ex2_approx(__fmaf_rn(x[k], 1.4426950408889634f, m2)); s += x[k]; }
-                const float inv = rcp_approx(s);
-#pragma unroll
-                for (int k = 0; k < K; ++k) p[k] = __fmaf_rn(x[k], inv, p[k]);
+                acc.add_row(x);
             }
         }
         if (USE_BULK && c + 2 < nchunks) {
@@ -326,10 +384,8 @@ k1_moments_kernel(K1Args a, int NC) {
             if (tid == 0) issue(c + 2);
         }
     }
+    acc.mean(1.0f / (float)N, p);
     if (valid) {
-        const float invN = 1.0f / (float)N;
-#pragma unroll
-        for (int k = 0; k < K; ++k) p[k] *= invN;
         if (a.probs_out != nullptr) {
             float* o = a.probs_out + ((size_t)b * a.A + anchor) * K;
 #pragma unroll
@@ -388,7 +444,10 @@ constexpr int kConsumerWarps = kTileAnchors / 32;
 
 constexpr int kPipeCtasPerSM = 6;   // resident CTAs per SM: their finalise phases overlap each other's streaming
 
-template <int K>
+// NSU > 0: the ring has exactly NSU stages and N is a multiple of NSU, so every tile starts at stage 0 and a round
+// of NSU samples is unrolled with every address a constant offset (no ring bookkeeping in the sample loop);
+// NSU = 0: any ring depth NS, any N.
+template <int K, int NSU>
 // Register cap of the pipeline kernel: 65536 / (MINBLOCKS * 160) -> 56 per thread.  Six CTAs of 56
 // registers leave ~11.7 k registers per SM, enough for one fusion (K4) CTA to run beside them in a
 // pipelined context; at 64 the kernel is ~1 % faster alone and the pipelined step ~2 % slower (measured).
@@ -452,18 +511,62 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
     }
 
     // ---- consumers: one thread per anchor of the tile ----
-    uint32_t full0 = smem_u32(&full_bar[0]);
+    // Shared-window addresses of the ring walk in registers: this thread's row and the full barrier of the current
+    // stage (its empty barrier sits a constant behind it); one compare per sample wraps both.
+    const uint32_t full0 = smem_u32(&full_bar[0]);
     constexpr uint32_t empty_minus_full = kMaxStages * 8;
-    uint32_t row0 = smem_u32(ring) + (uint32_t)tid * (uint32_t)(K * 4);
-    // opaque to the optimiser: otherwise it rematerialises the conversions (S2R SR_CgaCtaId + LEA) in every iteration
-    asm volatile("" : "+r"(full0), "+r"(row0));
+    const uint32_t row0 = smem_u32(ring) + (uint32_t)tid * (uint32_t)(K * 4);
     constexpr uint32_t kSlabBytes = (uint32_t)(slab_stride * 4);
-    uint32_t row_addr = row0, bar_off = 0;                   // this thread's row in the current stage; the stage's barrier offset
-    int stage = 0, phase = 0;
+    const uint32_t bar_end = full0 + (uint32_t)NS * 8u;
+    uint32_t row_addr = row0, bar = full0;
+    uint32_t phase = 0;
+    const float invN = 1.0f / (float)N;
     for (int tcount = 0;; ++tcount) {
-        mbar_wait_a(full0 + bar_off, (uint32_t)phase);       // first slab of the next tile, or the end marker
-        const int t = stage_tile[stage];
+        mbar_wait_a(bar, phase);                             // first slab of the next tile, or the end marker
+        const int t = stage_tile[NSU > 0 ? 0 : (bar - full0) >> 3];
         if (t < 0) break;
+
+        // H2: softmax per sample, mean over samples (fast-math allowed here).  Threads past the last anchor of a
+        // level's last tile run along on whatever their shared-memory rows hold (nothing of theirs is stored).
+        // Nothing but the ring state and the sums is live across this loop (the tile's coordinates are worked out
+        // behind it): at 56 registers per thread anything else is spilled or recomputed in every iteration.
+        SoftmaxSum<K> acc;
+        acc.clear();
+        if constexpr (NSU > 0) {
+#pragma unroll 1
+            for (int r = N; r > 0; r -= NSU) {
+#pragma unroll
+                for (int s = 0; s < NSU; ++s) {
+                    // (the first stage of a tile was waited for above: asking again returns at once, its phase cannot
+                    // advance before this warp has released the stage)
+                    mbar_wait_a(full0 + 8u * s, phase);
+                    float x[K];
+                    LoadRow<K>::run(row0 + kSlabBytes * s, x);
+                    acc.add_row(x);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(full0 + empty_minus_full + 8u * s);
+                }
+                phase ^= 1u;
+            }
+        } else {
+#pragma unroll 1
+            for (int n = N; n > 0; --n) {
+                if (n < N) mbar_wait_a(bar, phase);
+#ifdef BOD_DIAGNOSTICS
+                if (a.debug < 2)
+#endif
+                {
+                    float x[K];
+                    LoadRow<K>::run(row_addr, x);
+                    acc.add_row(x);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(bar + empty_minus_full);    // this warp is done with the stage
+                row_addr += kSlabBytes; bar += 8;
+                if (bar == bar_end) { bar = full0; row_addr = row0; phase ^= 1u; }
+            }
+        }
+
         const int b = t / tiles, tile = t - b * tiles;
         const TileRef tr = tile_ref(a.lv, tile);
         const int a0 = tile * kTileAnchors;                  // first slot of the tile
@@ -479,45 +582,12 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
 #pragma unroll
             for (int k = 0; k < K; ++k) cnt[k] = __ldg(c + k);
         }
-
-        // H2: softmax per sample, mean over samples (fast-math allowed here)
         float p[K];
+        acc.mean(invN, p);
+        if (valid && a.probs_out != nullptr) {
+            float* o = a.probs_out + ((size_t)b * a.A + anchor) * K;
 #pragma unroll
-        for (int k = 0; k < K; ++k) p[k] = 0.0f;
-        for (int n = 0; n < N; ++n) {
-            if (n > 0) mbar_wait_a(full0 + bar_off, (uint32_t)phase);
-#ifdef BOD_DIAGNOSTICS
-            if (valid && a.debug < 2) {
-#else
-            if (valid) {
-#endif
-                float x[K];
-                LoadRow<K>::run(row_addr, x);
-                float m = x[0];
-#pragma unroll
-                for (int k = 1; k < K; ++k) m = fmaxf(m, x[k]);
-                float s = 0.0f;
-                const float m2 = m * -1.4426950408889634f;                 // exp(x - m) = 2^(x*log2e - m*log2e)
-#pragma unroll
-                for (int k = 0; k < K; ++k) { x[k] = ex2_approx(__fmaf_rn(x[k], 1.4426950408889634f, m2)); s += x[k]; }
-                const float inv = rcp_approx(s);
-#pragma unroll
-                for (int k = 0; k < K; ++k) p[k] = __fmaf_rn(x[k], inv, p[k]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(full0 + empty_minus_full + bar_off);  // this warp is done with the stage
-            row_addr += kSlabBytes; bar_off += 8;
-            if (++stage == NS) { stage = 0; phase ^= 1; row_addr = row0; bar_off = 0; }
-        }
-        if (valid) {
-            const float invN = 1.0f / (float)N;
-#pragma unroll
-            for (int k = 0; k < K; ++k) p[k] *= invN;
-            if (a.probs_out != nullptr) {
-                float* o = a.probs_out + ((size_t)b * a.A + anchor) * K;
-#pragma unroll
-                for (int k = 0; k < K; ++k) o[k] = p[k];
-            }
+            for (int k = 0; k < K; ++k) o[k] = p[k];
         }
 
 #ifdef BOD_DIAGNOSTICS
@@ -589,16 +659,56 @@ static int k1_ctas_per_sm() {
     return v;
 }
 static int k1_pipe_ctas(const K1Args& a) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (const char* e = getenv("BOD_K1_SMS")) { const int x = atoi(e); if (x >= 1 && x < sms) sms = x; }   // experiment: leave SMs free
+    int sms = sm_count();
+    static const int sms_env = getenv("BOD_K1_SMS") ? atoi(getenv("BOD_K1_SMS")) : 0;                      // experiment: leave SMs free
+    if (sms_env >= 1 && sms_env < sms) sms = sms_env;
     int ctas = k1_ctas_per_sm() * sms;
     if (ctas > a.B * a.tiles) ctas = a.B * a.tiles;
     return ctas;
 }
 uint32_t k1_tickets_per_launch(const K1Args& a) {
     return k1_aligned(a) ? (uint32_t)(a.B * a.tiles + k1_pipe_ctas(a)) : 0u;
+}
+
+// The pipeline kernel for (K, ring): rounds of NSU samples unrolled for the class counts and ring depths of the
+// BASELINE configurations, the generic ring walk (NSU = 0) otherwise.
+template <int K>
+static const void* k1_pipe_func(int nsu) {
+    if constexpr (K == 4 || K == 8 || K == 11) {
+        switch (nsu) {
+            case 3: return (const void*)k1_moments_pipe_kernel<K, 3>;
+            case 4: return (const void*)k1_moments_pipe_kernel<K, 4>;
+            case 5: return (const void*)k1_moments_pipe_kernel<K, 5>;
+            case 6: return (const void*)k1_moments_pipe_kernel<K, 6>;
+            case 8: return (const void*)k1_moments_pipe_kernel<K, 8>;
+            case 10: return (const void*)k1_moments_pipe_kernel<K, 10>;
+            default: break;
+        }
+    }
+    return (const void*)k1_moments_pipe_kernel<K, 0>;
+}
+struct K1Plan { const void* fn; int NS; size_t ring; };
+template <int K>
+static K1Plan k1_plan(const K1Args& a) {
+    const size_t slab = (size_t)kTileAnchors * K * sizeof(float);
+    // Ring depth: all the shared memory of the SM when K1 runs alone.  In a pipelined context one posterior CTA
+    // (20.5 KB + 1 KB) and one fusion CTA (26.5 KB + 1 KB) have to fit beside the resident K1 CTAs (each: ring +
+    // 0.75 KB static + 1 KB reserved) in the SM's 228 KB.
+    const unsigned per_cta = a.leave_room ? (228u * 1024u - 50u * 1024u) / k1_ctas_per_sm() - 1792u
+                                          : 216u * 1024u / k1_ctas_per_sm() - 1024u;
+    int NS = (int)(per_cta / slab);
+    static const int ns_env = getenv("BOD_K1_NS") ? atoi(getenv("BOD_K1_NS")) : 0;                          // experiment: shallower ring
+    if (ns_env >= 2 && ns_env < NS) NS = ns_env;
+    if (NS > kMaxStages) NS = kMaxStages;
+    if (NS < 2) NS = 2;
+    int nsu = 0;
+    static const bool unroll = !(getenv("BOD_K1_UNROLL") && atoi(getenv("BOD_K1_UNROLL")) == 0);           // experiment: generic walk
+    if (unroll && (K == 4 || K == 8 || K == 11)) {
+        static const int cand[] = {10, 8, 6, 5, 4, 3};
+        for (int c : cand) if (c <= NS && a.N % c == 0) { nsu = c; break; }
+    }
+    if (nsu > 0) NS = nsu;
+    return K1Plan{k1_pipe_func<K>(nsu), NS, (size_t)NS * slab};
 }
 
 template <int K>
@@ -615,20 +725,16 @@ static cudaError_t launch_k(const K1Args& a, cudaStream_t st) {
     cudaError_t e;
     if (aligned) {
         // persistent pipeline: kPipeCtasPerSM CTAs per SM, each with a ring of NS one-sample slabs
-        // ring depth: all the shared memory of the SM when K1 runs alone; in a pipelined context ~56 KB per SM
-        // are left for the posterior / fusion CTAs that run beside it (one of each fits)
-        const unsigned budget = a.leave_room ? 176u * 1024u : 216u * 1024u;
-        int NS = (int)((budget / k1_ctas_per_sm() - 1024u - (a.leave_room ? 1792u : 0u)) / slab);
-        if (const char* e2 = getenv("BOD_K1_NS")) { const int x = atoi(e2); if (x >= 2 && x < NS) NS = x; }   // experiment: shallower ring
-        if (NS > kMaxStages) NS = kMaxStages;
-        if (NS < 2) NS = 2;
-        const size_t ring = (size_t)NS * slab;
+        const K1Plan pl = k1_plan<K>(a);
+        int NS = pl.NS;
         const int ctas = k1_pipe_ctas(a);
-        e = cudaFuncSetAttribute(k1_moments_pipe_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+        e = ensure_dyn_smem(pl.fn, pl.ring);
         if (e != cudaSuccess) return e;
-        k1_moments_pipe_kernel<K><<<ctas, kTileAnchors + 32, ring, st>>>(a, NS);
+        K1Args aa = a;
+        void* args[2] = {&aa, &NS};
+        return cudaLaunchKernel(pl.fn, dim3(ctas), dim3(kTileAnchors + 32), args, pl.ring, st);
     } else {
-        e = cudaFuncSetAttribute(k1_moments_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = ensure_dyn_smem((const void*)k1_moments_kernel<K, false>, smem);
         if (e != cudaSuccess) return e;
         k1_moments_kernel<K, false><<<grid, block, smem, st>>>(a, NC);
     }
@@ -679,7 +785,7 @@ cudaError_t launch_k1(const K1Args& a0, cudaStream_t st) {
 // launch of it at new arguments (same shapes; other input tensors) ----
 template <int K>
 static const void* k1_func_k(const K1Args& a) {
-    return k1_aligned(a) ? (const void*)k1_moments_pipe_kernel<K> : (const void*)k1_moments_kernel<K, false>;
+    return k1_aligned(a) ? k1_plan<K>(a).fn : (const void*)k1_moments_kernel<K, false>;
 }
 const void* k1_kernel_func(const K1Args& a) {
     switch (a.K) {

@@ -282,7 +282,10 @@ cudaError_t launch_generate_anchors(int im_h, int im_w, float* anchors, cudaStre
 // ---------------------------------------------------------------------------
 // K2
 // ---------------------------------------------------------------------------
-constexpr int kK2Threads = 128;
+#ifndef BOD_K2_THREADS
+#define BOD_K2_THREADS 128
+#endif
+constexpr int kK2Threads = BOD_K2_THREADS;
 
 // tfp.math.fill_triangular(x0..x9) element (i,j), lower triangle
 // (retinanet_model.py:110): rows of concat(x[4:], reverse(x)) reshaped 4x4.
@@ -588,14 +591,23 @@ __global__ void __launch_bounds__(1024) rank_normalise_kernel(K2Args a) {
 template <int K>
 static cudaError_t launch_k2_k(const K2Args& a, const AnchorLevels& L, cudaStream_t st) {
     const size_t smem = (size_t)a.N * 4 * kK2Threads * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(k2_posterior_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dyn_smem((const void*)k2_posterior_kernel<K>, smem);
     if (e != cudaSuccess) return e;
     // persistent grid: as many CTAs as are resident at once (chunks of 128 survivors are taken grid-stride)
-    int dev = 0, sms = 148, per_sm = 4;
+    const int sms = sm_count();
+    static std::mutex mu;
+    static int occ_N[64] = {0}, occ_v[64] = {0};         // resident CTAs per SM for the last N seen on the device
+    int dev = 0, per_sm = 4;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_posterior_kernel<K>, kK2Threads, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 4;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 0 && dev < 64 && occ_N[dev] == a.N && occ_v[dev] > 0) per_sm = occ_v[dev];
+        else {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_posterior_kernel<K>, kK2Threads, smem) != cudaSuccess || per_sm < 1)
+                per_sm = 4;
+            if (dev >= 0 && dev < 64) { occ_N[dev] = a.N; occ_v[dev] = per_sm; }
+        }
+    }
     k2_posterior_kernel<K><<<sms * per_sm, kK2Threads, smem, st>>>(a, L);
     return cudaGetLastError();
 }

@@ -326,7 +326,9 @@ BOD_DEVINL int ent_pairs(uint32_t e) { return (int)((e >> 14) & 63u); }
 // Returns the new score (>= 0), the negated bound, or -inf (removed by hard-NMS).
 #ifdef BOD_DIAGNOSTICS
 __device__ unsigned long long g_k3_cnt[8];     // 0 walks, 1 bounded (lazy) walks, 2 untouched, 3 products, 4 product entries, 5 folds, 6 woken
-#define K3_CNT(i, v) atomicAdd(&g_k3_cnt[i], (unsigned long long)(v))
+#endif
+#if defined(BOD_DIAGNOSTICS) && (BOD_DIAGNOSTICS + 0) >= 2   // event counters (global atomics: they cost a third of the kernel's time);
+#define K3_CNT(i, v) atomicAdd(&g_k3_cnt[i], (unsigned long long)(v))   // -DBOD_DIAGNOSTICS alone keeps the phase timers only
 #else
 #define K3_CNT(i, v)
 #endif

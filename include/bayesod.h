@@ -312,7 +312,10 @@ int bod_synchronize(bod_ctx* ctx);
 
 /* Device-time of the last run per stage in milliseconds (events recorded on the
  * run's stream): [0]=moments/filter, [1]=scan, [2]=posterior, [3]=soft-NMS,
- * [4]=fusion, [5]=total.  Syncs on the run. */
+ * [4]=fusion, [5]=total.  Syncs on the run.  Pipelined contexts (pipeline_depth
+ * > 1) time the moments kernel only: [1..5] read as zero there (the stages of
+ * consecutive runs overlap, and the event records of a one-image run are a
+ * visible share of its host time). */
 int bod_last_stage_ms(bod_ctx* ctx, float ms[6]);
 /* Stage events are recorded by default (6 cudaEventRecord per run); switch them
  * off for latency-critical callers. */

@@ -447,6 +447,38 @@ def test_philox_sampler_matches_restatement():
         compare_image_with_oracle(eng, res, b, r, spec.K)
 
 
+@pytest.mark.parametrize("K,N", [(11, 10), (8, 6), (4, 20), (7, 5)])
+def test_softmax_rows_far_apart(K, N):
+    """Mean class probabilities on logit rows the fast shift cannot handle: the moments kernel shifts every row by
+    its background logit first and redoes rows whose sum leaves [1e-30, 1e30] with the row maximum (overflow,
+    total underflow).  Rows: foreground far above / below the background, huge common offsets, one dominant column.
+    Covers the unrolled (K = 4, 8, 11 with N a multiple of the ring depth) and the generic sample loop."""
+    spec = synthetic.SceneSpec(im_h=96, im_w=160, N=N, K=K, g_min=3, g_max=5, box_hi=90., config_id=77)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, 2, with_counts=False))
+    cls = batch["cls"].copy()
+    A = cls.shape[2]
+    rng = np.random.default_rng(5)
+    rows = rng.permutation(A)[:600]
+    for i, a in enumerate(rows):
+        kind = i % 6
+        if kind == 0: cls[:, :, a, rng.integers(0, K - 1)] += 95.0            # exp overflows against the background shift
+        elif kind == 1: cls[:, :, a, K - 1] -= 120.0                          # every foreground column overflows
+        elif kind == 2: cls[:, :, a, :K - 1] -= 110.0                         # foreground underflows: background only
+        elif kind == 3: cls[:, :, a, :] += 3000.0 * (1 if i % 12 == 3 else -1)   # common offset
+        elif kind == 4: cls[:, rng.integers(0, N), a, rng.integers(0, K)] += 200.0   # one sample only
+        else: cls[:, :, a, :] *= 40.0                                          # spread rows
+    oc = oracle.OracleConfig(seed=3, image_id_base=11)
+    eng, res = run_gpu_batch(oc, cls, batch["box"], batch["cov"], batch["anchors"], None)
+    for b in range(2):
+        p = eng.probs(b)
+        ref = oracle.softmax_mean(cls[b], real="f64")
+        assert np.isfinite(p).all()
+        err = np.abs(p.astype(np.float64) - ref).max()
+        assert err <= 2e-6, f"image {b}: mean class probabilities differ by {err}"
+        c = eng.sampled_counts(b)
+        assert_bit_equal(c, oracle.philox_counts(p, 30, 3, 11 + b), "philox counts")
+
+
 def test_sampler_fast_path_equals_full_counts():
     """Without emit_probs the sampler skips the per-class draws of background-majority anchors;
     the survivors and everything downstream must not change."""
