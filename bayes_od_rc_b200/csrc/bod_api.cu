@@ -48,16 +48,15 @@ struct Lane {
     unsigned char* block = nullptr;                   // the lane's result arrays are one contiguous block (bod_result_block_layout)
     int32_t* block_status = nullptr;                  // its last word: the context's status as of the end of the lane's last tail
     const int32_t* h_block_status = nullptr;          // where that word lands on the host (last bod_fetch_block_async)
-    cudaEvent_t k1_begin = nullptr, k1_end = nullptr; // timing of the lane's last replayed moments kernel
-    bool k1_timed = false;
-    bool replayed = false;            // the lane's last run was a graph replay (k1_end was recorded by its head graph)
+    unsigned long long* clk = nullptr; // launch clock of the lane's moments kernels (K1Args::clk): [2 + 2 * kClkSlots]
+    unsigned long long clk_read = 0;   // launches already folded into a report
+    unsigned long long* tl = nullptr; // BOD_TIMELINE (diagnostic builds only): [5 kernels][4] timeline stamps of the lane's last run
 };
 
 // what run_range does differently while a lane's graphs are being captured: only one half of the run is
 // issued (1: the head -- ticket reset, moments kernel, scan; 2: the tail -- posterior, soft-NMS, fusion)
 struct GraphHooks {
     int phase;
-    cudaEvent_t k1_begin, k1_end;     // timing of the moments kernel (event nodes in the head graph)
     K1Args* k1_out; K2Args* k2_out;   // the arguments the captured moments / posterior kernels were given
 };
 
@@ -108,7 +107,6 @@ struct bod_ctx {
     bool k2_on_tail = true;           // pipelined contexts: K2 rides with the tail (see run_range); BOD_K2_TAIL=0 keeps it on the head
     bool use_graphs = true;           // pipelined contexts replay each lane's run as a CUDA graph (BOD_GRAPHS=0: stream launches)
     bool force_graphs = false;        // BOD_GRAPHS=2: also for short runs
-    double g_k1_ms = 0.0; long long g_k1_runs = 0;    // moments-kernel time of replayed runs (harvested when a lane is reused)
     long long next_ticket = 0;        // tickets of issued runs: 1, 2, 3, ...
     int64_t block_off[10] = {0};      // result block: offsets of num_dets, num_survivors, means, covs, cat_param, cat_count,
     int64_t block_bytes = 0;          //   nms_indices, centre_anchor_idx, centre_scores, status; total size
@@ -305,17 +303,22 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     }
     for (auto& set : c->evring) for (auto& ev : set) cudaEventCreate(&ev);
     for (auto& ev : c->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (int l = 0; l < c->nlanes; ++l) {
+        cudaMalloc(&c->lane[l].clk, (2 + 2 * kClkSlots) * sizeof(unsigned long long));
+        cudaMemset(c->lane[l].clk, 0, (2 + 2 * kClkSlots) * sizeof(unsigned long long));
+    }
     c->timing = getenv("BOD_NO_STAGE_EVENTS") == nullptr;
 #ifdef BOD_DIAGNOSTICS
     if (const char* d = getenv("BOD_K1_DEBUG")) c->k1_debug = atoi(d);
     if (const char* d = getenv("BOD_DEBUG_SKIP")) c->skip_mask = atoi(d);
+    if (getenv("BOD_TIMELINE"))
+        for (int l = 0; l < c->nlanes; ++l) { cudaMalloc(&c->lane[l].tl, 20 * sizeof(unsigned long long)); cudaMemset(c->lane[l].tl, 0, 20 * sizeof(unsigned long long)); }
     if (getenv("BOD_K3_DEBUG")) { cudaMalloc(&c->k3_dbg, ((size_t)B * 384 + 8) * sizeof(long long)); cudaMemset(c->k3_dbg, 0, ((size_t)B * 384 + 8) * sizeof(long long)); }
 #endif
     c->host_copy_all = getenv("BOD_HOST_COPY_ALL") != nullptr;
     if (const char* d = getenv("BOD_K2_TAIL")) c->k2_on_tail = atoi(d) != 0;
     if (const char* d = getenv("BOD_GRAPHS")) { c->use_graphs = atoi(d) != 0; c->force_graphs = atoi(d) >= 2; }
     for (int l = 0; l < c->nlanes; ++l) {
-        cudaEventCreate(&c->lane[l].k1_begin); cudaEventCreate(&c->lane[l].k1_end);
         cudaEventCreateWithFlags(&c->lane[l].fetch_done, cudaEventDisableTiming);
         cudaMallocHost(&c->lane[l].h_status, sizeof(int32_t));
         if (c->lane[l].h_status) *c->lane[l].h_status = 0;
@@ -342,8 +345,7 @@ extern "C" void bod_destroy(bod_ctx* c) {
     for (auto& L : c->lane) {
         if (L.head_done) cudaEventDestroy(L.head_done);
         if (L.tail_done) cudaEventDestroy(L.tail_done);
-        if (L.k1_begin) cudaEventDestroy(L.k1_begin);
-        if (L.k1_end) cudaEventDestroy(L.k1_end);
+        if (L.clk) cudaFree(L.clk);
         if (L.fetch_done) cudaEventDestroy(L.fetch_done);
         if (L.h_status) cudaFreeHost(L.h_status);
         for (int i = 0; i < 2; ++i) {
@@ -393,10 +395,9 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     // that tail is done -- also when K2 stays on the head stream (pre-NMS filter), where the scans would otherwise
     // rewrite num_survivors under a running tail.
     if (hs != ts && L.tail_pending) CU(c, cudaStreamWaitEvent(hs, L.tail_done, 0));
-    const bool do_head = !gh || gh->phase == 1, do_tail = !gh || gh->phase == 2;   // graph capture: one half at a time
+    const bool do_head = !gh || (gh->phase & 1), do_tail = !gh || (gh->phase & 2);   // graph capture: one half at a time, or both (3)
     // (the moments kernel's tile scheduler counts tickets from zero: the slab starts zeroed and every launch puts
     // the counter back itself; launches of a context never overlap)
-    if (gh && do_head) CU(c, cudaEventRecordWithFlags(gh->k1_begin, hs, cudaEventRecordExternal));
     if (record) CU(c, cudaEventRecord(c->ev[0], hs));
     K1Args k1{};
     k1.lv = lv; k1.counts_in = counts;
@@ -411,8 +412,10 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
 #endif
     k1.leave_room = (hs != ts || gh) ? 1 : 0;
     k1.ticket = L.tile_ticket; k1.ticket_base = 0u;
+    k1.tl = L.tl;
+    k1.clk = L.clk;
     if (do_head) CU(c, launch_k1(k1, hs));
-    if (gh && do_head) { CU(c, cudaEventRecordWithFlags(gh->k1_end, hs, cudaEventRecordExternal)); *gh->k1_out = k1; }
+    if (gh && do_head) *gh->k1_out = k1;
     if (record) CU(c, cudaEventRecord(c->ev[1], hs));
 
     int launches = 3;
@@ -422,6 +425,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     sc.tile_count = k1.tile_count; sc.tile_off = L.tile_off + (size_t)b0 * (c->tiles + 1);
     sc.num_survivors = L.num_survivors + b0; sc.status = c->status;
     sc.B = nb; sc.tiles = c->tiles; sc.capacity = c->capacity;
+    sc.tl = L.tl ? L.tl + 4 : nullptr;
     if (c->prefilter && do_head) {
         // scan (dense indexing of the slots) -> filter -> scan again on the new counts; the capacity check
         // belongs to the second scan only
@@ -459,6 +463,8 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
         CU(c, launch_scan(sc, hs));
         if (record > 1) CU(c, cudaEventRecord(c->ev[2], hs));
     }
+    // one graph for the whole run: "the head is done" is an event node between the scan and the posterior kernel
+    if (gh && gh->phase == 3) CU(c, cudaEventRecordWithFlags(L.head_done, hs, cudaEventRecordExternal));
     if (!do_tail) return BOD_OK;
     if (scan_in_tail_graph) CU(c, launch_scan(sc, ts, true));
     if (k2_tail) {
@@ -486,6 +492,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
                          g.dirichlet_prior != BOD_PRIOR_NONE) ? 1 : 0;
     k2.isotropic_variance = g.isotropic_variance; k2.scale_v = g.scale_v; k2.scale_u = g.scale_u;
     k2.anchor_mode = g.anchor_mode; k2.im_h = g.im_h; k2.im_w = g.im_w;
+    k2.tl = L.tl ? L.tl + 8 : nullptr;
 #ifdef BOD_DIAGNOSTICS
     if (!(c->skip_mask & 1))
 #endif
@@ -510,6 +517,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     k3.B = nb; k3.capacity = c->capacity; k3.Dmax = c->Dmax;
     k3.iou_threshold = g.iou_threshold; k3.soft_nms_sigma = g.soft_nms_sigma;
     k3.threads = c->k3_threads; k3.force_big = c->k3_force_big; k3.psm_max = c->k3_psm_max; k3.seg_cap = c->k3_seg_cap;
+    k3.tl = L.tl ? L.tl + 12 : nullptr;
 #ifdef BOD_DIAGNOSTICS
     k3.dbg = c->k3_dbg ? c->k3_dbg + (size_t)b0 * 384 : nullptr;
     if (!(c->skip_mask & 2))
@@ -525,6 +533,7 @@ static int run_range(bod_ctx* c, Lane& L, int b0, int nb, const LevelTable& lv,
     k4.out_param = L.out_param + b0 * D * K; k4.out_count = L.out_count + b0 * D * K;
     k4.B = nb; k4.K = g.K; k4.capacity = c->capacity; k4.Dmax = c->Dmax; k4.words = c->words;
     k4.calibration = g.cov_calibration; k4.iou_threshold = g.iou_threshold;
+    k4.tl = L.tl ? L.tl + 16 : nullptr;
     // the context's (sticky) status word rides in the lane's result block, so a block fetch brings it along
     k4.status_in = c->status; k4.status_out = (b0 + nb == c->cfg.B) ? L.block_status : nullptr;
 #ifdef BOD_DIAGNOSTICS
@@ -552,13 +561,21 @@ static int check_inputs(bod_ctx* c, const float* cls, const float* box, const fl
     return BOD_OK;
 }
 
-// moments-kernel time of the lane's last replayed run (if it has finished), into the context's accumulators
-static void harvest_k1_time(bod_ctx* c, Lane& L) {
-    if (!L.k1_timed) return;
-    float ms = 0.0f;
-    if (cudaEventElapsedTime(&ms, L.k1_begin, L.k1_end) == cudaSuccess) { c->g_k1_ms += ms; ++c->g_k1_runs; }
-    else cudaGetLastError();
-    L.k1_timed = false;
+// Durations of the lane's moments-kernel launches that no report has covered yet (its launch clock: the last
+// kClkSlots launches at most), added to *sum_ms / *runs.  The caller has synchronised with the lane's work.
+static int fold_launch_clock(bod_ctx* c, Lane& L, double* sum_ms, long long* runs) {
+    if (!L.clk) return BOD_OK;
+    unsigned long long h[2 + 2 * kClkSlots];
+    CU(c, cudaMemcpy(h, L.clk, sizeof h, cudaMemcpyDeviceToHost));
+    const unsigned long long n = h[0];
+    unsigned long long first = L.clk_read;
+    if (n - first > (unsigned long long)kClkSlots) first = n - kClkSlots;
+    for (unsigned long long i = first; i < n; ++i) {
+        const unsigned long long t0 = h[2 + 2 * (i % kClkSlots)], t1 = h[3 + 2 * (i % kClkSlots)];
+        if (t1 > t0) { *sum_ms += (double)(t1 - t0) * 1e-6; ++*runs; }
+    }
+    L.clk_read = n;
+    return BOD_OK;
 }
 
 // Capture (first replay of a lane) or re-point (input tensors changed) the lane's two graphs -- head: ticket
@@ -567,32 +584,36 @@ static void harvest_k1_time(bod_ctx* c, Lane& L) {
 // cudaEventRecord, so its meaning for later cudaStreamWaitEvent calls is the usual one.
 static int capture_half(bod_ctx* c, Lane& L, int phase, const LevelTable& lv, const float* anchors, const float* counts) {
     cudaStream_t ls = L.tail_stream;
-    GraphHooks gh{phase, L.k1_begin, L.k1_end, &L.ga1, &L.ga2};
+    GraphHooks gh{phase, &L.ga1, &L.ga2};
     CU(c, cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed));
     int rc = run_range(c, L, 0, c->cfg.B, lv, anchors, counts, ls, ls, false, &gh);
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(ls, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(c, BOD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-    L.graph[phase - 1] = g;
-    // the kernel node whose arguments follow the caller's tensors
+    const int slot = phase == 2 ? 1 : 0;
+    L.graph[slot] = g;
+    // the kernel nodes whose arguments follow the caller's tensors
     size_t n = 0;
     CU(c, cudaGraphGetNodes(g, nullptr, &n));
     std::vector<cudaGraphNode_t> nodes(n);
     CU(c, cudaGraphGetNodes(g, nodes.data(), &n));
-    const void* want = phase == 1 ? k1_kernel_func(L.ga1) : k2_kernel_func(L.ga2);
-    cudaGraphNode_t found = nullptr;
-    for (cudaGraphNode_t nd : nodes) {
-        cudaGraphNodeType t;
-        CU(c, cudaGraphNodeGetType(nd, &t));
-        if (t != cudaGraphNodeTypeKernel) continue;
-        cudaKernelNodeParams p;
-        CU(c, cudaGraphKernelNodeGetParams(nd, &p));
-        if (p.func == want) found = nd;
+    for (int which = 1; which <= 2; ++which) {
+        if (!(phase & which)) continue;
+        const void* want = which == 1 ? k1_kernel_func(L.ga1) : k2_kernel_func(L.ga2);
+        cudaGraphNode_t found = nullptr;
+        for (cudaGraphNode_t nd : nodes) {
+            cudaGraphNodeType t;
+            CU(c, cudaGraphNodeGetType(nd, &t));
+            if (t != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams p;
+            CU(c, cudaGraphKernelNodeGetParams(nd, &p));
+            if (p.func == want) found = nd;
+        }
+        if (!found) return fail(c, BOD_ERR_CUDA, "graph capture: %s kernel node not found", which == 1 ? "moments" : "posterior");
+        (which == 1 ? L.gk1 : L.gk2) = found;
     }
-    if (!found) return fail(c, BOD_ERR_CUDA, "graph capture: %s kernel node not found", phase == 1 ? "moments" : "posterior");
-    (phase == 1 ? L.gk1 : L.gk2) = found;
-    CU(c, cudaGraphInstantiate(&L.gexec[phase - 1], g, 0));
+    CU(c, cudaGraphInstantiate(&L.gexec[slot], g, 0));
     return BOD_OK;
 }
 
@@ -600,14 +621,16 @@ static int replay_run(bod_ctx* c, Lane& L, const LevelTable& lv, const float* an
     cudaStream_t ls = L.tail_stream;
     if (L.gexec[0] && (L.ga1.counts_in == nullptr) != (counts == nullptr)) {   // sampler <-> injected counts: other outputs
         for (int i = 0; i < 2; ++i) {
-            cudaGraphExecDestroy(L.gexec[i]); cudaGraphDestroy(L.graph[i]);
+            if (L.gexec[i]) cudaGraphExecDestroy(L.gexec[i]);
+            if (L.graph[i]) cudaGraphDestroy(L.graph[i]);
             L.gexec[i] = nullptr; L.graph[i] = nullptr;
         }
     }
-    harvest_k1_time(c, L);
+    // BOD_MERGED_GRAPH=1 (experiment): one graph per run, the posterior kernel right behind the scan
+    static const bool merged = getenv("BOD_MERGED_GRAPH") && atoi(getenv("BOD_MERGED_GRAPH")) != 0;
     if (!L.gexec[0]) {
-        int rc = capture_half(c, L, 1, lv, anchors, counts);
-        if (!rc) rc = capture_half(c, L, 2, lv, anchors, counts);
+        int rc = merged ? capture_half(c, L, 3, lv, anchors, counts) : capture_half(c, L, 1, lv, anchors, counts);
+        if (!rc && !merged) rc = capture_half(c, L, 2, lv, anchors, counts);
         if (rc) return rc;
     } else {
         K1Args a1 = L.ga1;
@@ -623,7 +646,7 @@ static int replay_run(bod_ctx* c, Lane& L, const LevelTable& lv, const float* an
         a2.scale_v = c->cfg.scale_v; a2.scale_u = c->cfg.scale_u;
         if (!cov_width(c->cfg.cov_layout)) for (int l = 0; l < a2.lv.n; ++l) a2.lv.cov[l] = nullptr;
         if (memcmp(&a2, &L.ga2, sizeof a2) != 0) {
-            cudaError_t e = k2_graph_update(L.gexec[1], L.gk2, a2);
+            cudaError_t e = k2_graph_update(L.gexec[merged ? 0 : 1], L.gk2, a2);
             if (e != cudaSuccess) return fail(c, BOD_ERR_CUDA, "graph update (posterior kernel): %s", cudaGetErrorString(e));
             L.ga2 = a2;
         }
@@ -631,17 +654,14 @@ static int replay_run(bod_ctx* c, Lane& L, const LevelTable& lv, const float* an
     // the caller's tensors are ready; the previous lane's moments kernel is done (one moments kernel at a time has the GPU)
     const Lane& P = c->lane[(int)((&L - c->lane) + c->nlanes - 1) % c->nlanes];
     CU(c, cudaStreamWaitEvent(ls, c->ev_in, 0));
-    // (BOD_K1_CHAIN=1: behind the previous lane's moments kernel itself -- the event node right behind it in that
-    // lane's head graph -- instead of behind its whole head, whose scan then runs beside this moments kernel)
-    static const bool k1_chain = getenv("BOD_K1_CHAIN") && atoi(getenv("BOD_K1_CHAIN")) != 0;
-    CU(c, cudaStreamWaitEvent(ls, (k1_chain && P.replayed) ? P.k1_end : P.head_done, 0));
+    CU(c, cudaStreamWaitEvent(ls, P.head_done, 0));
     CU(c, cudaGraphLaunch(L.gexec[0], ls));
-    CU(c, cudaEventRecord(L.head_done, ls));
-    CU(c, cudaGraphLaunch(L.gexec[1], ls));
+    if (!merged) {
+        CU(c, cudaEventRecord(L.head_done, ls));
+        CU(c, cudaGraphLaunch(L.gexec[1], ls));
+    }
     CU(c, cudaEventRecord(L.tail_done, ls));
     L.tail_pending = true;
-    L.k1_timed = true;
-    L.replayed = true;
     c->launches = 6;            // ticket reset, moments, scan, posterior, soft-NMS, fusion
     return BOD_OK;
 }
@@ -672,7 +692,7 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
         // with a fetch per run, graphs 44.9 k without and 33.9 k with it).  BOD_GRAPHS=2 forces replay.
         const bool long_run = 4.0 * c->cfg.B * c->cfg.N * c->cfg.A * c->cfg.K >= 0.8e9;
         const bool graphs = c->use_graphs && !c->prefilter && c->k2_on_tail && (long_run || c->force_graphs);
-        if (graphs) recorded = false;
+        recorded = false;         // pipelined contexts record no stage events (the moments kernel keeps a launch clock)
         if (graphs && L.uses > 0) {
             // Replay: the whole run (moments, scan, posterior, soft-NMS, fusion) is one graph launch on the lane's
             // stream -- a dozen stream calls per run make batches of a few images host-bound.  Stream order puts it
@@ -693,10 +713,10 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
                 const Lane& P = c->lane[(c->cur + c->nlanes - 1) % c->nlanes];
                 if (P.uses > 0) CU(c, cudaStreamWaitEvent(hs, P.head_done, 0));
             }
-            // (pipelined: only the moments kernel is timed -- its launch time is what the roofline needs; seven event
-            // records per run are a tenth of the host time of a one-image run)
-            rc = run_range(c, L, 0, c->cfg.B, lv, anchors, counts, hs, L.tail_stream, (c->timing && !graphs) ? 1 : 0);
-            L.replayed = false;
+            // (pipelined: no stage events -- seven event records per run are a tenth of the host time of a one-image run,
+            // and timing events around the moments kernel put ~10 us between two of them; the moments kernel keeps its
+            // own launch clock instead, K1Args::clk)
+            rc = run_range(c, L, 0, c->cfg.B, lv, anchors, counts, hs, L.tail_stream, 0);
             if (rc) return rc;
         }
         ++L.uses;
@@ -1016,6 +1036,16 @@ extern "C" int bod_fetch_sampled_counts(bod_ctx* c, int32_t b, float* counts) {
 }
 
 #ifdef BOD_DIAGNOSTICS
+// diagnostic builds only (not part of the public header): the timeline stamps of every lane's last run,
+// out[lane][kernel: moments, scan, posterior, soft-NMS, fusion][first CTA start, last CTA start, end, -] in ns
+extern "C" int bod_debug_timeline(bod_ctx* c, unsigned long long* out) {
+    if (!c || !out || !c->lane[0].tl) return BOD_ERR_STATE;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    for (int l = 0; l < c->nlanes; ++l)
+        CU(c, cudaMemcpy(out + 20 * l, c->lane[l].tl, 20 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return BOD_OK;
+}
 // diagnostic builds only (not part of the public header): per-image, per-warp soft-NMS phase cycle counters
 extern "C" int bod_debug_k3_counters(bod_ctx* c, long long* out) {
     if (!c || !out || !c->k3_dbg) return BOD_ERR_STATE;
@@ -1037,13 +1067,19 @@ extern "C" int bod_last_stage_ms(bod_ctx* c, float ms[6]) {
     if (!c || !ms) return BOD_ERR_INVALID;
     int rc = sync_and_status(c);
     if (rc) return rc;
-    if (!c->last_timed || c->runs_recorded == 0) return fail(c, BOD_ERR_STATE, "the last run recorded no stage events");
-    cudaEvent_t* ev = c->evring[(c->runs_recorded - 1) % bod_ctx::kEvRing];
-    if (c->nlanes > 1) {                                     // pipelined contexts time the moments kernel only
-        for (int i = 1; i < 6; ++i) ms[i] = 0.0f;
-        CU(c, cudaEventElapsedTime(&ms[0], ev[0], ev[1]));
+    if (c->nlanes > 1) {                                     // pipelined contexts time the moments kernel only: its launch clock
+        for (int i = 0; i < 6; ++i) ms[i] = 0.0f;
+        Lane& L = c->lane[c->cur];
+        if (!L.clk) return fail(c, BOD_ERR_STATE, "the last run kept no launch clock");
+        unsigned long long h[2 + 2 * kClkSlots];
+        CU(c, cudaMemcpy(h, L.clk, sizeof h, cudaMemcpyDeviceToHost));
+        if (h[0] == 0) return fail(c, BOD_ERR_STATE, "the last run kept no launch clock");
+        const unsigned long long i = (h[0] - 1) % kClkSlots;
+        if (h[3 + 2 * i] > h[2 + 2 * i]) ms[0] = (float)((double)(h[3 + 2 * i] - h[2 + 2 * i]) * 1e-6);
         return BOD_OK;
     }
+    if (!c->last_timed || c->runs_recorded == 0) return fail(c, BOD_ERR_STATE, "the last run recorded no stage events");
+    cudaEvent_t* ev = c->evring[(c->runs_recorded - 1) % bod_ctx::kEvRing];
     for (int i = 0; i < 5; ++i) CU(c, cudaEventElapsedTime(&ms[i], ev[i == 3 ? 6 : i], ev[i + 1]));
     CU(c, cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
     return BOD_OK;
@@ -1063,11 +1099,13 @@ extern "C" int bod_stage_ms_accum(bod_ctx* c, float sum_ms[6], int32_t* runs) {
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->last_stream));
     { int rc0 = drain_tails(c); if (rc0) return rc0; }      // earlier runs' tails live on other streams
-    // graph replays (pipelined contexts) time their moments kernel only; the other stages read as zero there
-    for (int l = 0; l < c->nlanes; ++l) harvest_k1_time(c, c->lane[l]);
-    if (c->g_k1_runs > 0) {
-        sum_ms[0] = (float)c->g_k1_ms; *runs = (int32_t)c->g_k1_runs;
-        c->g_k1_ms = 0.0; c->g_k1_runs = 0;
+    if (c->nlanes > 1) {
+        // pipelined contexts time the moments kernel only (its launch clock, see K1Args::clk: the last 64 launches of
+        // every lane at most); the other stages read as zero there
+        double sum = 0.0;
+        long long n = 0;
+        for (int l = 0; l < c->nlanes; ++l) { int rc0 = fold_launch_clock(c, c->lane[l], &sum, &n); if (rc0) return rc0; }
+        sum_ms[0] = (float)sum; *runs = (int32_t)n;
         c->runs_reported = c->runs_recorded;
         return BOD_OK;
     }
@@ -1076,15 +1114,27 @@ extern "C" int bod_stage_ms_accum(bod_ctx* c, float sum_ms[6], int32_t* runs) {
     for (long long r = first; r < c->runs_recorded; ++r) {
         cudaEvent_t* ev = c->evring[r % bod_ctx::kEvRing];
         float ms = 0.0f;
-        if (c->nlanes > 1) {                                 // pipelined contexts time the moments kernel only
-            CU(c, cudaEventElapsedTime(&ms, ev[0], ev[1])); sum_ms[0] += ms;
-        } else {
-            for (int i = 0; i < 5; ++i) { CU(c, cudaEventElapsedTime(&ms, ev[i == 3 ? 6 : i], ev[i + 1])); sum_ms[i] += ms; }
-            CU(c, cudaEventElapsedTime(&ms, ev[0], ev[5])); sum_ms[5] += ms;
-        }
+        for (int i = 0; i < 5; ++i) { CU(c, cudaEventElapsedTime(&ms, ev[i == 3 ? 6 : i], ev[i + 1])); sum_ms[i] += ms; }
+        CU(c, cudaEventElapsedTime(&ms, ev[0], ev[5])); sum_ms[5] += ms;
         ++*runs;
     }
     c->runs_reported = c->runs_recorded;
+    return BOD_OK;
+}
+
+// Device-clock durations of the moments-kernel launches since the previous call (any context; the last 64 launches of
+// every lane at most): what bod_stage_ms_accum reports as stage 0 of a pipelined context, available beside the CUDA
+// events of a serial one (tests compare the two).
+extern "C" int bod_moments_clock_accum(bod_ctx* c, double* sum_ms, int32_t* runs) {
+    if (!c || !sum_ms || !runs) return BOD_ERR_INVALID;
+    *sum_ms = 0.0; *runs = 0;
+    if (!c->ran) return BOD_OK;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->last_stream));
+    { int rc0 = drain_tails(c); if (rc0) return rc0; }
+    long long n = 0;
+    for (int l = 0; l < c->nlanes; ++l) { int rc0 = fold_launch_clock(c, c->lane[l], sum_ms, &n); if (rc0) return rc0; }
+    *runs = (int32_t)n;
     return BOD_OK;
 }
 

@@ -25,6 +25,27 @@ constexpr int kPendStride = 8;      // 32-bit words of soft-NMS scratch per cand
 // correctly rounded binary32 exp / log (via binary64; 1 ulp of binary64 error
 // leaves the binary32 rounding unchanged except with probability ~2^-28)
 // ---------------------------------------------------------------------------
+// ---- diagnostic builds (-DBOD_DIAGNOSTICS): a kernel's place on the device timeline ----
+// tl[0] = start of CTA (0,0), tl[1] = start of the CTA placed last, tl[2] = end of the CTA that ended last
+// (%globaltimer, ns).  The guard object stamps the end wherever the kernel returns.
+#ifdef BOD_DIAGNOSTICS
+struct TimelineStamp {
+    unsigned long long* tl;
+    static __device__ __forceinline__ unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+    __device__ __forceinline__ explicit TimelineStamp(unsigned long long* p) : tl(p) {
+        if (tl && threadIdx.x == 0) {
+            const unsigned long long t = now();
+            if (blockIdx.x == 0 && blockIdx.y == 0) tl[0] = t;
+            atomicMax(tl + 1, t);
+        }
+    }
+    __device__ __forceinline__ ~TimelineStamp() { if (tl && threadIdx.x == 0) atomicMax(tl + 2, now()); }
+};
+#define BOD_TIMELINE(ptr) TimelineStamp timeline_stamp_(ptr)
+#else
+#define BOD_TIMELINE(ptr)
+#endif
+
 BOD_DEVINL float exp_cr(float x) { return (float)exp((double)x); }
 BOD_DEVINL float log_cr(float x) { return (float)log((double)x); }
 

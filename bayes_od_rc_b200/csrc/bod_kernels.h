@@ -46,6 +46,7 @@ inline int sm_count() {
 // level l covers the global anchors [first_anchor[l], first_anchor[l+1]) and the tiles
 // [first_tile[l], first_tile[l+1]) of the per-image tile grid (tiles never straddle levels).
 constexpr int kMaxLevels = 8;
+constexpr int kClkSlots = 64;            // launches a K1 launch clock remembers
 struct LevelTable {
     int n;
     int first_anchor[kMaxLevels + 1];   // entries >= n: INT_MAX (a level is found by counting entries <= the index)
@@ -77,6 +78,12 @@ struct K1Args {
     int leave_room;          // pipelined context: size the ring so that other stages' CTAs fit beside K1's
     uint32_t* ticket;        // dynamic tile scheduler: global ticket counter (never reset) ...
     uint32_t ticket_base;    // ... and its value when this launch starts
+    unsigned long long* tl;     // BOD_DIAGNOSTICS builds only: the kernel's three timeline stamps (bod_common.cuh), or nullptr
+    // Launch clock (pipelined contexts; nullptr: none): clk[0] = launches so far, clk[2 + 2*(i % 64)] / clk[3 + 2*(i % 64)] =
+    // %globaltimer at the start of CTA 0 / at the end of the CTA that ended last, of launch i.  A launch's duration costs
+    // the host nothing this way; two timing events around the kernel add ~10 us between two short launches (and ~25 us
+    // as event nodes of a graph).
+    unsigned long long* clk;
 };
 // tickets a launch of launch_k1 consumes (tiles + one failing fetch per CTA); 0 for the non-pipelined fallback
 uint32_t k1_tickets_per_launch(const K1Args& a);
@@ -93,6 +100,7 @@ struct ScanArgs {
     int32_t* num_survivors;     // [B]
     int32_t* status;            // [1] sticky error flags
     int B, tiles, capacity;
+    unsigned long long* tl;     // BOD_DIAGNOSTICS builds only: the kernel's three timeline stamps (bod_common.cuh), or nullptr
 };
 cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st, bool beside_k1 = false);
 
@@ -134,6 +142,7 @@ struct K2Args {
     int cov_layout, use_full_covar, dirichlet_prior, gaussian_prior, ranking_method;
     float isotropic_variance, scale_v, scale_u;
     int anchor_mode, im_h, im_w;
+    unsigned long long* tl;     // BOD_DIAGNOSTICS builds only: the kernel's three timeline stamps (bod_common.cuh), or nullptr
 };
 cudaError_t launch_k2(const K2Args& a, cudaStream_t st);
 const void* k2_kernel_func(const K2Args& a);
@@ -168,6 +177,7 @@ struct K3Args {
     int psm_max;                // cap on the pending weights kept in shared memory per candidate (-1: none; tests)
     int seg_cap;                // pairs per warp list segment (-1: the kernel's own; tests shrink it, >= 32, to reach the piecewise path)
     long long* dbg;             // BOD_DIAGNOSTICS builds only: [B][32 warps][12] phase cycle counters, or nullptr
+    unsigned long long* tl;     // BOD_DIAGNOSTICS builds only: the kernel's three timeline stamps (bod_common.cuh), or nullptr
 };
 cudaError_t launch_k3(const K3Args& a, cudaStream_t st);
 
@@ -190,6 +200,7 @@ struct K4Args {
     float calibration, iou_threshold;
     const int32_t* status_in;   // the context's status word ...
     int32_t* status_out;        // ... copied into the lane's result block by the kernel's first thread (or nullptr)
+    unsigned long long* tl;     // BOD_DIAGNOSTICS builds only: the kernel's three timeline stamps (bod_common.cuh), or nullptr
 };
 cudaError_t launch_k4(const K4Args& a, cudaStream_t st);
 

@@ -30,6 +30,7 @@ namespace bod {
 // mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS.*, UBLKCP)
 // ---------------------------------------------------------------------------
 // fast math of the softmax (tolerance-checked output): MUFU.EX2 / MUFU.RCP
+BOD_DEVINL unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 BOD_DEVINL float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 BOD_DEVINL float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -99,6 +100,24 @@ template <int K> struct SoftmaxSum {
         if (K & 1) p[K - 1] = last * scale;
     }
 };
+
+// Launch clock (K1Args::clk): CTA (0,0) opens a slot with its start time, every CTA leaves its end time behind.
+BOD_DEVINL void launch_clock_begin(unsigned long long* clk_) {
+    if (clk_ != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        volatile unsigned long long* clk = clk_;
+        const unsigned long long i = clk[0];
+        clk[2 + 2 * (i % kClkSlots)] = global_ns();
+        clk[3 + 2 * (i % kClkSlots)] = 0ull;
+        __threadfence();
+        clk[0] = i + 1;
+    }
+}
+BOD_DEVINL void launch_clock_end(unsigned long long* clk_) {
+    if (clk_ != nullptr && threadIdx.x == 0) {
+        const unsigned long long i = *reinterpret_cast<volatile unsigned long long*>(clk_) - 1ull;   // CTA (0,0) opened the slot long ago
+        atomicMax(clk_ + 3 + 2 * (i % kClkSlots), global_ns());
+    }
+}
 
 BOD_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 BOD_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
@@ -307,6 +326,7 @@ BOD_DEVINL TileRef tile_ref(const LevelTable& lv, int tile) {
 template <int K, bool USE_BULK>
 __global__ void __launch_bounds__(kTileAnchors, 2)
 k1_moments_kernel(K1Args a, int NC) {
+    launch_clock_begin(a.clk);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
     __shared__ int warp_count[kTileAnchors / 32];
@@ -434,6 +454,7 @@ k1_moments_kernel(K1Args a, int NC) {
         for (int k = 0; k < K; ++k) o[k] = cnt[k];
     }
     if (tid == 0) a.tile_count[(size_t)b * a.tiles + tile] = total;
+    launch_clock_end(a.clk);
 }
 
 // ---------------------------------------------------------------------------
@@ -456,6 +477,8 @@ template <int K, int NSU>
 #endif
 __global__ void __launch_bounds__(kTileAnchors + 32, BOD_K1_MINBLOCKS)
 k1_moments_pipe_kernel(K1Args a, int NS) {
+    BOD_TIMELINE(a.tl);
+    launch_clock_begin(a.clk);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[2 * kMaxStages];         // one array: empty_bar = full_bar + a compile-time offset
     uint64_t* const full_bar = bars;
@@ -639,6 +662,7 @@ k1_moments_pipe_kernel(K1Args a, int NS) {
         }
         if (tid == 0) a.tile_count[(size_t)b * tiles + tile] = total;
     }
+    launch_clock_end(a.clk);
 }
 
 static bool k1_aligned(const K1Args& a) {
@@ -697,6 +721,11 @@ static K1Plan k1_plan(const K1Args& a) {
     const unsigned per_cta = a.leave_room ? (228u * 1024u - 50u * 1024u) / k1_ctas_per_sm() - 1792u
                                           : 216u * 1024u / k1_ctas_per_sm() - 1024u;
     int NS = (int)(per_cta / slab);
+    // Pipelined contexts: at most five slabs (>= 10 KB) in flight per CTA.  A deeper ring makes the kernel faster alone and
+    // the step slower: with K = 4 (2 KB slabs) ten stages stream at 5.1 TB/s alone, but the posterior / soft-NMS kernels
+    // of earlier runs then wait on a saturated memory system while they hold their SMs (KITTI shape, B = 64: 1.00 ms per
+    // step with ten stages, 0.86 ms with five; measured, round 2).
+    if (a.leave_room) { const int cap = (int)(10240 / slab) > 5 ? (int)(10240 / slab) : 5; if (NS > cap) NS = cap; }
     static const int ns_env = getenv("BOD_K1_NS") ? atoi(getenv("BOD_K1_NS")) : 0;                          // experiment: shallower ring
     if (ns_env >= 2 && ns_env < NS) NS = ns_env;
     if (NS > kMaxStages) NS = kMaxStages;

@@ -16,6 +16,7 @@
 // Only the S survivors are gathered: N*(16 + 64|40) bytes each, i.e. the
 // [N,A,4] and [N,A,4,4] tensors are never streamed in full (the reference
 // decodes and reduces them for all A anchors before masking).
+#include <cstdlib>
 #include "bod_common.cuh"
 #include "bod_kernels.h"
 
@@ -25,6 +26,7 @@ namespace bod {
 // K1b: exclusive scan of the per-tile survivor counts of every image
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(ScanArgs a) {
+    BOD_TIMELINE(a.tl);
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -297,6 +299,7 @@ __device__ __constant__ int kPackedOf[16] = {4, -1, -1, -1, 8, 9, -1, -1, 7, 6, 
 template <int K>
 __global__ void __launch_bounds__(kK2Threads, BOD_K2_MINBLOCKS)
 k2_posterior_kernel(K2Args a, AnchorLevels L) {
+    BOD_TIMELINE(a.tl);
     extern __shared__ float sbox[];          // decoded boxes [N][4][kK2Threads]
     __shared__ int chunk_first[129];         // prefix of 128-survivor chunks over the images of the batch
 
@@ -608,6 +611,8 @@ static cudaError_t launch_k2_k(const K2Args& a, const AnchorLevels& L, cudaStrea
             if (dev >= 0 && dev < 64) { occ_N[dev] = a.N; occ_v[dev] = per_sm; }
         }
     }
+    static const int cap_env = getenv("BOD_K2_CTAS") ? atoi(getenv("BOD_K2_CTAS")) : 0;   // experiment: fewer resident CTAs per SM
+    if (cap_env >= 1 && cap_env < per_sm) per_sm = cap_env;
     k2_posterior_kernel<K><<<sms * per_sm, kK2Threads, smem, st>>>(a, L);
     return cudaGetLastError();
 }

@@ -902,6 +902,7 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 k3_softnms_kernel(K3Args a, int pool_bytes) {
+    BOD_TIMELINE(a.tl);
     __shared__ K3Smem sm;
     const int b = blockIdx.x;
     const int S = a.num_survivors[b];

@@ -22,6 +22,7 @@
 // ascending survivor order (one lane per matrix entry walks the chunk), which
 // keeps the result bit-identical to a sequential host loop while the expensive
 // part (the 4x4 inverses, the KL terms) runs 32 wide.
+#include <cstdlib>
 #include "bod_common.cuh"
 #include "bod_kernels.h"
 
@@ -49,16 +50,10 @@ BOD_DEVINL float kl_div_norm(const float (&p)[K], const float (&qk_raw)[K]) {
     return acc;
 }
 
+// one (image, centre) on one warp; st / ml: the warp's staging rows and member index list in shared memory
 template <int K>
-__global__ void __launch_bounds__(kK4Warps * 32, 6)
-k4_fusion_kernel(K4Args a) {
-    __shared__ float stage[kK4Warps][32][21];     // per lane: 16 precision entries + 4 weighted-mean entries (+pad)
-    __shared__ uint32_t mlist[kK4Warps][kK4List]; // ascending member indices of the segment being processed
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int d = blockIdx.x * kK4Warps + warp, b = blockIdx.y;
-    if (a.status_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.status_out = *a.status_in;
-    if (d >= a.Dmax) return;                      // warp-uniform
+BOD_DEVINL void k4_centre(const K4Args& a, const int d, const int b, float (*st)[21], uint32_t* ml) {
+    const int lane = threadIdx.x & 31;
     if (d >= a.num_dets[b]) {                     // padding rows of the result blocks read as zero
         const size_t prow = (size_t)b * a.Dmax + d;
         if (lane < 16) a.out_covs[prow * 16 + lane] = 0.0f;
@@ -73,8 +68,6 @@ k4_fusion_kernel(K4Args a) {
     const float4* mu = reinterpret_cast<const float4*>(a.mu_post) + (size_t)b * a.capacity;
     const float4* sig = reinterpret_cast<const float4*>(a.sig_post) + (size_t)b * a.capacity * 4;
     const int centre = a.nms_idx[(size_t)b * a.Dmax + d];
-    float (*st)[21] = stage[warp];
-    uint32_t* ml = mlist[warp];
 
     // membership row of this centre (:214-215, :316) and the cluster size (the KL ranking is only needed
     // for more than 3 members, :338)
@@ -291,8 +284,28 @@ k4_fusion_kernel(K4Args a) {
     }
 }
 
+// grid = (gx, B): CTA (x, b) takes the centres x*4 + warp, stepping by 4*gx.  One CTA per group of four centres when
+// the kernel has the GPU to itself; BOD_K4_GRIDX (experiments) caps gx, which makes the grid small enough to be placed
+// at once beside the resident moments-kernel CTAs of a pipelined context.
+template <int K>
+__global__ void __launch_bounds__(kK4Warps * 32, 6)
+k4_fusion_kernel(K4Args a) {
+    BOD_TIMELINE(a.tl);
+    __shared__ float stage[kK4Warps][32][21];     // per lane: 16 precision entries + 4 weighted-mean entries (+pad)
+    __shared__ uint32_t mlist[kK4Warps][kK4List]; // ascending member indices of the segment being processed
+    const int warp = threadIdx.x >> 5, b = blockIdx.y;
+    if (a.status_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.status_out = *a.status_in;
+    for (int d = blockIdx.x * kK4Warps + warp; d < a.Dmax; d += gridDim.x * kK4Warps) {   // warp-uniform
+        k4_centre<K>(a, d, b, stage[warp], mlist[warp]);
+        __syncwarp();
+    }
+}
+
 cudaError_t launch_k4(const K4Args& a, cudaStream_t st) {
-    dim3 grid((a.Dmax + kK4Warps - 1) / kK4Warps, a.B), block(kK4Warps * 32);
+    int gx = (a.Dmax + kK4Warps - 1) / kK4Warps;
+    static const int gx_env = getenv("BOD_K4_GRIDX") ? atoi(getenv("BOD_K4_GRIDX")) : 0;
+    if (gx_env >= 1 && gx_env < gx) gx = gx_env;
+    dim3 grid(gx, a.B), block(kK4Warps * 32);
     switch (a.K) {
 #define BOD_CASE(KK) case KK: k4_fusion_kernel<KK><<<grid, block, 0, st>>>(a); break;
         BOD_CASE(2) BOD_CASE(3) BOD_CASE(4) BOD_CASE(5) BOD_CASE(6) BOD_CASE(7) BOD_CASE(8) BOD_CASE(9)

@@ -464,6 +464,14 @@ class BayesODEngine:
         self._check(self.lib.bod_stage_ms_accum(self._ctx, ms, C.byref(runs)))
         return dict(zip(self.STAGES, [float(x) for x in ms])), int(runs.value)
 
+    def moments_clock_accum(self):
+        """(summed milliseconds, launches) of the moments kernel since the previous call, by the kernel's own launch
+        clock (bod_moments_clock_accum)."""
+        ms = C.c_double(0.0)
+        runs = C.c_int32(0)
+        self._check(self.lib.bod_moments_clock_accum(self._ctx, C.byref(ms), C.byref(runs)))
+        return float(ms.value), int(runs.value)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.bod_last_launch_count(self._ctx))

@@ -374,7 +374,9 @@ def main():
         k1_bytes = 4.0 * N * A * K * B            # algorithmic bytes of ONE K1 launch: the [B,N,A,K] logits, read once
         achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
         traffic = None                            # dram bytes of one K1 launch from the committed ncu --set full capture
-        tp = os.path.join(ROOT, "profiles", "k1_traffic_r1.json")
+        tp = os.path.join(ROOT, "profiles", "k1_traffic_r2.json")
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, "profiles", "k1_traffic_r1.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 tj = json.load(f)
@@ -401,7 +403,13 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k1_moments_pipe_kernel", "achieved": round(achieved, 1) if achieved else None,
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": round(k1_ms, 4)},
+                         "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": round(k1_ms, 4),
+                         "launches_timed": int(stage_runs),
+                         "timer": ("the kernel's own launch clock (%globaltimer at the start of its first CTA and at the end of "
+                                   "its last one), every launch of the timed region that the per-lane 64-slot clocks still hold; "
+                                   "CUDA events around a kernel of a pipelined context would put ~10 us between two launches. "
+                                   "tests/test_gpu_parity.py::test_moments_launch_clock_agrees_with_cuda_events checks it against "
+                                   "CUDA events on a serial context") if args.pipeline > 1 else "CUDA events on the launching stream"},
             "clocks": sampler.summary(t0, t1),
         }
         if verification is not None:

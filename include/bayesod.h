@@ -313,9 +313,10 @@ int bod_synchronize(bod_ctx* ctx);
 /* Device-time of the last run per stage in milliseconds (events recorded on the
  * run's stream): [0]=moments/filter, [1]=scan, [2]=posterior, [3]=soft-NMS,
  * [4]=fusion, [5]=total.  Syncs on the run.  Pipelined contexts (pipeline_depth
- * > 1) time the moments kernel only: [1..5] read as zero there (the stages of
- * consecutive runs overlap, and the event records of a one-image run are a
- * visible share of its host time). */
+ * > 1) time the moments kernel only, with the kernel's own launch clock (see
+ * bod_moments_clock_accum): [1..5] read as zero there (the stages of
+ * consecutive runs overlap, and event records cost a one-image run a visible
+ * share of its host time). */
 int bod_last_stage_ms(bod_ctx* ctx, float ms[6]);
 /* Stage events are recorded by default (6 cudaEventRecord per run); switch them
  * off for latency-critical callers. */
@@ -324,6 +325,13 @@ int bod_set_stage_timing(bod_ctx* ctx, int enabled);
  * runs issued since the previous call (at most the last 128), and how many runs
  * that was.  Syncs on the last run. */
 int bod_stage_ms_accum(bod_ctx* ctx, float sum_ms[6], int32_t* runs);
+/* Sum of the device-clock durations (%globaltimer: start of the first CTA to the
+ * end of the last one, written by the kernel itself) of the moments-kernel
+ * launches since the previous call -- at most the last 64 per lane -- and how
+ * many launches that was.  This is what stage [0] of a pipelined context is
+ * measured with (timing events around a kernel cost ~10 us between two short
+ * launches); serial contexts have it beside their CUDA events.  Syncs. */
+int bod_moments_clock_accum(bod_ctx* ctx, double* sum_ms, int32_t* runs);
 /* Number of kernels the last bod_run launched. */
 int bod_last_launch_count(const bod_ctx* ctx);
 

@@ -479,6 +479,27 @@ def test_softmax_rows_far_apart(K, N):
         assert_bit_equal(c, oracle.philox_counts(p, 30, 3, 11 + b), "philox counts")
 
 
+@pytest.mark.parametrize("hw", [(320, 512), (384, 640)], ids=["pipeline_kernel", "unaligned_fallback_kernel"])
+def test_moments_launch_clock_agrees_with_cuda_events(hw):
+    """Pipelined contexts time the moments kernel with its own launch clock (%globaltimer stamps of the first CTA's start
+    and the last CTA's end) instead of CUDA events; on a serial context both are available and have to agree.
+    320x512 has 30 708 anchors (rows 16-byte aligned: the bulk-copy pipeline kernel), 384x640 has 46 035 (the fallback)."""
+    spec = synthetic.SceneSpec(im_h=hw[0], im_w=hw[1], N=10, K=11, g_min=4, g_max=6, config_id=5)
+    batch = synthetic.to_numpy(synthetic.make_batch(spec, 4, with_counts=False))
+    oc = oracle.OracleConfig(seed=1)
+    eng, _ = run_gpu_batch(oc, batch["cls"], batch["box"], batch["cov"], batch["anchors"], None, emit_probs=False)
+    import torch
+    dev = [torch.from_numpy(batch[k]).cuda() for k in ("cls", "box", "cov", "anchors")]
+    eng.stage_ms_accum(); eng.moments_clock_accum()
+    for _ in range(12):
+        eng.run(*dev, None)
+    ev, n_ev = eng.stage_ms_accum()
+    clk, n_clk = eng.moments_clock_accum()
+    assert n_ev == 12 and n_clk == 12
+    ev_ms, clk_ms = ev["moments_filter"] / n_ev, clk / n_clk
+    assert clk_ms > 0 and abs(ev_ms - clk_ms) <= 0.15 * ev_ms + 0.004, (ev_ms, clk_ms)   # events bracket launch latency too
+
+
 def test_sampler_fast_path_equals_full_counts():
     """Without emit_probs the sampler skips the per-class draws of background-majority anchors;
     the survivors and everything downstream must not change."""
