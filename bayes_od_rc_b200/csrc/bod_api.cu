@@ -161,7 +161,9 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
     if (cfg->B < 1 || cfg->B > 128) return bad("B must be in [1,128]");
     if (cfg->N < 1) return bad("N (mc_dropout_samples) must be >= 1");
     if (cfg->A < 1) return bad("A must be positive");
-    if (!k1_supports(cfg->K)) return bad("unsupported K (classes + background)");
+    if (!k1_supports(cfg->K))
+        return bad("unsupported K (classes + background): the kernels are instantiated for K = 2..13, 16, 21 and 32 -- BDD (11), KITTI (4 / 8), "
+                   "Pascal VOC (21); COCO's 81 columns are not (one thread holds an anchor's K probabilities in registers)");
     if (cfg->max_output_size < 1 || cfg->max_output_size > 255) return bad("max_output_size must be in [1,255]");
     if (cfg->cov_layout < 0 || cfg->cov_layout > 2) return bad("bad cov_layout");
     if (!(cfg->iou_threshold >= 0.0f)) return bad("iou_threshold must be >= 0");

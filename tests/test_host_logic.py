@@ -86,7 +86,7 @@ def test_create_rejects_bad_configs_before_touching_the_device():
             lib.bod_destroy(ctx)
         return rc, (lib.bod_last_error(None) or b"").decode()
 
-    for kw, what in [(dict(B=0), "B must"), (dict(N=0), "N (mc"), (dict(K=1), "unsupported K"), (dict(K=14), "unsupported K"),
+    for kw, what in [(dict(B=0), "B must"), (dict(N=0), "N (mc"), (dict(K=1), "unsupported K"), (dict(K=14), "unsupported K"), (dict(K=81), "COCO"),
                      (dict(max_output_size=0), "max_output_size"), (dict(max_output_size=256), "max_output_size"),
                      (dict(iou_threshold=-0.1), "iou_threshold"), (dict(soft_nms_sigma=-1.0), "soft_nms_sigma"),
                      (dict(num_draws=0), "num_draws"), (dict(pre_nms_top_k=-1), "pre_nms_top_k"),
