@@ -99,6 +99,7 @@ SYMBOLS = {
     "bod_fetch_probs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "bod_fetch_sampled_counts": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "bod_synchronize": (C.c_int, [C.c_void_p]),
+    "bod_set_input_hold": (C.c_int, [C.c_void_p, C.c_int]),
     "bod_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bod_moments_clock_accum": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "bod_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -83,8 +83,9 @@ struct bod_ctx {
     // device staging of host inputs (bod_run_host), allocated on first use
     float* in_cls = nullptr; float* in_box = nullptr; float* in_cov = nullptr; float* in_anchors = nullptr; float* in_counts = nullptr;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
-    cudaStream_t own_stream2 = nullptr;   // second head stream (BOD_HEADS=2): see issue_run
+    cudaStream_t head_a = nullptr, head_b = nullptr;   // the two head streams of short runs with held inputs (bod_set_input_hold)
     int head_flip = 0;
+    bool hold_inputs = false;
     cudaStream_t last_stream = nullptr;
     cudaEvent_t ev_in = nullptr;
     // stage-timing events: a ring of the last kEvRing runs, 7 events each
@@ -280,17 +281,13 @@ extern "C" int bod_create(bod_ctx** out, int device, const bod_config* cfg) {
         L.nms_score = reinterpret_cast<float*>(b + c->block_off[8]); L.block_status = reinterpret_cast<int32_t*>(b + c->block_off[9]);
     }
     cudaMemset(c->slab, 0, off);
-    {
-        const char* e = getenv("BOD_HEADS");
-        if (e && atoi(e) == 2 && c->nlanes > 1) {
-            // two head streams of different priority: the next run's moments kernel is queued while the current one
-            // still runs and its CTAs move in as the current one's retire; the priorities keep the block scheduler
-            // from interleaving two grids that become eligible at the same moment
-            cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, -1);
-            cudaStreamCreateWithPriority(&c->own_stream2, cudaStreamNonBlocking, 0);
-        } else {
-            cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
-        }
+    cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (c->nlanes > 1) {
+        // two more head streams, of different priority, for short runs with held inputs (bod_set_input_hold): the next
+        // run's moments kernel is queued while the current one still runs, and its CTAs move in as the current one's
+        // retire; the priorities break the tie when two grids become eligible at the same moment
+        cudaStreamCreateWithPriority(&c->head_a, cudaStreamNonBlocking, -1);
+        cudaStreamCreateWithPriority(&c->head_b, cudaStreamNonBlocking, 0);
     }
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     {
@@ -340,7 +337,8 @@ extern "C" void bod_destroy(bod_ctx* c) {
     if (c->slab) cudaFree(c->slab);
     for (float* p : {c->in_cls, c->in_box, c->in_cov, c->in_anchors, c->in_counts}) if (p) cudaFree(p);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
-    if (c->own_stream2) cudaStreamDestroy(c->own_stream2);
+    if (c->head_a) cudaStreamDestroy(c->head_a);
+    if (c->head_b) cudaStreamDestroy(c->head_b);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto& L : c->lane) if (L.tail_stream) cudaStreamDestroy(L.tail_stream);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
@@ -709,7 +707,10 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
             // 20-25 %.)  With graphs the first run of a lane goes through the streams: one-time kernel attributes and
             // tables are set up there, and its head has to follow the previous lane's, which may have been a replay.
             cudaStream_t hs = c->own_stream;
-            if (c->own_stream2 && !graphs && (c->head_flip ^= 1)) hs = c->own_stream2;
+            // (not with emit_probs: the probability / sampled-count planes are per context, two moments kernels in
+            // flight would both write them)
+            if (c->hold_inputs && !graphs && c->head_a && c->head_b && !c->probs && !c->sampled)
+                hs = (c->head_flip ^= 1) ? c->head_b : c->head_a;
             CU(c, cudaStreamWaitEvent(hs, c->ev_in, 0));
             if (graphs) {
                 const Lane& P = c->lane[(c->cur + c->nlanes - 1) % c->nlanes];
@@ -722,7 +723,9 @@ static int issue_run(bod_ctx* c, const LevelTable& lv, const float* anchors, con
             if (rc) return rc;
         }
         ++L.uses;
-        CU(c, cudaStreamWaitEvent(st, L.head_done, 0));
+        // (held inputs, bod_set_input_hold: the caller's stream is not made to wait for the head, so consecutive runs
+        // issued from one stream do not depend on each other through it)
+        if (!c->hold_inputs) CU(c, cudaStreamWaitEvent(st, L.head_done, 0));
         c->last_stream = L.tail_stream;
     }
     c->lane[c->cur].ticket = ++c->next_ticket;
@@ -770,6 +773,12 @@ extern "C" int bod_set_image_scale(bod_ctx* c, float scale_v, float scale_u) {
     if (!c) return BOD_ERR_INVALID;
     if (!(scale_v > 0.0f) || !(scale_u > 0.0f)) return fail(c, BOD_ERR_INVALID, "scale factors must be positive");
     c->cfg.scale_v = scale_v; c->cfg.scale_u = scale_u;
+    return BOD_OK;
+}
+
+extern "C" int bod_set_input_hold(bod_ctx* c, int enabled) {
+    if (!c) return BOD_ERR_INVALID;
+    c->hold_inputs = enabled != 0;
     return BOD_OK;
 }
 

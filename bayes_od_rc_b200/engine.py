@@ -295,6 +295,11 @@ class BayesODEngine:
         """Philox stream of the next runs: image b draws from (seed, image_id_base + b, anchor)."""
         self._check(self.lib.bod_set_sampler_stream(self._ctx, int(seed), int(image_id_base) & 0xFFFFFFFF))
 
+    def set_input_hold(self, enabled: bool = True):
+        """Promise (pipelined contexts) that every input of a run stays untouched until its results are complete; runs
+        then do not wait for each other through the caller's stream (bod_set_input_hold)."""
+        self._check(self.lib.bod_set_input_hold(self._ctx, 1 if enabled else 0))
+
     def set_image_scale(self, scale_v: float, scale_u: float):
         """KITTI rescale factors of the next runs (inference_utils.py:147-167)."""
         self._check(self.lib.bod_set_image_scale(self._ctx, float(scale_v), float(scale_u)))

@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-verify", action="store_true", help="skip the bit-for-bit check of timed results against the oracle")
+    ap.add_argument("--no-input-hold", action="store_true", help="do not declare the inputs held (bod_set_input_hold)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (global batch split over the GPUs)")
     ap.add_argument("--no-stream-fetch", action="store_true", help="do not copy every step's result blocks to the host")
     args = ap.parse_args()
@@ -229,6 +230,8 @@ def main():
                         max_survivors=min(A, 32768), pipeline_depth=args.pipeline,
                         score_threshold=wl.get("score_threshold", float("-inf")), pre_nms_top_k=wl.get("pre_nms_top_k", 0))
     eng = BayesODEngine(B, N, A, K, cfg, device=local_rank)
+    if args.pipeline > 1 and not args.no_input_hold:
+        eng.set_input_hold(True)                # the input tensors of a step are never overwritten here (see config.inputs)
     stream = torch.cuda.Stream(device=dev)
 
     def barrier():
@@ -319,6 +322,8 @@ def main():
         import dataclasses
         lanes_s = default_lanes(Bg)
         eng_s = BayesODEngine(Bg, N, A, K, dataclasses.replace(cfg, image_id_base=first_s, pipeline_depth=lanes_s), device=local_rank)
+        if not args.no_input_hold:
+            eng_s.set_input_hold(True)
 
         def step_s():
             eng_s.run(sb["cls"], sb["box"], sb["cov"], sb["anchors"], None, stream=stream.cuda_stream)
@@ -401,6 +406,10 @@ def main():
                        "images_per_gpu": B, "global_batch": B * world, "parallelism": f"image-shard x{world}, no collective",
                        "l2": "inputs (%.2f GB per step) larger than L2" % ((cls.numel() + box.numel() + cov.numel()) * 4 / 1e9),
                        "pipeline_depth": args.pipeline,
+                       "inputs": ("resident in HBM, never overwritten: held until each run's results are complete "
+                                  "(bod_set_input_hold), so consecutive steps do not depend on each other through the "
+                                  "caller's stream") if (args.pipeline > 1 and not args.no_input_hold) else
+                                 "resident in HBM; the caller's stream waits for each run's logits to be consumed",
                        "results": ("every step's padded result blocks copied to pinned host memory behind its tail "
                                    f"(bod_fetch_async, {d2h_stream} bytes per step)") if stream_fetch else "left on the device",
                        "mean_survivors": round(S_mean, 1), "mean_dets": round(D_mean, 1),

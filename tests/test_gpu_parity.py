@@ -256,9 +256,10 @@ def test_pipelined_runs_equal_serial_runs(depth):
         assert_bit_equal(getattr(res, k), getattr(serial[2], k), f"host entry: {k}")
 
 
+@pytest.mark.parametrize("hold", [False, True], ids=["caller_waits", "inputs_held"])
 @pytest.mark.parametrize("graphs", ["2", "0"])
 @pytest.mark.parametrize("depth", [1, 2, 4])
-def test_streaming_retrieval_of_every_run(depth, graphs, monkeypatch):
+def test_streaming_retrieval_of_every_run(depth, graphs, hold, monkeypatch):
     """bod_fetch_async / bod_ticket_wait: a stream of different batches through one (pipelined) context, every
     run's result blocks copied out behind its own tail while later runs keep streaming; device results of run i
     survive the issue of runs i+1 .. i+L-1 (fetched oldest first after L back-to-back runs); tickets older than
@@ -276,6 +277,8 @@ def test_streaming_retrieval_of_every_run(depth, graphs, monkeypatch):
     serial = [run_gpu_batch(oc, b["cls"], b["box"], b["cov"], b["anchors"], b["counts"], emit_probs=False)[1] for b in batches]
     N, A, K = batches[0]["cls"].shape[1:]
     eng = BayesODEngine(B, N, A, K, engine_config_from_oracle(oc, pipeline_depth=depth))
+    if hold:        # every run has its own input tensors below and they live to the end of the test: heads of short runs
+        eng.set_input_hold(True)   # alternate between two streams and the caller's stream is left alone (bod_set_input_hold)
     dev = [{k: torch.from_numpy(b[k]).cuda() for k in ("cls", "box", "cov", "anchors", "counts")} for b in batches]
     torch.cuda.synchronize()
     st = torch.cuda.Stream()
