@@ -17,6 +17,11 @@ PY
 for tool in memcheck racecheck initcheck synccheck; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitize_${tool}_smoke.log 2>&1
   echo "$tool smoke: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|smoke ok' gpurun_out/sanitize_${tool}_smoke.log | tr '\n' ' ')"
+  if [ "${SAN_ONLY:-}" != "pdq" ] && [ "$tool" != "initcheck" ]; then   # pipelined / graph-replay / held-input path (round 2)
+    timeout 600 compute-sanitizer --tool $tool --print-limit 20 python scripts/san_stream.py > gpurun_out/sanitize_${tool}_stream.log 2>&1
+    echo "$tool stream: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|stream ok' gpurun_out/sanitize_${tool}_stream.log | tr '\n' ' ')"
+  fi
+  [ "${SAN_SKIP_PDQ:-}" = "1" ] && continue
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_pdq.py > gpurun_out/sanitize_${tool}_pdq.log 2>&1
   echo "$tool pdq: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|pdq ok' gpurun_out/sanitize_${tool}_pdq.log | tr '\n' ' ')"
 done
