@@ -327,6 +327,11 @@ BOD_DEVINL int ent_pairs(uint32_t e) { return (int)((e >> 14) & 63u); }
 #ifdef BOD_DIAGNOSTICS
 __device__ unsigned long long g_k3_cnt[8];     // 0 walks, 1 bounded (lazy) walks, 2 untouched, 3 products, 4 product entries, 5 folds, 6 woken
 #endif
+#if defined(BOD_DIAGNOSTICS) && (BOD_DIAGNOSTICS + 0) < 2   // timers-only builds: why a round's batch ended, in the otherwise unused slots
+#define K3_WHY(i) do { if (lane == 0) atomicAdd(&g_k3_cnt[i], 1ull); } while (0)   // (one atomic per round): [0] a candidate outside the examined
+#else                                                        // 32 may come first, [1] pending list too long for the loop, [2] batch / output full, [3] rounds
+#define K3_WHY(i)
+#endif
 #if defined(BOD_DIAGNOSTICS) && (BOD_DIAGNOSTICS + 0) >= 2   // event counters (global atomics: they cost a third of the kernel's time);
 #define K3_CNT(i, v) atomicAdd(&g_k3_cnt[i], (unsigned long long)(v))   // -DBOD_DIAGNOSTICS alone keeps the phase timers only
 #else
@@ -653,7 +658,7 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
 #pragma unroll 1
             while (m < kBatch && r + m < Dmax) {
                 const uint32_t mh = __reduce_max_sync(0xffffffffu, hu);
-                if (mh == 0u || mh < Gbh) break;
+                if (mh == 0u || mh < Gbh) { K3_WHY(0); break; }
                 uint32_t bal = __ballot_sync(0xffffffffu, hu == mh);
                 if (bal & (bal - 1u)) {                                  // equal scores: the lower index comes first
                     const uint32_t ml = __reduce_max_sync(0xffffffffu, hu == mh ? lo : 0u);
@@ -661,7 +666,7 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
                 }
                 const int L = __ffs(bal) - 1;
                 const uint32_t ll = __shfl_sync(0xffffffffu, lo, L);
-                if (mh == Gbh && ll < Gbl) break;
+                if (mh == Gbh && ll < Gbl) { K3_WHY(0); break; }
                 K3_CNT(2, lane == 0);
                 bool stop = false;
                 if (lane == L) {                                         // selection r + m
@@ -695,8 +700,10 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
                     }
                 }
                 ++m; lowest = fminf(lowest, key_score((unsigned long long)mh << 32));
-                if (__any_sync(0xffffffffu, stop)) break;
+                if (__any_sync(0xffffffffu, stop)) { K3_WHY(1); break; }
             }
+            if (!(m < kBatch && r + m < Dmax)) K3_WHY(2);
+            K3_WHY(3);
             if (lane == 0) {
                 // laziness threshold of the round's passes: a fixed fraction below the lowest score examined or selected
                 if (nvalid > 0) {
