@@ -190,7 +190,10 @@ __device__ void k3_generic(const K3Args& a, int b, unsigned long long (*warp_bes
 // ---------------------------------------------------------------------------
 constexpr int kTop = 32;              // candidates examined per round (one per lane of the acceptance warp)
 constexpr int kBatch = 31;            // centres selected per round at most (a bit per centre in a 32-bit mask + the wake bit)
-constexpr float kTauFrac = 0.97f;     // scores below this fraction of the lowest examined score are kept as upper bounds
+#ifndef BOD_K3_TAU
+#define BOD_K3_TAU 0.97f
+#endif
+constexpr float kTauFrac = BOD_K3_TAU;     // scores below this fraction of the lowest examined score are kept as upper bounds
 constexpr int kStateBytes = 25;       // shared memory per candidate besides its pending weights: corners, two scores, a count
 constexpr int kSimOld = 32;           // pending weights of an examined candidate the batch loop can multiply in itself
 constexpr int kListed = 128;          // keys listed per round by all warps together
@@ -201,6 +204,9 @@ struct K3Smem {
     unsigned long long warp_best[2][32];         // generic kernel scratch
     unsigned long long top_flat[kListed];        // per-warp top keys (descending, 0 = none): warp w at [w * kTop1, (w+1) * kTop1)
     unsigned long long bound_w[32];              // every key of the warp that is not listed is below this (0: there is none)
+#ifdef BOD_DIAGNOSTICS
+    int bound_kind[32];                          // what bound_w is: 0 the warp's last listed key, 1 a cut (a thread ran out of tracked keys), 2 a lazy bound
+#endif
     unsigned long long sel_key[kMaxOut];         // key (score, -index) of every selected centre
     float4 sel_box[kMaxOut];
     unsigned long long cand_key[kTop];           // the round's examined candidates ...
@@ -328,8 +334,10 @@ BOD_DEVINL int ent_pairs(uint32_t e) { return (int)((e >> 14) & 63u); }
 __device__ unsigned long long g_k3_cnt[8];     // 0 walks, 1 bounded (lazy) walks, 2 untouched, 3 products, 4 product entries, 5 folds, 6 woken
 #endif
 #if defined(BOD_DIAGNOSTICS) && (BOD_DIAGNOSTICS + 0) < 2   // timers-only builds: why a round's batch ended, in the otherwise unused slots
+#define K3_GB_SLOT (gb_is_next ? 0 : 4 + gb_kind)
 #define K3_WHY(i) do { if (lane == 0) atomicAdd(&g_k3_cnt[i], 1ull); } while (0)   // (one atomic per round): [0] a candidate outside the examined
 #else                                                        // 32 may come first, [1] pending list too long for the loop, [2] batch / output full, [3] rounds
+#define K3_GB_SLOT 0
 #define K3_WHY(i)
 #endif
 #if defined(BOD_DIAGNOSTICS) && (BOD_DIAGNOSTICS + 0) >= 2   // event counters (global atomics: they cost a third of the kernel's time);
@@ -547,6 +555,9 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
             // a candidate whose score is only an upper bound is never examined, and nothing below its bound is
             const unsigned long long ixw = warp_max_u64(ixmax);
             if (lane == 0) sm.bound_w[warp] = bound > ixw ? bound : ixw;
+#ifdef BOD_DIAGNOSTICS
+            if (lane == 0) sm.bound_kind[warp] = ixw > bound ? 2 : (bound == out[kTop1 - 1] ? 0 : 1);
+#endif
         }
         if (tid < kTop) { sm.cand_key[tid] = 0ull; sm.rowmask[tid] = 0u; }     // filled by the acceptance phases below
         if (tid < kListed) sm.rank_cnt[tid] = 0;
@@ -632,6 +643,12 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
             const int nvalid = __popc(__ballot_sync(0xffffffffu, myk != 0ull));      // candidates are a prefix
             unsigned long long Gb = warp_max_u64((lane < W) ? sm.bound_w[lane] : 0ull);
             const bool any_bound = Gb != 0ull;
+#if defined(BOD_DIAGNOSTICS) && (BOD_DIAGNOSTICS + 0) < 2
+            const bool gb_is_next = sm.next_key > Gb;         // the bound is the best listed key that was not examined; else slot 4 + kind of the binding warp bound
+            int gb_kind = 0;
+            { const unsigned bw = __ballot_sync(0xffffffffu, lane < W && sm.bound_w[lane] == Gb && Gb != 0ull);
+              if (bw) gb_kind = sm.bound_kind[__ffs(bw) - 1]; }
+#endif
             { const unsigned long long nk = sm.next_key; Gb = nk > Gb ? nk : Gb; }
             const int x = key_index(myk);
             const int si = (myk != 0ull) ? row_of(x) : 0;
@@ -658,7 +675,7 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
 #pragma unroll 1
             while (m < kBatch && r + m < Dmax) {
                 const uint32_t mh = __reduce_max_sync(0xffffffffu, hu);
-                if (mh == 0u || mh < Gbh) { K3_WHY(0); break; }
+                if (mh == 0u || mh < Gbh) { K3_WHY(K3_GB_SLOT); break; }
                 uint32_t bal = __ballot_sync(0xffffffffu, hu == mh);
                 if (bal & (bal - 1u)) {                                  // equal scores: the lower index comes first
                     const uint32_t ml = __reduce_max_sync(0xffffffffu, hu == mh ? lo : 0u);
@@ -666,7 +683,7 @@ BOD_DEVINL void k3_rounds(const K3Args& a, const int pool_bytes, K3Smem& sm, con
                 }
                 const int L = __ffs(bal) - 1;
                 const uint32_t ll = __shfl_sync(0xffffffffu, lo, L);
-                if (mh == Gbh && ll < Gbl) { K3_WHY(0); break; }
+                if (mh == Gbh && ll < Gbl) { K3_WHY(K3_GB_SLOT); break; }
                 K3_CNT(2, lane == 0);
                 bool stop = false;
                 if (lane == L) {                                         // selection r + m
