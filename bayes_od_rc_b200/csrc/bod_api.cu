@@ -662,7 +662,7 @@ static int replay_run(bod_ctx* c, Lane& L, const LevelTable& lv, const float* an
     }
     CU(c, cudaEventRecord(L.tail_done, ls));
     L.tail_pending = true;
-    c->launches = 6;            // ticket reset, moments, scan, posterior, soft-NMS, fusion
+    c->launches = 5;            // moments, scan, posterior, soft-NMS, fusion (the moments kernel puts its ticket counter back itself)
     return BOD_OK;
 }
 
